@@ -1,0 +1,347 @@
+"""Python harness over the C ABI, named after the reference's interface for this path so the
+parity tests read like the reference's own tests (util.h, config.h, loss.h, training.h).
+Everything computes inside libcu2b.so; numpy only carries the buffers."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import Config as _CConfig, Csr, Metrics, Rating, Stats, check
+
+RATING_DTYPE = np.dtype([("user", np.int32), ("item", np.int32), ("rating", np.float32)])
+
+MODE_HOGWILD, MODE_DETERMINISTIC = 0, 1
+SAMPLER_PER_USER, SAMPLER_PER_RATING = 0, 1
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+# ------------------------------------------------------------------------------------------
+# config::Config (config.h:20-58)
+# ------------------------------------------------------------------------------------------
+class Config:
+    """Mirror of config::Config. Attribute names are the reference's field names."""
+
+    def __init__(self, **kw):
+        self.c = _CConfig()
+        _lib.load().cu2b_config_default(C.byref(self.c))
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+    def __getattr__(self, name):
+        c = object.__getattribute__(self, "c")
+        if name in dict(_CConfig._fields_):
+            return getattr(c, name)
+        raise AttributeError(name)
+
+    def __setattr__(self, name, value):
+        if name == "c":
+            object.__setattr__(self, name, value)
+        elif name in dict(_CConfig._fields_):
+            setattr(self.c, name, value)
+        else:
+            raise AttributeError(name)
+
+    def read_config(self, path):  # config.cu:7-13
+        check(_lib.load().cu2b_config_read(str(path).encode(), C.byref(self.c)))
+        return True
+
+    def write_config(self, path):  # config.cu:15-22
+        check(_lib.load().cu2b_config_write(str(path).encode(), C.byref(self.c)))
+        return True
+
+    def format(self):  # config.cu:50-64 print_config text
+        buf = C.create_string_buffer(1024)
+        _lib.load().cu2b_config_format(C.byref(self.c), buf, 1024)
+        return buf.value.decode()
+
+    def print_config(self):
+        print(self.format(), end="")
+
+    def copy(self):
+        other = Config()
+        C.memmove(C.byref(other.c), C.byref(self.c), C.sizeof(_CConfig))
+        return other
+
+
+# ------------------------------------------------------------------------------------------
+# util.h
+# ------------------------------------------------------------------------------------------
+def readCSV(path):
+    """util.cu:17-45 -> (ratings[RATING_DTYPE], rows, cols, global_bias)."""
+    lib = _lib.load()
+    p = C.POINTER(Rating)()
+    n = C.c_int64()
+    rows, cols, gb = C.c_int(), C.c_int(), C.c_float()
+    check(lib.cu2b_read_csv(str(path).encode(), C.byref(p), C.byref(n), C.byref(rows), C.byref(cols), C.byref(gb)))
+    try:
+        out = np.empty(n.value, dtype=RATING_DTYPE)
+        if n.value:
+            C.memmove(out.ctypes.data, p, n.value * RATING_DTYPE.itemsize)
+    finally:
+        lib.cu2b_free(p)
+    return out, rows.value, cols.value, np.float32(gb.value)
+
+
+@dataclass
+class CSRMatrix:
+    """Host-side CSR view (matrix.h:11-19); the device copy lives inside a session."""
+    rows: int
+    cols: int
+    indptr: np.ndarray
+    indices: np.ndarray
+    data: np.ndarray
+
+    @property
+    def nonzeros(self):
+        return int(self.indices.shape[0])
+
+    def c(self):
+        m = Csr()
+        m.rows, m.cols, m.nonzeros = self.rows, self.cols, self.nonzeros
+        m.indptr, m.indices, m.data = _ptr(self.indptr), _ptr(self.indices), _ptr(self.data)
+        m.on_device = 0
+        return m
+
+
+def createSparseMatrix(ratings, rows, cols):
+    """util.cu:152-179 (host part)."""
+    ratings = np.ascontiguousarray(ratings, dtype=RATING_DTYPE)
+    n = ratings.shape[0]
+    indptr = np.empty(rows + 1, dtype=np.int32)
+    indices = np.empty(n, dtype=np.int32)
+    data = np.empty(n, dtype=np.float32)
+    check(_lib.load().cu2b_build_csr(_ptr(ratings), n, rows, _ptr(indptr), _ptr(indices), _ptr(data)))
+    return CSRMatrix(rows, cols, indptr, indices, data)
+
+
+def read_array(path):
+    """util.cu:52-76 -> (flat float32 array, n_rows, n_cols as accumulated by the reference)."""
+    lib = _lib.load()
+    p = C.POINTER(C.c_float)()
+    r, c = C.c_int(), C.c_int()
+    check(lib.cu2b_read_array(str(path).encode(), C.byref(p), C.byref(r), C.byref(c)))
+    try:
+        out = np.empty(c.value, dtype=np.float32)
+        if c.value:
+            C.memmove(out.ctypes.data, p, c.value * 4)
+    finally:
+        lib.cu2b_free(p)
+    return out, r.value, c.value
+
+
+def writeCSV(path, data, rows, cols):  # util.cu:86-97
+    data = _f32(data)
+    check(_lib.load().cu2b_write_csv(str(path).encode(), _ptr(data), rows, cols))
+
+
+def writeToFile(parent_dir, base_filename, extension, component, data, rows, cols, factors):  # util.cu:99-103
+    data = _f32(data)
+    check(_lib.load().cu2b_write_component(str(parent_dir).encode(), base_filename.encode(), extension.encode(),
+                                           component.encode(), _ptr(data), rows, cols, factors))
+
+
+def initialize_normal_array(size, n_factors, mean=0.0, stddev=1.0, seed=42):  # util.cu:124-144
+    out = np.empty(size, dtype=np.float32)
+    _lib.load().cu2b_init_normal(_ptr(out), size, n_factors, mean, stddev, seed)
+    return out
+
+
+def synth_ratings(users, items, target_ratings, rank=16, noise=0.5, integer_ratings=True, test_fraction=0.1,
+                  seed=20240607):
+    """Synthetic low-rank-plus-noise ratings -> (train, test) RATING_DTYPE arrays."""
+    lib = _lib.load()
+    ntr, nte = C.c_int64(), C.c_int64()
+    args = (users, items, target_ratings, rank, noise, int(integer_ratings), test_fraction, seed)
+    check(lib.cu2b_synth_ratings(*args, None, C.byref(ntr), None, C.byref(nte)))
+    train = np.empty(ntr.value, dtype=RATING_DTYPE)
+    test = np.empty(nte.value, dtype=RATING_DTYPE)
+    check(lib.cu2b_synth_ratings(*args, _ptr(train), C.byref(ntr), _ptr(test), C.byref(nte)))
+    return train, test
+
+
+# ------------------------------------------------------------------------------------------
+# loss.h
+# ------------------------------------------------------------------------------------------
+def calculate_loss_gpu(P, Q, n_factors, matrix, user_bias, item_bias, global_bias):
+    """loss.cu:40-49 -> residual vector error[i] = data[i] - prediction."""
+    P, Q, ub, ib = _f32(P), _f32(Q), _f32(user_bias), _f32(item_bias)
+    err = np.empty(matrix.nonzeros, dtype=np.float32)
+    m = matrix.c()
+    check(_lib.load().cu2b_residuals(C.byref(m), _ptr(P), _ptr(Q), _ptr(ub), _ptr(ib), float(global_bias), n_factors, _ptr(err)))
+    return err
+
+
+def get_error_metrics_gpu(errors):
+    """loss.cu:196-200 -> (mae, rmse)."""
+    errors = _f32(errors)
+    mae, rmse = C.c_float(), C.c_float()
+    check(_lib.load().cu2b_error_metrics(_ptr(errors), errors.shape[0], C.byref(mae), C.byref(rmse)))
+    return np.float32(mae.value), np.float32(rmse.value)
+
+
+def loss(P, Q, n_factors, matrix, user_bias, item_bias, global_bias):
+    """Fused single pass: (mae, rmse) of the model on `matrix`."""
+    P, Q, ub, ib = _f32(P), _f32(Q), _f32(user_bias), _f32(item_bias)
+    mae, rmse = C.c_float(), C.c_float()
+    m = matrix.c()
+    check(_lib.load().cu2b_loss(C.byref(m), _ptr(P), _ptr(Q), _ptr(ub), _ptr(ib), float(global_bias), n_factors,
+                                C.byref(mae), C.byref(rmse)))
+    return np.float32(mae.value), np.float32(rmse.value)
+
+
+# ------------------------------------------------------------------------------------------
+# sgd.h
+# ------------------------------------------------------------------------------------------
+def sample_per_user(matrix, seed, iter0, n_iter):
+    """sgd.cu:27-37 sampling step -> triplet stream [n_iter * active_users]."""
+    lib = _lib.load()
+    m = matrix.c()
+    n = C.c_int64()
+    check(lib.cu2b_sample_per_user(C.byref(m), seed, iter0, n_iter, None, C.byref(n)))
+    out = np.empty(n.value, dtype=RATING_DTYPE)
+    check(lib.cu2b_sample_per_user(C.byref(m), seed, iter0, n_iter, _ptr(out), C.byref(n)))
+    return out
+
+
+def sgd_apply(stream, P, Q, user_bias, item_bias, global_bias, cfg, order=0):
+    """sgd.cu:40-72 arithmetic over an explicit stream; returns updated copies."""
+    stream = np.ascontiguousarray(stream, dtype=RATING_DTYPE)
+    P, Q, ub, ib = (np.array(_f32(x), copy=True) for x in (P, Q, user_bias, item_bias))
+    k = cfg.n_factors
+    rows, cols = P.size // k, Q.size // k
+    check(_lib.load().cu2b_sgd_apply(_ptr(stream), stream.shape[0], _ptr(P), rows, _ptr(Q), cols, _ptr(ub), _ptr(ib),
+                                     float(global_bias), C.byref(cfg.c), order))
+    return P, Q, ub, ib
+
+
+def sgd_blocked(coo, P, Q, user_bias, item_bias, global_bias, cfg, n_blocks, n_passes=1):
+    """Deterministic conflict-free pass(es) over `coo`; returns updated copies."""
+    coo = np.ascontiguousarray(coo, dtype=RATING_DTYPE)
+    P, Q, ub, ib = (np.array(_f32(x), copy=True) for x in (P, Q, user_bias, item_bias))
+    k = cfg.n_factors
+    rows, cols = P.size // k, Q.size // k
+    check(_lib.load().cu2b_sgd_blocked(_ptr(coo), coo.shape[0], _ptr(P), rows, _ptr(Q), cols, _ptr(ub), _ptr(ib),
+                                       float(global_bias), C.byref(cfg.c), n_blocks, n_passes))
+    return P, Q, ub, ib
+
+
+# ------------------------------------------------------------------------------------------
+# training.h
+# ------------------------------------------------------------------------------------------
+def _metrics_rows(buf, n):
+    return [dict(iteration=m.iteration, train_mae=m.train_mae, train_rmse=m.train_rmse, test_mae=m.test_mae,
+                 test_rmse=m.test_rmse, learning_rate=m.learning_rate) for m in buf[:n]]
+
+
+def _stats_dict(st):
+    return {name: getattr(st, name) for name, _ in Stats._fields_}
+
+
+def train(train_matrix, test_matrix, cfg, global_bias, Q=None, item_bias=None):
+    """training.h:12-15. With Q/item_bias None this is the 8-argument overload (they are
+    initialised inside, training.cu:208-217); otherwise the 10-argument one. cfg is updated
+    in place (learning_rate, cur_iterations). Returns dict(P, Q, losses, user_bias, item_bias,
+    log, stats)."""
+    lib = _lib.load()
+    k = cfg.n_factors
+    rows, cols = train_matrix.rows, train_matrix.cols
+    init_item = Q is None
+    P = np.empty(rows * k, dtype=np.float32)
+    ub = np.empty(rows, dtype=np.float32)
+    Q = np.empty(cols * k, dtype=np.float32) if init_item else np.array(_f32(Q).reshape(-1), copy=True)
+    ib = np.empty(cols, dtype=np.float32) if item_bias is None else np.array(_f32(item_bias), copy=True)
+    losses = np.empty(max(1, cfg.total_iterations), dtype=np.float32)
+    cap = cfg.total_iterations // max(1, cfg.check_error) + 8
+    log = (Metrics * cap)()
+    n_log = C.c_int()
+    st = Stats()
+    tm, te = train_matrix.c(), test_matrix.c()
+    check(lib.cu2b_train(C.byref(tm), C.byref(te), C.byref(cfg.c), _ptr(P), _ptr(Q), _ptr(ub), _ptr(ib),
+                         float(global_bias), int(init_item), _ptr(losses), log, cap, C.byref(n_log), C.byref(st)))
+    return dict(P=P.reshape(rows, k), Q=Q.reshape(cols, k), losses=losses[:cfg.total_iterations], user_bias=ub,
+                item_bias=ib, log=_metrics_rows(log, min(cap, n_log.value)), stats=_stats_dict(st))
+
+
+class Session:
+    """Resident-data training session (cu2b_session_*)."""
+
+    def __init__(self, train_matrix, test_matrix, cfg, P, Q, user_bias, item_bias, global_bias, device=0):
+        self.lib = _lib.load()
+        self.h = C.c_void_p()
+        self.k = cfg.n_factors
+        self.rows, self.cols = train_matrix.rows, train_matrix.cols
+        self.cfg = cfg
+        P, Q, ub, ib = _f32(P), _f32(Q), _f32(user_bias), _f32(item_bias)
+        tm, te = train_matrix.c(), test_matrix.c()
+        check(self.lib.cu2b_session_create(C.byref(self.h), device, C.byref(tm), C.byref(te), C.byref(cfg.c),
+                                           _ptr(P), _ptr(Q), _ptr(ub), _ptr(ib), float(global_bias)))
+
+    def run(self, n_iterations):
+        check(self.lib.cu2b_session_run(self.h, n_iterations))
+
+    def eval(self):
+        v = [C.c_float() for _ in range(4)]
+        check(self.lib.cu2b_session_eval(self.h, *[C.byref(x) for x in v]))
+        return dict(train_mae=v[0].value, train_rmse=v[1].value, test_mae=v[2].value, test_rmse=v[3].value)
+
+    def log(self):
+        cap = self.cfg.total_iterations // max(1, self.cfg.check_error) + 8
+        buf = (Metrics * cap)()
+        n = C.c_int()
+        check(self.lib.cu2b_session_log(self.h, buf, cap, C.byref(n)))
+        return _metrics_rows(buf, min(cap, n.value))
+
+    def download(self):
+        P = np.empty((self.rows, self.k), dtype=np.float32)
+        Q = np.empty((self.cols, self.k), dtype=np.float32)
+        ub = np.empty(self.rows, dtype=np.float32)
+        ib = np.empty(self.cols, dtype=np.float32)
+        check(self.lib.cu2b_session_download(self.h, _ptr(P), _ptr(Q), _ptr(ub), _ptr(ib)))
+        return P, Q, ub, ib
+
+    def config(self):
+        out = Config()
+        check(self.lib.cu2b_session_get_config(self.h, C.byref(out.c)))
+        return out
+
+    def stats(self, reset=False):
+        st = Stats()
+        check(self.lib.cu2b_session_stats(self.h, C.byref(st), int(reset)))
+        return _stats_dict(st)
+
+    def close(self):
+        if self.h:
+            self.lib.cu2b_session_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def device_info(device=0):
+    lib = _lib.load()
+    name = C.create_string_buffer(256)
+    sm, maj, mnr = C.c_int(), C.c_int(), C.c_int()
+    fb, tb = C.c_int64(), C.c_int64()
+    check(lib.cu2b_device_info(device, name, 256, C.byref(sm), C.byref(maj), C.byref(mnr), C.byref(fb), C.byref(tb)))
+    return dict(name=name.value.decode(), sm_count=sm.value, cc=(maj.value, mnr.value), free_bytes=fb.value,
+                total_bytes=tb.value)

@@ -1,0 +1,858 @@
+// libcu2b engine: device data layout, kernel dispatch, the device-resident training loop
+// (replaces training.cu:21-217) and the C-ABI entry points that touch the GPU.
+//
+// HBM layout of a session
+//   P  [rows x kp] fp32, Q [cols x kp] fp32, kp = n_factors rounded up to 4 (16-byte rows)
+//   user_bias [rows], item_bias [cols] fp32
+//   train / test matrices: indptr [rows+1] int32 + COO triplets (user,item,rating) 12 B each in
+//     CSR order (the loss stream; the per-user sampler gathers (item,rating) from it)
+//   update stream: [max_batch_segs x seg_pitch] triplets written by the sampler, consumed by
+//     the SGD kernel through TMA bulk copies
+//   DevState + metric log + loss partials: a few KB
+// There is no CPU fallback anywhere in this file.
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "cu2b_internal.h"
+#include "loss_kernels.cuh"
+#include "sgd_kernels.cuh"
+
+using namespace cu2b;
+
+#define CUDA_TRY(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return cu2b_fail(CU2B_ERR_CUDA, "Cuda Error: %s (%s:%d)", cudaGetErrorString(e__), \
+                             __FILE__, __LINE__);                                             \
+    } while (0)
+
+#define CU2B_TRY(expr)                      \
+    do {                                    \
+        cu2b_status s__ = (expr);           \
+        if (s__ != CU2B_OK) return s__;     \
+    } while (0)
+
+namespace {
+
+// ---------------------------------------------------------------------------------------
+// small RAII pool: everything allocated through it is released when it goes out of scope
+// ---------------------------------------------------------------------------------------
+struct DevPool {
+    std::vector<void *> ptrs;
+    ~DevPool() { release(); }
+    void release() {
+        for (void *p : ptrs) cudaFree(p);
+        ptrs.clear();
+    }
+    template <typename T>
+    cu2b_status alloc(T **out, size_t count) {
+        void *p = nullptr;
+        size_t bytes = std::max<size_t>(16, count * sizeof(T));
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {
+            *out = nullptr;
+            return cu2b_fail(e == cudaErrorMemoryAllocation ? CU2B_ERR_NOMEM : CU2B_ERR_CUDA,
+                             "cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
+        }
+        ptrs.push_back(p);
+        *out = (T *)p;
+        return CU2B_OK;
+    }
+    void free_one(void *p) {
+        auto it = std::find(ptrs.begin(), ptrs.end(), p);
+        if (it != ptrs.end()) { cudaFree(p); ptrs.erase(it); }
+    }
+};
+
+struct DevMatrix {
+    int rows = 0, cols = 0;
+    long long nnz = 0;
+    int *indptr = nullptr;        // rows + 1
+    cu2b_rating *coo = nullptr;   // nnz, padded to a multiple of 4 (+kChunkMax slack)
+};
+
+// thread per rating: user = last row whose indptr <= j
+__global__ void __launch_bounds__(256)
+expand_coo_kernel(const int *__restrict__ indptr, int rows, const int *__restrict__ indices,
+                  const float *__restrict__ data, long long nnz, cu2b_rating *__restrict__ coo) {
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < nnz;
+         j += (long long)gridDim.x * blockDim.x) {
+        int lo = 0, hi = rows;  // find the largest u in [0, rows) with indptr[u] <= j
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(indptr + mid) <= j) lo = mid; else hi = mid;
+        }
+        cu2b_rating r;
+        r.user = lo;
+        r.item = __ldg(indices + j);
+        r.rating = __ldg(data + j);
+        coo[j] = r;
+    }
+}
+
+cu2b_status check_device() {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10)
+        return cu2b_fail(CU2B_ERR_CUDA, "libcu2b is built for sm_100a only; device %d is sm_%d%d (%s)",
+                         dev, prop.major, prop.minor, prop.name);
+    return CU2B_OK;
+}
+
+cu2b_status validate_csr(const cu2b_csr *m, const char *what) {
+    if (!m || !m->indptr || m->rows < 0 || m->cols < 0 || m->nonzeros < 0 ||
+        (m->nonzeros > 0 && (!m->indices || !m->data)))
+        return cu2b_fail(CU2B_ERR_INVALID, "%s: malformed cu2b_csr", what);
+    return CU2B_OK;
+}
+
+// Uploads (or adopts) a CSR matrix and expands it to COO triplets on the device.
+cu2b_status upload_matrix(DevPool &pool, cudaStream_t st, const cu2b_csr *m, DevMatrix *out,
+                          std::vector<int> *indptr_host) {
+    CU2B_TRY(validate_csr(m, "upload_matrix"));
+    out->rows = m->rows;
+    out->cols = m->cols;
+    out->nnz = m->nonzeros;
+    const size_t nnz = (size_t)m->nonzeros;
+    CU2B_TRY(pool.alloc(&out->indptr, (size_t)m->rows + 1));
+    CU2B_TRY(pool.alloc(&out->coo, nnz + kChunkMax + 4));
+    const cudaMemcpyKind kind = m->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    CUDA_TRY(cudaMemcpyAsync(out->indptr, m->indptr, ((size_t)m->rows + 1) * sizeof(int), kind, st));
+    if (indptr_host) {
+        indptr_host->resize((size_t)m->rows + 1);
+        if (m->on_device) {
+            CUDA_TRY(cudaMemcpyAsync(indptr_host->data(), m->indptr, ((size_t)m->rows + 1) * sizeof(int),
+                                     cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+        } else {
+            memcpy(indptr_host->data(), m->indptr, ((size_t)m->rows + 1) * sizeof(int));
+        }
+    }
+    if (nnz == 0) return CU2B_OK;
+    const int *indices = m->indices;
+    const float *data = m->data;
+    int *tmp_i = nullptr;
+    float *tmp_d = nullptr;
+    if (!m->on_device) {
+        CU2B_TRY(pool.alloc(&tmp_i, nnz));
+        CU2B_TRY(pool.alloc(&tmp_d, nnz));
+        CUDA_TRY(cudaMemcpyAsync(tmp_i, m->indices, nnz * sizeof(int), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(tmp_d, m->data, nnz * sizeof(float), cudaMemcpyHostToDevice, st));
+        indices = tmp_i;
+        data = tmp_d;
+    }
+    const int grid = (int)std::min<size_t>((nnz + 255) / 256, 148 * 16);
+    expand_coo_kernel<<<grid, 256, 0, st>>>(out->indptr, m->rows, indices, data, (long long)nnz, out->coo);
+    CUDA_TRY(cudaGetLastError());
+    if (tmp_i) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        pool.free_one(tmp_i);
+        pool.free_one(tmp_d);
+    }
+    return CU2B_OK;
+}
+
+// dense [rows x k] host matrix <-> [rows x kp] device matrix
+cu2b_status upload_dense(cudaStream_t st, float *dst, const float *src, int rows, int k, int kp) {
+    if (rows == 0) return CU2B_OK;
+    if (kp != k) CUDA_TRY(cudaMemsetAsync(dst, 0, (size_t)rows * kp * sizeof(float), st));
+    CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)kp * sizeof(float), src, (size_t)k * sizeof(float),
+                               (size_t)k * sizeof(float), (size_t)rows, cudaMemcpyHostToDevice, st));
+    return CU2B_OK;
+}
+cu2b_status download_dense(cudaStream_t st, float *dst, const float *src, int rows, int k, int kp) {
+    if (rows == 0) return CU2B_OK;
+    CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)k * sizeof(float), src, (size_t)kp * sizeof(float),
+                               (size_t)k * sizeof(float), (size_t)rows, cudaMemcpyDeviceToHost, st));
+    return CU2B_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// kernel dispatch on the lane layout (L lanes per rating, V float4 per lane)
+// ---------------------------------------------------------------------------------------
+typedef void (*SgdKernel)(const SgdParams);
+typedef void (*LossKernel)(const LossParams);
+
+cu2b_status layout_for(int kp, int *L, int *V) {
+    const int vecs = kp / 4;
+    if (vecs < 1 || vecs > 128) return cu2b_fail(CU2B_ERR_UNSUPPORTED, "n_factors must be in [1, 512]");
+    int l = 1;
+    while (l < vecs && l < 32) l <<= 1;
+    *L = l;
+    *V = (vecs + l - 1) / l;
+    return CU2B_OK;
+}
+
+SgdKernel pick_sgd(int L, int V) {
+    switch (L) {
+        case 1: return mf_sgd_hogwild<1, 1, 2>;
+        case 2: return mf_sgd_hogwild<2, 1, 2>;
+        case 4: return mf_sgd_hogwild<4, 1, 2>;
+        case 8: return mf_sgd_hogwild<8, 1, 2>;
+        case 16: return mf_sgd_hogwild<16, 1, 2>;
+        default:
+            switch (V) {
+                case 1: return mf_sgd_hogwild<32, 1, 2>;
+                case 2: return mf_sgd_hogwild<32, 2, 2>;
+                case 3: return mf_sgd_hogwild<32, 3, 1>;
+                default: return mf_sgd_hogwild<32, 4, 1>;
+            }
+    }
+}
+LossKernel pick_loss(int L, int V) {
+    switch (L) {
+        case 1: return mf_loss_fused<1, 1>;
+        case 2: return mf_loss_fused<2, 1>;
+        case 4: return mf_loss_fused<4, 1>;
+        case 8: return mf_loss_fused<8, 1>;
+        case 16: return mf_loss_fused<16, 1>;
+        default:
+            switch (V) {
+                case 1: return mf_loss_fused<32, 1>;
+                case 2: return mf_loss_fused<32, 2>;
+                case 3: return mf_loss_fused<32, 3>;
+                default: return mf_loss_fused<32, 4>;
+            }
+    }
+}
+
+StreamView flat_view(const cu2b_rating *base, long long n, int chunk) {
+    StreamView sv;
+    sv.base = base;
+    sv.seg_pitch = (n + 3) & ~3LL;
+    sv.seg_len = (int)n;
+    sv.chunk = chunk;
+    sv.chunks_per_seg = (int)((n + chunk - 1) / chunk);
+    sv.num_chunks = sv.chunks_per_seg;
+    return sv;
+}
+
+int pick_chunk(long long per_segment, int resident_ctas) {
+    long long c = per_segment / std::max(1, resident_ctas);
+    c &= ~3LL;
+    return (int)std::min<long long>(kChunkMax, std::max<long long>(32, c));
+}
+
+struct Timing {  // CUDA-event stopwatch per kernel family, resolved after a stream sync
+    enum Kind { SGD = 0, LOSS = 1, SAMPLER = 2, TOTAL = 3, NKIND = 4 };
+    struct Span { cudaEvent_t a, b; int kind; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t get() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+    int begin(int kind, cudaStream_t st) {
+        Span s{get(), get(), kind};
+        cudaEventRecord(s.a, st);
+        spans.push_back(s);
+        return (int)spans.size() - 1;
+    }
+    void end(int id, cudaStream_t st) { cudaEventRecord(spans[id].b, st); }
+    void collect(double ms[NKIND]) {  // call after the stream is idle
+        for (Span &s : spans) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, s.a, s.b) == cudaSuccess) ms[s.kind] += t;
+            pool.push_back(s.a);
+            pool.push_back(s.b);
+        }
+        spans.clear();
+    }
+    ~Timing() {
+        for (Span &s : spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+        for (cudaEvent_t e : pool) cudaEventDestroy(e);
+    }
+};
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+// session
+// ---------------------------------------------------------------------------------------
+struct cu2b_session {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    DevPool pool;
+    cu2b_config cfg;
+    float mu = 0.f;
+    int k = 0, kp = 0, L = 1, V = 1;
+    int rows = 0, cols = 0;
+    DevMatrix train, test;
+    float *P = nullptr, *Q = nullptr, *ub = nullptr, *ib = nullptr;
+    int *active = nullptr;
+    int n_active = 0;
+    // update stream
+    cu2b_rating *stream_buf = nullptr;
+    long long seg_pitch = 0;
+    int chunk = 0, chunks_per_seg = 0, max_batch_segs = 0;
+    int *gate = nullptr;
+    int segs_done = 0;
+    unsigned long long *counters = nullptr;
+    int counter_slots = 0, counter_next = 0;
+    // loss
+    DevState *state = nullptr;
+    cu2b_metrics *log_dev = nullptr;
+    int log_cap = 0;
+    double *part_train = nullptr, *part_test = nullptr;
+    int loss_grid_max = 0, sgd_grid_max = 0;
+    int loss_chunk = kChunkMax;
+    SgdKernel sgd_kernel = nullptr;
+    LossKernel loss_kernel = nullptr;
+    int sm_count = 0;
+    int iter_done = 0;  // the reference loop variable i (training.cu:107)
+    Timing timing;
+    cu2b_stats stats;
+    ~cu2b_session() {
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+cu2b_status launch_loss(cu2b_session *s, const DevMatrix &m, double *partials, int *nblk, float *err_out) {
+    LossParams lp;
+    lp.sv = flat_view(m.coo, m.nnz, s->loss_chunk);
+    lp.P = s->P; lp.Q = s->Q; lp.user_bias = s->ub; lp.item_bias = s->ib;
+    lp.kp = s->kp;
+    lp.mu = s->mu;
+    lp.partials = partials;
+    lp.err_out = err_out;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(lp.sv.num_chunks, s->loss_grid_max));
+    s->loss_kernel<<<grid, kThreads, 0, s->stream>>>(lp);
+    CUDA_TRY(cudaGetLastError());
+    s->stats.kernel_launches++;
+    *nblk = grid;
+    return CU2B_OK;
+}
+
+cu2b_status enqueue_check(cu2b_session *s, int iteration_1based, int apply_schedule, bool log) {
+    const int id = s->timing.begin(Timing::LOSS, s->stream);
+    int nb_tr = 0, nb_te = 0;
+    CU2B_TRY(launch_loss(s, s->train, s->part_train, &nb_tr, nullptr));
+    CU2B_TRY(launch_loss(s, s->test, s->part_test, &nb_te, nullptr));
+    loss_finalize_kernel<<<1, 256, 0, s->stream>>>(s->state, s->part_train, nb_tr, s->train.nnz,
+                                                  s->part_test, nb_te, s->test.nnz, iteration_1based,
+                                                  apply_schedule, log ? s->log_dev : nullptr);
+    CUDA_TRY(cudaGetLastError());
+    s->stats.kernel_launches++;
+    s->timing.end(id, s->stream);
+    return CU2B_OK;
+}
+
+cu2b_status launch_sgd(cu2b_session *s, const StreamView &sv, int *gate, int seg0, int serial) {
+    SgdParams sp;
+    sp.sv = sv;
+    sp.P = s->P; sp.Q = s->Q; sp.user_bias = s->ub; sp.item_bias = s->ib;
+    sp.kp = s->kp;
+    sp.mu = s->mu;
+    sp.lr = &s->state->lr;
+    sp.P_reg = s->cfg.P_reg; sp.Q_reg = s->cfg.Q_reg;
+    sp.ub_reg = s->cfg.user_bias_reg; sp.ib_reg = s->cfg.item_bias_reg;
+    sp.is_train = s->cfg.is_train;
+    if (s->counter_next == 0)
+        CUDA_TRY(cudaMemsetAsync(s->counters, 0, sizeof(unsigned long long) * s->counter_slots, s->stream));
+    sp.chunk_counter = s->counters + s->counter_next;
+    s->counter_next = (s->counter_next + 1) % s->counter_slots;
+    sp.gate = gate;
+    sp.seg0 = seg0;
+    sp.serial = serial;
+    const int grid = serial ? 1 : (int)std::max<long long>(1, std::min<long long>(sv.num_chunks, s->sgd_grid_max));
+    s->sgd_kernel<<<grid, kThreads, 0, s->stream>>>(sp);
+    CUDA_TRY(cudaGetLastError());
+    s->stats.kernel_launches++;
+    s->stats.sgd_launches++;
+    return CU2B_OK;
+}
+
+// n_seg reference iterations starting at absolute iteration `iter_abs`
+cu2b_status enqueue_sgd_iterations(cu2b_session *s, int iter_abs, int n_seg) {
+    while (n_seg > 0) {
+        const int nb = std::min(n_seg, s->max_batch_segs);
+        // 1. sampler: one draw per active user per iteration (sgd.cu:27-37)
+        {
+            const int id = s->timing.begin(Timing::SAMPLER, s->stream);
+            const long long draws = (long long)nb * s->n_active;
+            const int grid = (int)std::min<long long>((draws + 255) / 256, (long long)s->sm_count * 16);
+            sample_per_user_kernel<<<grid, 256, 0, s->stream>>>(
+                s->train.indptr, s->train.coo, s->active, s->n_active, (uint32_t)s->cfg.seed, iter_abs,
+                draws, s->stream_buf, s->seg_pitch);
+            CUDA_TRY(cudaGetLastError());
+            s->stats.kernel_launches++;
+            s->timing.end(id, s->stream);
+        }
+        // 2. Hogwild updates over the sampled stream
+        {
+            const int id = s->timing.begin(Timing::SGD, s->stream);
+            StreamView sv;
+            sv.base = s->stream_buf;
+            sv.seg_pitch = s->seg_pitch;
+            sv.seg_len = s->n_active;
+            sv.chunk = s->chunk;
+            sv.chunks_per_seg = s->chunks_per_seg;
+            sv.num_chunks = (long long)nb * s->chunks_per_seg;
+            CU2B_TRY(launch_sgd(s, sv, s->gate, s->segs_done, 0));
+            s->timing.end(id, s->stream);
+        }
+        s->segs_done += nb;
+        s->stats.updates += (long long)nb * s->n_active;
+        iter_abs += nb;
+        n_seg -= nb;
+    }
+    return CU2B_OK;
+}
+
+}  // namespace
+
+extern "C" cu2b_status cu2b_session_create(cu2b_session **out, int device, const cu2b_csr *train,
+                                           const cu2b_csr *test, const cu2b_config *cfg,
+                                           const float *P, const float *Q, const float *user_bias,
+                                           const float *item_bias, float global_bias) {
+    if (!out || !cfg || !P || !Q || !user_bias || !item_bias)
+        return cu2b_fail(CU2B_ERR_INVALID, "cu2b_session_create: null argument");
+    *out = nullptr;
+    CU2B_TRY(validate_csr(train, "train"));
+    CU2B_TRY(validate_csr(test, "test"));
+    if (test->rows > train->rows || test->cols > train->cols)
+        return cu2b_fail(CU2B_ERR_INVALID,
+                         "test matrix (%d x %d) exceeds the model dimensions (%d x %d); size the train "
+                         "matrix with max(train, test)", test->rows, test->cols, train->rows, train->cols);
+    if (cfg->n_factors < 1) return cu2b_fail(CU2B_ERR_INVALID, "n_factors must be >= 1");
+    if (cfg->check_error < 1) return cu2b_fail(CU2B_ERR_INVALID, "check_error must be >= 1");
+    if (cfg->mode != CU2B_MODE_HOGWILD || cfg->sampler != CU2B_SAMPLER_PER_USER)
+        return cu2b_fail(CU2B_ERR_UNSUPPORTED, "session supports mode=hogwild, sampler=per_user in this build");
+    CUDA_TRY(cudaSetDevice(device));
+    CU2B_TRY(check_device());
+    cu2b_session *s = new cu2b_session();
+    std::unique_ptr<cu2b_session> guard(s);
+    s->device = device;
+    s->cfg = *cfg;
+    s->mu = global_bias;
+    s->k = cfg->n_factors;
+    s->kp = cu2b_padded_factors(s->k);
+    CU2B_TRY(layout_for(s->kp, &s->L, &s->V));
+    s->rows = train->rows;
+    s->cols = train->cols;
+    memset(&s->stats, 0, sizeof(s->stats));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    s->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+
+    std::vector<int> indptr_host;
+    CU2B_TRY(upload_matrix(s->pool, s->stream, train, &s->train, &indptr_host));
+    CU2B_TRY(upload_matrix(s->pool, s->stream, test, &s->test, nullptr));
+    // users with at least one training rating (sgd.cu:35 skips the others)
+    std::vector<int> active;
+    active.reserve(s->rows);
+    for (int u = 0; u < s->rows; ++u)
+        if (indptr_host[u + 1] > indptr_host[u]) active.push_back(u);
+    s->n_active = (int)active.size();
+    CU2B_TRY(s->pool.alloc(&s->active, active.size()));
+    if (!active.empty())
+        CUDA_TRY(cudaMemcpyAsync(s->active, active.data(), active.size() * sizeof(int), cudaMemcpyHostToDevice, s->stream));
+
+    CU2B_TRY(s->pool.alloc(&s->P, (size_t)s->rows * s->kp));
+    CU2B_TRY(s->pool.alloc(&s->Q, (size_t)s->cols * s->kp));
+    CU2B_TRY(s->pool.alloc(&s->ub, (size_t)s->rows));
+    CU2B_TRY(s->pool.alloc(&s->ib, (size_t)s->cols));
+    CU2B_TRY(upload_dense(s->stream, s->P, P, s->rows, s->k, s->kp));
+    CU2B_TRY(upload_dense(s->stream, s->Q, Q, s->cols, s->k, s->kp));
+    CUDA_TRY(cudaMemcpyAsync(s->ub, user_bias, (size_t)s->rows * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->ib, item_bias, (size_t)s->cols * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+
+    // kernels and their persistent grid sizes
+    s->sgd_kernel = pick_sgd(s->L, s->V);
+    s->loss_kernel = pick_loss(s->L, s->V);
+    int occ = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s->sgd_kernel, kThreads, 0));
+    s->sgd_grid_max = std::max(1, occ) * s->sm_count;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s->loss_kernel, kThreads, 0));
+    s->loss_grid_max = std::max(1, occ) * s->sm_count;
+
+    // update stream geometry: one segment per reference iteration
+    s->seg_pitch = ((long long)s->n_active + 3) & ~3LL;
+    s->chunk = pick_chunk(s->n_active, s->sgd_grid_max);
+    s->chunks_per_seg = std::max(1, (s->n_active + s->chunk - 1) / s->chunk);
+    const long long cap_ratings = 48LL << 20;  // <= 576 MB of triplets per batch
+    s->max_batch_segs = (int)std::max<long long>(1, std::min<long long>(cap_ratings / std::max<long long>(1, s->seg_pitch), 4096));
+    CU2B_TRY(s->pool.alloc(&s->stream_buf, (size_t)s->max_batch_segs * s->seg_pitch + kChunkMax + 4));
+    CU2B_TRY(s->pool.alloc(&s->gate, (size_t)s->chunks_per_seg));
+    CUDA_TRY(cudaMemsetAsync(s->gate, 0, (size_t)s->chunks_per_seg * sizeof(int), s->stream));
+    s->counter_slots = 256;
+    CU2B_TRY(s->pool.alloc(&s->counters, (size_t)s->counter_slots));
+
+    // loss scratch + device-resident schedule state
+    CU2B_TRY(s->pool.alloc(&s->part_train, (size_t)2 * s->loss_grid_max));
+    CU2B_TRY(s->pool.alloc(&s->part_test, (size_t)2 * s->loss_grid_max));
+    s->log_cap = cfg->total_iterations / cfg->check_error + 8;
+    CU2B_TRY(s->pool.alloc(&s->log_dev, (size_t)s->log_cap));
+    CU2B_TRY(s->pool.alloc(&s->state, 1));
+    DevState st;
+    memset(&st, 0, sizeof(st));
+    st.lr = cfg->learning_rate;
+    st.current_patience = (int)cfg->patience;  // training.cu:103
+    st.patience0 = (int)cfg->patience;
+    st.lr_decay = cfg->learning_rate_decay;
+    st.validation_rmse = FLT_MAX;              // training.cu:102
+    st.n_log = 0;
+    st.log_cap = s->log_cap;
+    CUDA_TRY(cudaMemcpyAsync(s->state, &st, sizeof(st), cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    *out = guard.release();
+    return CU2B_OK;
+}
+
+extern "C" cu2b_status cu2b_session_run(cu2b_session *s, int n_iterations) {
+    if (!s || n_iterations < 0) return cu2b_fail(CU2B_ERR_INVALID, "cu2b_session_run: bad argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    const int total = s->cfg.total_iterations, ce = s->cfg.check_error;
+    auto is_check = [&](int i) {  // training.cu:118
+        return (i + 1) % ce == 0 || i == 0 || (total > 0 && (i + 1) % total == 0);
+    };
+    const int tot_id = s->timing.begin(Timing::TOTAL, s->stream);
+    int i = s->iter_done;
+    const int end = i + n_iterations;
+    while (i < end) {
+        int j = i;
+        while (j < end && !is_check(j)) ++j;  // next check iteration (or end)
+        const int seg_end = std::min(j + 1, end);
+        if (s->n_active > 0)
+            CU2B_TRY(enqueue_sgd_iterations(s, s->cfg.cur_iterations + i, seg_end - i));
+        if (j < end) CU2B_TRY(enqueue_check(s, j + 1, 1, true));
+        i = seg_end;
+    }
+    s->timing.end(tot_id, s->stream);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));  // the only host sync of the loop
+    s->iter_done = end;
+    double ms[Timing::NKIND] = {0, 0, 0, 0};
+    s->timing.collect(ms);
+    s->stats.sgd_ms += ms[Timing::SGD];
+    s->stats.loss_ms += ms[Timing::LOSS];
+    s->stats.sampler_ms += ms[Timing::SAMPLER];
+    s->stats.total_ms += ms[Timing::TOTAL];
+    return CU2B_OK;
+}
+
+extern "C" cu2b_status cu2b_session_eval(cu2b_session *s, float *train_mae, float *train_rmse,
+                                         float *test_mae, float *test_rmse) {
+    if (!s) return cu2b_fail(CU2B_ERR_INVALID, "cu2b_session_eval: null session");
+    CUDA_TRY(cudaSetDevice(s->device));
+    CU2B_TRY(enqueue_check(s, 0, 0, false));
+    DevState st;
+    CUDA_TRY(cudaMemcpyAsync(&st, s->state, sizeof(st), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    double ms[Timing::NKIND] = {0, 0, 0, 0};
+    s->timing.collect(ms);
+    s->stats.loss_ms += ms[Timing::LOSS];
+    if (train_rmse) *train_rmse = (float)sqrt(st.sums[0] / (double)s->train.nnz);
+    if (train_mae) *train_mae = (float)(st.sums[1] / (double)s->train.nnz);
+    if (test_rmse) *test_rmse = (float)sqrt(st.sums[2] / (double)s->test.nnz);
+    if (test_mae) *test_mae = (float)(st.sums[3] / (double)s->test.nnz);
+    return CU2B_OK;
+}
+
+extern "C" cu2b_status cu2b_session_log(cu2b_session *s, cu2b_metrics *out, int cap, int *n) {
+    if (!s || !n) return cu2b_fail(CU2B_ERR_INVALID, "cu2b_session_log: bad argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    DevState st;
+    CUDA_TRY(cudaMemcpy(&st, s->state, sizeof(st), cudaMemcpyDeviceToHost));
+    const int have = std::min(st.n_log, s->log_cap);
+    *n = have;
+    const int take = std::min(have, cap);
+    if (out && take > 0)
+        CUDA_TRY(cudaMemcpy(out, s->log_dev, (size_t)take * sizeof(cu2b_metrics), cudaMemcpyDeviceToHost));
+    return CU2B_OK;
+}
+
+extern "C" cu2b_status cu2b_session_download(cu2b_session *s, float *P, float *Q, float *user_bias,
+                                             float *item_bias) {
+    if (!s) return cu2b_fail(CU2B_ERR_INVALID, "cu2b_session_download: null session");
+    CUDA_TRY(cudaSetDevice(s->device));
+    if (P) CU2B_TRY(download_dense(s->stream, P, s->P, s->rows, s->k, s->kp));
+    if (Q) CU2B_TRY(download_dense(s->stream, Q, s->Q, s->cols, s->k, s->kp));
+    if (user_bias) CUDA_TRY(cudaMemcpyAsync(user_bias, s->ub, (size_t)s->rows * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    if (item_bias) CUDA_TRY(cudaMemcpyAsync(item_bias, s->ib, (size_t)s->cols * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return CU2B_OK;
+}
+
+extern "C" cu2b_status cu2b_session_get_config(cu2b_session *s, cu2b_config *out) {
+    if (!s || !out) return cu2b_fail(CU2B_ERR_INVALID, "cu2b_session_get_config: bad argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    DevState st;
+    CUDA_TRY(cudaMemcpy(&st, s->state, sizeof(st), cudaMemcpyDeviceToHost));
+    *out = s->cfg;
+    out->learning_rate = st.lr;                                   // training.cu:151
+    out->cur_iterations = s->cfg.cur_iterations + s->iter_done;   // training.cu:170
+    return CU2B_OK;
+}
+
+extern "C" cu2b_status cu2b_session_stats(cu2b_session *s, cu2b_stats *out, int reset) {
+    if (!s) return cu2b_fail(CU2B_ERR_INVALID, "cu2b_session_stats: null session");
+    if (out) *out = s->stats;
+    if (reset) memset(&s->stats, 0, sizeof(s->stats));
+    return CU2B_OK;
+}
+
+extern "C" void cu2b_session_destroy(cu2b_session *s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    delete s;
+}
+
+extern "C" cu2b_status cu2b_train(const cu2b_csr *train, const cu2b_csr *test, cu2b_config *cfg,
+                                  float *P, float *Q, float *user_bias, float *item_bias,
+                                  float global_bias, int init_item_side, float *losses,
+                                  cu2b_metrics *log, int log_cap, int *n_log, cu2b_stats *stats) {
+    if (!train || !test || !cfg || !P || !Q || !user_bias || !item_bias)
+        return cu2b_fail(CU2B_ERR_INVALID, "cu2b_train: null argument");
+    const int k = cfg->n_factors;
+    if (k < 1) return cu2b_fail(CU2B_ERR_INVALID, "n_factors must be >= 1");
+    // training.cu:212-213 (Q, item_bias) then training.cu:28,54 (P, user_bias): every array is
+    // drawn from its own mt19937(42), so all four share a prefix of identical values.
+    if (init_item_side) {
+        cu2b_init_normal(Q, (int64_t)train->cols * k, k, 0.f, 1.f, 42);
+        cu2b_init_normal(item_bias, train->cols, k, 0.f, 1.f, 42);
+    }
+    cu2b_init_normal(P, (int64_t)train->rows * k, k, 0.f, 1.f, 42);
+    cu2b_init_normal(user_bias, train->rows, k, 0.f, 1.f, 42);
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    cu2b_session *s = nullptr;
+    CU2B_TRY(cu2b_session_create(&s, dev, train, test, cfg, P, Q, user_bias, item_bias, global_bias));
+    cu2b_status rc = cu2b_session_run(s, cfg->total_iterations);
+    if (rc == CU2B_OK) rc = cu2b_session_download(s, P, Q, user_bias, item_bias);
+    std::vector<cu2b_metrics> rows_log;
+    int have = 0;
+    if (rc == CU2B_OK) {
+        rows_log.resize((size_t)s->log_cap);
+        rc = cu2b_session_log(s, rows_log.data(), s->log_cap, &have);
+    }
+    if (rc == CU2B_OK) {
+        if (losses) {  // training.cu:158: only check iterations are written; we NaN the rest
+            for (int i = 0; i < cfg->total_iterations; ++i) losses[i] = NAN;
+            for (int r = 0; r < have; ++r) {
+                const int it = rows_log[r].iteration;
+                if (it >= 1 && it <= cfg->total_iterations) losses[it - 1] = rows_log[r].test_rmse;
+            }
+        }
+        if (log) memcpy(log, rows_log.data(), (size_t)std::min(have, log_cap) * sizeof(cu2b_metrics));
+        if (n_log) *n_log = have;
+        if (stats) *stats = s->stats;
+        cu2b_config after;
+        rc = cu2b_session_get_config(s, &after);
+        if (rc == CU2B_OK) {
+            cfg->learning_rate = after.learning_rate;
+            cfg->cur_iterations = after.cur_iterations;
+        }
+    }
+    cu2b_session_destroy(s);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------
+// kernel-level entry points (host buffers)
+// ---------------------------------------------------------------------------------------
+namespace {
+
+// A throw-away model on the device for the host-buffer entry points below.
+struct Scratch {
+    cu2b_session s;  // reuses the session fields / launch helpers
+    cu2b_status init(int rows, int cols, int k, const float *P, const float *Q, const float *ub,
+                     const float *ib, float mu, const cu2b_config *cfg) {
+        CU2B_TRY(check_device());
+        CUDA_TRY(cudaGetDevice(&s.device));
+        if (cfg) s.cfg = *cfg; else cu2b_config_default(&s.cfg);
+        s.cfg.n_factors = k;
+        s.mu = mu;
+        s.k = k;
+        s.kp = cu2b_padded_factors(k);
+        CU2B_TRY(layout_for(s.kp, &s.L, &s.V));
+        s.rows = rows;
+        s.cols = cols;
+        memset(&s.stats, 0, sizeof(s.stats));
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, s.device));
+        s.sm_count = prop.multiProcessorCount;
+        CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CU2B_TRY(s.pool.alloc(&s.P, (size_t)rows * s.kp));
+        CU2B_TRY(s.pool.alloc(&s.Q, (size_t)cols * s.kp));
+        CU2B_TRY(s.pool.alloc(&s.ub, (size_t)rows));
+        CU2B_TRY(s.pool.alloc(&s.ib, (size_t)cols));
+        CU2B_TRY(upload_dense(s.stream, s.P, P, rows, k, s.kp));
+        CU2B_TRY(upload_dense(s.stream, s.Q, Q, cols, k, s.kp));
+        CUDA_TRY(cudaMemcpyAsync(s.ub, ub, (size_t)rows * sizeof(float), cudaMemcpyHostToDevice, s.stream));
+        CUDA_TRY(cudaMemcpyAsync(s.ib, ib, (size_t)cols * sizeof(float), cudaMemcpyHostToDevice, s.stream));
+        s.sgd_kernel = pick_sgd(s.L, s.V);
+        s.loss_kernel = pick_loss(s.L, s.V);
+        int occ = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s.sgd_kernel, kThreads, 0));
+        s.sgd_grid_max = std::max(1, occ) * s.sm_count;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s.loss_kernel, kThreads, 0));
+        s.loss_grid_max = std::max(1, occ) * s.sm_count;
+        s.counter_slots = 8;
+        CU2B_TRY(s.pool.alloc(&s.counters, (size_t)s.counter_slots));
+        CU2B_TRY(s.pool.alloc(&s.part_train, (size_t)2 * s.loss_grid_max));
+        CU2B_TRY(s.pool.alloc(&s.state, 1));
+        DevState st;
+        memset(&st, 0, sizeof(st));
+        st.lr = s.cfg.learning_rate;
+        CUDA_TRY(cudaMemcpyAsync(s.state, &st, sizeof(st), cudaMemcpyHostToDevice, s.stream));
+        return CU2B_OK;
+    }
+};
+
+cu2b_status sum_partials(cudaStream_t st, const double *partials_dev, int nblk, double *sse, double *sae) {
+    std::vector<double> h((size_t)2 * nblk);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), partials_dev, h.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    double a = 0, b = 0;
+    for (int i = 0; i < nblk; ++i) { a += h[2 * i]; b += h[2 * i + 1]; }
+    *sse = a;
+    *sae = b;
+    return CU2B_OK;
+}
+
+cu2b_status loss_impl(const cu2b_csr *m, const float *P, const float *Q, const float *ub, const float *ib,
+                      float mu, int k, float *mae, float *rmse, float *err) {
+    CU2B_TRY(validate_csr(m, "cu2b_loss"));
+    if (!P || !Q || !ub || !ib || k < 1) return cu2b_fail(CU2B_ERR_INVALID, "cu2b_loss: bad argument");
+    Scratch sc;
+    CU2B_TRY(sc.init(m->rows, m->cols, k, P, Q, ub, ib, mu, nullptr));
+    cu2b_session &s = sc.s;
+    CU2B_TRY(upload_matrix(s.pool, s.stream, m, &s.train, nullptr));
+    float *err_dev = nullptr;
+    if (err) CU2B_TRY(s.pool.alloc(&err_dev, (size_t)m->nonzeros));
+    int nblk = 0;
+    CU2B_TRY(launch_loss(&s, s.train, s.part_train, &nblk, err_dev));
+    double sse, sae;
+    CU2B_TRY(sum_partials(s.stream, s.part_train, nblk, &sse, &sae));
+    if (err && m->nonzeros > 0)
+        CUDA_TRY(cudaMemcpy(err, err_dev, (size_t)m->nonzeros * sizeof(float), cudaMemcpyDeviceToHost));
+    if (mae) *mae = (float)(sae / (double)m->nonzeros);
+    if (rmse) *rmse = (float)sqrt(sse / (double)m->nonzeros);
+    return CU2B_OK;
+}
+
+}  // namespace
+
+extern "C" cu2b_status cu2b_loss(const cu2b_csr *m, const float *P, const float *Q, const float *ub,
+                                 const float *ib, float mu, int k, float *mae, float *rmse) {
+    return loss_impl(m, P, Q, ub, ib, mu, k, mae, rmse, nullptr);
+}
+
+extern "C" cu2b_status cu2b_residuals(const cu2b_csr *m, const float *P, const float *Q, const float *ub,
+                                      const float *ib, float mu, int k, float *err) {
+    if (!err) return cu2b_fail(CU2B_ERR_INVALID, "cu2b_residuals: null output");
+    return loss_impl(m, P, Q, ub, ib, mu, k, nullptr, nullptr, err);
+}
+
+extern "C" cu2b_status cu2b_error_metrics(const float *err, int64_t n, float *mae, float *rmse) {
+    if (!err || n <= 0 || !mae || !rmse) return cu2b_fail(CU2B_ERR_INVALID, "cu2b_error_metrics: bad argument");
+    CU2B_TRY(check_device());
+    DevPool pool;
+    float *e_dev;
+    double *part;
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+    CU2B_TRY(pool.alloc(&e_dev, (size_t)n));
+    CU2B_TRY(pool.alloc(&part, (size_t)2 * grid));
+    CUDA_TRY(cudaMemcpy(e_dev, err, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+    error_metrics_kernel<<<grid, 256>>>(e_dev, (long long)n, part);
+    CUDA_TRY(cudaGetLastError());
+    double sse, sae;
+    CU2B_TRY(sum_partials(0, part, grid, &sse, &sae));
+    *mae = (float)(sae / (double)n);
+    *rmse = (float)sqrt(sse / (double)n);
+    return CU2B_OK;
+}
+
+extern "C" cu2b_status cu2b_sample_per_user(const cu2b_csr *m, int seed, int iter0, int n_iter,
+                                            cu2b_rating *out, int64_t *n_out) {
+    CU2B_TRY(validate_csr(m, "cu2b_sample_per_user"));
+    if (n_iter < 0 || !n_out) return cu2b_fail(CU2B_ERR_INVALID, "cu2b_sample_per_user: bad argument");
+    CU2B_TRY(check_device());
+    DevPool pool;
+    cudaStream_t st = 0;
+    DevMatrix dm;
+    std::vector<int> indptr;
+    CU2B_TRY(upload_matrix(pool, st, m, &dm, &indptr));
+    std::vector<int> active;
+    for (int u = 0; u < m->rows; ++u)
+        if (indptr[u + 1] > indptr[u]) active.push_back(u);
+    const long long draws = (long long)n_iter * (long long)active.size();
+    *n_out = draws;
+    if (!out || draws == 0) return CU2B_OK;
+    int *act_dev;
+    cu2b_rating *out_dev;
+    CU2B_TRY(pool.alloc(&act_dev, active.size()));
+    CU2B_TRY(pool.alloc(&out_dev, (size_t)draws));
+    CUDA_TRY(cudaMemcpy(act_dev, active.data(), active.size() * sizeof(int), cudaMemcpyHostToDevice));
+    const int grid = (int)std::min<long long>((draws + 255) / 256, 148 * 16);
+    sample_per_user_kernel<<<grid, 256, 0, st>>>(dm.indptr, dm.coo, act_dev, (int)active.size(), (uint32_t)seed,
+                                                 iter0, draws, out_dev, (long long)active.size());
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(out, out_dev, (size_t)draws * sizeof(cu2b_rating), cudaMemcpyDeviceToHost));
+    return CU2B_OK;
+}
+
+extern "C" cu2b_status cu2b_sgd_apply(const cu2b_rating *stream, int64_t n, float *P, int rows, float *Q,
+                                      int cols, float *ub, float *ib, float mu, const cu2b_config *cfg,
+                                      int order) {
+    if ((!stream && n > 0) || n < 0 || !P || !Q || !ub || !ib || !cfg || rows < 0 || cols < 0)
+        return cu2b_fail(CU2B_ERR_INVALID, "cu2b_sgd_apply: bad argument");
+    for (int64_t t = 0; t < n; ++t)
+        if (stream[t].user < 0 || stream[t].user >= rows || stream[t].item < 0 || stream[t].item >= cols)
+            return cu2b_fail(CU2B_ERR_INVALID, "cu2b_sgd_apply: rating %ld out of range", (long)t);
+    Scratch sc;
+    CU2B_TRY(sc.init(rows, cols, cfg->n_factors, P, Q, ub, ib, mu, cfg));
+    cu2b_session &s = sc.s;
+    if (n > 0) {
+        cu2b_rating *sdev;
+        CU2B_TRY(s.pool.alloc(&sdev, (size_t)n + kChunkMax + 4));
+        CUDA_TRY(cudaMemcpyAsync(sdev, stream, (size_t)n * sizeof(cu2b_rating), cudaMemcpyHostToDevice, s.stream));
+        const int chunk = order == 1 ? kChunkMax : pick_chunk(n, s.sgd_grid_max);
+        CU2B_TRY(launch_sgd(&s, flat_view(sdev, n, chunk), nullptr, 0, order == 1));
+    }
+    CU2B_TRY(download_dense(s.stream, P, s.P, rows, s.k, s.kp));
+    CU2B_TRY(download_dense(s.stream, Q, s.Q, cols, s.k, s.kp));
+    CUDA_TRY(cudaMemcpyAsync(ub, s.ub, (size_t)rows * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(cudaMemcpyAsync(ib, s.ib, (size_t)cols * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
+    return CU2B_OK;
+}
+
+extern "C" cu2b_status cu2b_sgd_blocked(const cu2b_rating *, int64_t, float *, int, float *, int, float *,
+                                        float *, float, const cu2b_config *, int, int) {
+    return cu2b_fail(CU2B_ERR_UNSUPPORTED, "cu2b_sgd_blocked: not built yet");
+}
+
+extern "C" cu2b_status cu2b_device_info(int device, char *name, int name_cap, int *sm_count, int *cc_major,
+                                        int *cc_minor, int64_t *free_bytes, int64_t *total_bytes) {
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (name && name_cap > 0) snprintf(name, (size_t)name_cap, "%s", prop.name);
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    if (free_bytes || total_bytes) {
+        CUDA_TRY(cudaSetDevice(device));
+        size_t f = 0, t = 0;
+        CUDA_TRY(cudaMemGetInfo(&f, &t));
+        if (free_bytes) *free_bytes = (int64_t)f;
+        if (total_bytes) *total_bytes = (int64_t)t;
+    }
+    return CU2B_OK;
+}

@@ -1,0 +1,629 @@
+// Host side of the drop-in boundary: config file, ratings CSV ingest, CSR build, factor
+// matrix writer/reader and model initialisation. Behavioural contract = the reference's
+// config.cu / util.cu (cited per function in include/cu2b.h); the implementation is ours:
+// mmap + multi-threaded tokenizer instead of ifstream>>, exact integer "%f" formatter
+// instead of fprintf per element.
+
+#include <fcntl.h>
+#include <omp.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "cu2b_internal.h"
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+cu2b_status cu2b_fail(cu2b_status code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+extern "C" const char *cu2b_last_error(void) { return g_err; }
+extern "C" int cu2b_version(void) { return CU2B_VERSION; }
+extern "C" void cu2b_free(void *p) { free(p); }
+
+// ------------------------------------------------------------------------------------------
+// config
+// ------------------------------------------------------------------------------------------
+extern "C" void cu2b_config_default(cu2b_config *c) {
+    c->cur_iterations = 0;
+    c->total_iterations = 5000;
+    c->n_factors = 50;
+    c->learning_rate = 0.01f;
+    c->seed = 42;
+    c->P_reg = c->Q_reg = c->user_bias_reg = c->item_bias_reg = 0.02f;
+    c->is_train = 1;
+    c->n_threads = 32;
+    c->check_error = 500;
+    c->patience = 2.0f;
+    c->learning_rate_decay = 0.2f;
+    c->mode = CU2B_MODE_HOGWILD;
+    c->sampler = CU2B_SAMPLER_PER_USER;
+    c->n_blocks = 0;
+    c->n_gpus = 1;
+}
+
+namespace {
+// Whitespace separated token reader with the stop-at-first-failure behaviour of a chained
+// operator>>: once one extraction fails, every later field keeps its previous value.
+struct TokenReader {
+    FILE *f;
+    bool ok = true;
+    bool next(char *tok, size_t cap) {
+        if (!ok) return false;
+        int c;
+        do { c = fgetc(f); } while (c != EOF && isspace(c));
+        if (c == EOF) return ok = false;
+        size_t n = 0;
+        while (c != EOF && !isspace(c)) {
+            if (n + 1 < cap) tok[n++] = (char)c;
+            c = fgetc(f);
+        }
+        tok[n] = 0;
+        return true;
+    }
+    void get(int *v) {
+        char t[64], *e;
+        if (!next(t, sizeof t)) return;
+        long x = strtol(t, &e, 10);
+        if (e == t) { ok = false; return; }
+        *v = (int)x;
+    }
+    void get(float *v) {
+        char t[64], *e;
+        if (!next(t, sizeof t)) return;
+        float x = strtof(t, &e);
+        if (e == t) { ok = false; return; }
+        *v = x;
+    }
+};
+}  // namespace
+
+extern "C" cu2b_status cu2b_config_read(const char *path, cu2b_config *c) {
+    if (!path || !c) return cu2b_fail(CU2B_ERR_INVALID, "cu2b_config_read: null argument");
+    FILE *f = fopen(path, "r");
+    // The reference silently keeps the defaults when the file cannot be opened
+    // (config.cu:8-12 never checks the stream); we keep the defaults too but report it.
+    if (!f) return cu2b_fail(CU2B_ERR_IO, "cannot open config file %s", path);
+    TokenReader r{f};
+    r.get(&c->cur_iterations);
+    r.get(&c->total_iterations);
+    r.get(&c->n_factors);
+    r.get(&c->learning_rate);
+    r.get(&c->seed);
+    r.get(&c->P_reg);
+    r.get(&c->Q_reg);
+    r.get(&c->user_bias_reg);
+    r.get(&c->item_bias_reg);
+    // optional extension tokens
+    r.get(&c->n_threads);
+    r.get(&c->patience);
+    r.get(&c->learning_rate_decay);
+    r.get(&c->check_error);
+    r.get(&c->mode);
+    r.get(&c->sampler);
+    r.get(&c->n_blocks);
+    r.get(&c->n_gpus);
+    fclose(f);
+    return CU2B_OK;
+}
+
+extern "C" cu2b_status cu2b_config_write(const char *path, const cu2b_config *c) {
+    if (!path || !c) return cu2b_fail(CU2B_ERR_INVALID, "cu2b_config_write: null argument");
+    FILE *f = fopen(path, "w");
+    if (!f) return cu2b_fail(CU2B_ERR_IO, "cannot create config file %s", path);
+    // ostream<<float prints with 6 significant digits == "%g"
+    fprintf(f, "%d %d %d %g %d %g %g %g %g\n", c->cur_iterations, c->total_iterations,
+            c->n_factors, c->learning_rate, c->seed, c->P_reg, c->Q_reg, c->user_bias_reg,
+            c->item_bias_reg);
+    fclose(f);
+    return CU2B_OK;
+}
+
+extern "C" int cu2b_config_format(const cu2b_config *c, char *buf, int cap) {
+    return snprintf(buf, cap > 0 ? (size_t)cap : 0,
+                    "Hyperparameters:\n"
+                    "total_iterations: %d\n"
+                    "n_factors: %d\n"
+                    "learning_rate: %f\n"
+                    "P_reg: %f\n"
+                    "Q_reg: %f\n"
+                    "user_bias_reg: %f\n"
+                    "item_bias_reg: %f\n"
+                    "is_train: %s\n"
+                    "n_threads: %d\n"
+                    "check_error: %d\n"
+                    "patience: %f\n"
+                    "learning_rate_decay: %f\n",
+                    c->total_iterations, c->n_factors, c->learning_rate, c->P_reg, c->Q_reg,
+                    c->user_bias_reg, c->item_bias_reg, c->is_train ? "true" : "false",
+                    c->n_threads, c->check_error, c->patience, c->learning_rate_decay);
+}
+
+// ------------------------------------------------------------------------------------------
+// ratings CSV
+// ------------------------------------------------------------------------------------------
+namespace {
+inline bool is_ws(char c) { return c == ' ' || c == '\n' || c == '\t' || c == '\r' || c == '\v' || c == '\f'; }
+
+// One "int <char> int <char> float" record starting at p (leading whitespace allowed).
+// Returns the position just after the float, or nullptr if the record does not parse.
+const char *parse_record(const char *p, const char *end, cu2b_rating *out) {
+    int ids[2];
+    for (int part = 0; part < 2; ++part) {
+        while (p < end && is_ws(*p)) ++p;
+        if (p >= end) return nullptr;
+        bool neg = false;
+        if (*p == '-' || *p == '+') { neg = *p == '-'; ++p; }
+        if (p >= end || *p < '0' || *p > '9') return nullptr;
+        long v = 0;
+        while (p < end && *p >= '0' && *p <= '9') { v = v * 10 + (*p - '0'); ++p; }
+        ids[part] = (int)(neg ? -v : v);
+        while (p < end && is_ws(*p)) ++p;  // operator>>(char&) skips whitespace,
+        if (p >= end) return nullptr;      // then takes any one character as the delimiter
+        ++p;
+    }
+    while (p < end && is_ws(*p)) ++p;
+    if (p >= end) return nullptr;
+    // fast path: [sign] digits [. digits] with <= 7 significant digits and no exponent is
+    // correctly rounded by a single float division (both operands exact in float).
+    const char *q = p;
+    bool neg = false;
+    if (*q == '-' || *q == '+') { neg = *q == '-'; ++q; }
+    uint32_t mant = 0;
+    int ndig = 0, nfrac = 0;
+    bool any = false;
+    while (q < end && *q >= '0' && *q <= '9') { mant = mant * 10 + (uint32_t)(*q - '0'); ndig += (mant != 0); ++q; any = true; if (ndig > 7) break; }
+    if (ndig <= 7 && q < end && *q == '.') {
+        ++q;
+        while (q < end && *q >= '0' && *q <= '9') { mant = mant * 10 + (uint32_t)(*q - '0'); ndig += (mant != 0); ++nfrac; ++q; any = true; if (ndig > 7) break; }
+    }
+    static const float pow10[] = {1.f, 1e1f, 1e2f, 1e3f, 1e4f, 1e5f, 1e6f, 1e7f, 1e8f, 1e9f, 1e10f};
+    bool simple = any && ndig <= 7 && nfrac <= 10 &&
+                  (q >= end || !(*q == 'e' || *q == 'E' || *q == '.' || (*q >= '0' && *q <= '9') ||
+                                 *q == 'x' || *q == 'X' || *q == 'n' || *q == 'N' || *q == 'i' || *q == 'I'));
+    float val;
+    if (simple) {
+        val = (float)mant / pow10[nfrac];
+        if (neg) val = -val;
+        p = q;
+    } else {
+        char tmp[64];
+        size_t n = std::min<size_t>(sizeof(tmp) - 1, (size_t)(end - p));
+        memcpy(tmp, p, n);
+        tmp[n] = 0;
+        char *e;
+        val = strtof(tmp, &e);
+        if (e == tmp) return nullptr;
+        p += (e - tmp);
+    }
+    out->user = ids[0] - 1;
+    out->item = ids[1] - 1;
+    out->rating = val;
+    return p;
+}
+}  // namespace
+
+extern "C" cu2b_status cu2b_read_csv(const char *path, cu2b_rating **ratings, int64_t *n_out,
+                                     int *rows, int *cols, float *global_bias) {
+    if (!path || !ratings || !n_out || !rows || !cols || !global_bias)
+        return cu2b_fail(CU2B_ERR_INVALID, "cu2b_read_csv: null argument");
+    *ratings = nullptr;
+    *n_out = 0;
+    int fd = open(path, O_RDONLY);
+    // reference: prints "ERROR: The file isnt open." and returns an empty vector (util.cu:41-44)
+    if (fd < 0) return cu2b_fail(CU2B_ERR_IO, "ERROR: The file isnt open. (%s)", path);
+    struct stat st;
+    fstat(fd, &st);
+    size_t size = (size_t)st.st_size;
+    if (size == 0) { close(fd); *rows = *cols = 0; *global_bias = NAN; return CU2B_OK; }
+    const char *base = (const char *)mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (base == MAP_FAILED) return cu2b_fail(CU2B_ERR_IO, "mmap failed for %s", path);
+    madvise((void *)base, size, MADV_SEQUENTIAL);
+    const char *end = base + size;
+    // header: ignore(1000, '\n') -- at most 1000 characters, stopping after the first newline
+    const char *body = base;
+    {
+        size_t lim = std::min<size_t>(size, 1000);
+        const char *nl = (const char *)memchr(base, '\n', lim);
+        body = nl ? nl + 1 : base + lim;
+    }
+
+    int nthreads = std::max(1, omp_get_max_threads());
+    size_t body_size = (size_t)(end - body);
+    if (body_size < (1u << 20)) nthreads = 1;
+    // split at newline boundaries
+    std::vector<const char *> cut(nthreads + 1);
+    cut[0] = body;
+    cut[nthreads] = end;
+    for (int t = 1; t < nthreads; ++t) {
+        const char *p = body + body_size * t / nthreads;
+        const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
+        cut[t] = nl ? nl + 1 : end;
+    }
+    std::vector<std::vector<cu2b_rating>> part(nthreads);
+    std::vector<const char *> stopped(nthreads);  // first unparsed non-ws position (or cut end)
+#pragma omp parallel for num_threads(nthreads) schedule(static, 1)
+    for (int t = 0; t < nthreads; ++t) {
+        const char *p = cut[t], *e = cut[t + 1];
+        std::vector<cu2b_rating> &v = part[t];
+        v.reserve((size_t)(e - p) / 12 + 16);
+        cu2b_rating r;
+        while (true) {
+            const char *nx = parse_record(p, e, &r);
+            if (!nx) break;
+            v.push_back(r);
+            p = nx;
+        }
+        while (p < e && is_ws(*p)) ++p;
+        stopped[t] = p;
+    }
+    // A chunk that stopped early marks the end of the stream (>> fails => loop ends), unless
+    // the stop was caused by a record straddling our artificial cut; then re-parse serially.
+    bool straddle = false;
+    int last = nthreads;
+    for (int t = 0; t < nthreads; ++t) {
+        if (stopped[t] != cut[t + 1]) {
+            if (t + 1 < nthreads) {
+                cu2b_rating r;  // would the record parse if it could continue past the cut?
+                if (parse_record(stopped[t], end, &r)) straddle = true;
+            }
+            last = t + 1;
+            break;
+        }
+    }
+    if (straddle) {
+        part.assign(1, {});
+        const char *p = body;
+        cu2b_rating r;
+        while (const char *nx = parse_record(p, end, &r)) { part[0].push_back(r); p = nx; }
+        last = 1;
+    }
+    int64_t n = 0;
+    for (int t = 0; t < last; ++t) n += (int64_t)part[t].size();
+    cu2b_rating *out = (cu2b_rating *)malloc(std::max<size_t>(1, (size_t)n) * sizeof(cu2b_rating));
+    if (!out) { munmap((void *)base, size); return cu2b_fail(CU2B_ERR_NOMEM, "out of memory for %ld ratings", (long)n); }
+    int64_t w = 0;
+    int max_row = 0, max_col = 0;
+    double sum = 0.0;
+    for (int t = 0; t < last; ++t) {
+        const std::vector<cu2b_rating> &v = part[t];
+        if (!v.empty()) memcpy(out + w, v.data(), v.size() * sizeof(cu2b_rating));
+        for (const cu2b_rating &r : v) {  // sequential double sum, same order as util.cu:34
+            sum += r.rating;
+            max_row = std::max(max_row, r.user + 1);
+            max_col = std::max(max_col, r.item + 1);
+        }
+        w += (int64_t)v.size();
+    }
+    munmap((void *)base, size);
+    *ratings = out;
+    *n_out = n;
+    *rows = max_row;
+    *cols = max_col;
+    *global_bias = (float)(sum / (1.0 * (double)n));
+    return CU2B_OK;
+}
+
+extern "C" cu2b_status cu2b_build_csr(const cu2b_rating *r, int64_t n, int rows, int *indptr,
+                                      int *indices, float *data) {
+    if ((!r && n > 0) || !indptr || rows < 0 || n < 0 || n > INT32_MAX)
+        return cu2b_fail(CU2B_ERR_INVALID, "cu2b_build_csr: bad argument");
+    // Same contract as the reference: input grouped by ascending user id. We additionally
+    // reject input that violates it (the reference would loop forever / write out of bounds).
+    int next = 0;  // next indptr slot to fill
+    for (int64_t k = 0; k < n; ++k) {
+        int u = r[k].user;
+        if (u < 0 || u >= rows)
+            return cu2b_fail(CU2B_ERR_INVALID, "rating %ld: user id %d outside [0,%d)", (long)k, u, rows);
+        if (u + 1 < next)
+            return cu2b_fail(CU2B_ERR_INVALID, "rating %ld: ratings are not grouped by ascending user", (long)k);
+        while (next <= u) indptr[next++] = (int)k;
+        if (indices) indices[k] = r[k].item;
+        if (data) data[k] = r[k].rating;
+    }
+    while (next <= rows) indptr[next++] = (int)n;
+    return CU2B_OK;
+}
+
+extern "C" cu2b_status cu2b_read_array(const char *path, float **data, int *n_rows, int *n_cols) {
+    if (!path || !data) return cu2b_fail(CU2B_ERR_INVALID, "cu2b_read_array: null argument");
+    *data = nullptr;
+    FILE *f = fopen(path, "r");
+    if (!f) return cu2b_fail(CU2B_ERR_IO, "cannot open %s", path);  // reference returns nullptr
+    std::vector<float> nums;
+    int rows = 0, cols = 0;
+    char *line = nullptr;
+    size_t cap = 0;
+    ssize_t len;
+    while ((len = getline(&line, &cap, f)) >= 0) {
+        // getline(array_file, line) strips '\n'; then split on ',' and stof each piece.
+        if (len > 0 && line[len - 1] == '\n') line[--len] = 0;
+        char *p = line;
+        // std::getline on an empty stringstream yields no tokens; a line "a,b," yields 2
+        while (*p) {
+            char *comma = strchr(p, ',');
+            if (comma) *comma = 0;
+            char *e;
+            float v = strtof(p, &e);
+            if (e == p) {  // std::stof would throw std::invalid_argument
+                free(line);
+                fclose(f);
+                return cu2b_fail(CU2B_ERR_IO, "%s: not a number: '%s'", path, p);
+            }
+            nums.push_back(v);
+            ++cols;
+            if (!comma) break;
+            p = comma + 1;
+        }
+        ++rows;
+    }
+    free(line);
+    fclose(f);
+    float *out = (float *)malloc(std::max<size_t>(1, nums.size()) * sizeof(float));
+    if (!out) return cu2b_fail(CU2B_ERR_NOMEM, "out of memory");
+    if (!nums.empty()) memcpy(out, nums.data(), nums.size() * sizeof(float));
+    *data = out;
+    if (n_rows) *n_rows = rows;
+    if (n_cols) *n_cols = cols;  // accumulates over all rows, exactly like util.cu:61-66
+    return CU2B_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// writer: byte-identical to fprintf("%f") without calling it per element
+// ------------------------------------------------------------------------------------------
+namespace {
+// Appends the "%f" rendering of v (6 decimals, round-half-even on the exact binary value,
+// like glibc) to dst; returns the new end. dst must have >= 64 bytes of room.
+char *format_f(float v, char *dst) {
+    uint32_t bits;
+    memcpy(&bits, &v, 4);
+    uint32_t expo = (bits >> 23) & 0xff;
+    uint32_t frac = bits & 0x7fffff;
+    if (expo == 0xff || expo >= 127 + 40) {  // inf / nan / huge: rare, defer to libc
+        return dst + sprintf(dst, "%f", v);
+    }
+    if (bits >> 31) *dst++ = '-';
+    uint64_t m = expo ? (uint64_t)(frac | 0x800000u) : frac;
+    int e = (expo ? (int)expo : 1) - 127 - 23;  // value = m * 2^e
+    // scaled = round(m * 10^6 * 2^e) ; m*10^6 < 2^24 * 2^20 = 2^44
+    unsigned __int128 N = (unsigned __int128)m * 1000000u;
+    unsigned __int128 q;
+    if (e >= 0) {
+        q = N << e;  // e < 17 here because expo < 127+40
+    } else {
+        int sh = -e;
+        if (sh >= 100) {
+            q = 0;
+        } else {
+            q = N >> sh;
+            unsigned __int128 rem = N - (q << sh);
+            unsigned __int128 half = (unsigned __int128)1 << (sh - 1);
+            if (rem > half || (rem == half && (q & 1))) ++q;
+        }
+    }
+    uint64_t ip = (uint64_t)(q / 1000000u);
+    uint32_t fp = (uint32_t)(q % 1000000u);
+    char tmp[32];
+    int n = 0;
+    do { tmp[n++] = (char)('0' + ip % 10); ip /= 10; } while (ip);
+    while (n) *dst++ = tmp[--n];
+    *dst++ = '.';
+    for (int d = 5; d >= 0; --d) { dst[d] = (char)('0' + fp % 10); fp /= 10; }
+    return dst + 6;
+}
+}  // namespace
+
+extern "C" cu2b_status cu2b_write_csv(const char *path, const float *data, int rows, int cols) {
+    if (!path || (!data && rows > 0 && cols > 0) || rows < 0 || cols < 0)
+        return cu2b_fail(CU2B_ERR_INVALID, "cu2b_write_csv: bad argument");
+    FILE *fp = fopen(path, "w");
+    if (!fp) return cu2b_fail(CU2B_ERR_IO, "cannot create %s", path);
+    const int block = std::max(1, (1 << 16) / std::max(1, cols));  // rows per work item
+    const int nblocks = (rows + block - 1) / block;
+    const int nthreads = std::max(1, std::min(omp_get_max_threads(), nblocks));
+    // process `nthreads` blocks at a time, write them in order
+    std::vector<std::vector<char>> bufs(nthreads);
+    for (int b0 = 0; b0 < nblocks; b0 += nthreads) {
+        int nb = std::min(nthreads, nblocks - b0);
+#pragma omp parallel for num_threads(nthreads) schedule(static, 1)
+        for (int t = 0; t < nb; ++t) {
+            int r0 = (b0 + t) * block, r1 = std::min(rows, r0 + block);
+            std::vector<char> &buf = bufs[t];
+            buf.resize((size_t)(r1 - r0) * ((size_t)cols * 48 + 2) + 64);
+            char *p = buf.data();
+            for (int i = r0; i < r1; ++i) {
+                const float *row = data + (size_t)i * cols;
+                for (int j = 0; j < cols; ++j) {
+                    p = format_f(row[j], p);
+                    *p++ = (j + 1 < cols) ? ',' : '\n';
+                }
+                if (cols == 0) *p++ = '\n';
+            }
+            buf.resize((size_t)(p - buf.data()));
+        }
+        for (int t = 0; t < nb; ++t)
+            if (fwrite(bufs[t].data(), 1, bufs[t].size(), fp) != bufs[t].size()) {
+                fclose(fp);
+                return cu2b_fail(CU2B_ERR_IO, "short write to %s", path);
+            }
+    }
+    fclose(fp);
+    return CU2B_OK;
+}
+
+extern "C" cu2b_status cu2b_write_component(const char *parent_dir, const char *base,
+                                            const char *ext, const char *component,
+                                            const float *data, int rows, int cols, int factors) {
+    char filename[4096];
+    snprintf(filename, sizeof filename, "%s/%s_f%d_%s.%s", parent_dir, base, factors, component, ext);
+    return cu2b_write_csv(filename, data, rows, cols);
+}
+
+extern "C" void cu2b_init_normal(float *out, int64_t size, int n_factors, float mean,
+                                 float stddev, int seed) {
+    std::mt19937 generator(seed);
+    std::normal_distribution<float> distribution(mean, stddev / n_factors);
+    for (int64_t i = 0; i < size; ++i) out[i] = distribution(generator);
+}
+
+// ------------------------------------------------------------------------------------------
+// synthetic workload generator (tests / smoke / bench only)
+// ------------------------------------------------------------------------------------------
+namespace {
+inline uint64_t mix64(uint64_t x) {  // splitmix64 finaliser
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+inline uint64_t h3(uint64_t seed, uint64_t stream, uint64_t idx) {
+    return mix64(mix64(seed ^ (stream * 0xD1342543DE82EF95ull)) + idx);
+}
+inline double u01(uint64_t h) { return ((h >> 11) + 0.5) * (1.0 / 9007199254740992.0); }
+inline float gauss(uint64_t seed, uint64_t stream, uint64_t idx) {  // Box-Muller, one value
+    double a = u01(h3(seed, stream, 2 * idx)), b = u01(h3(seed, stream, 2 * idx + 1));
+    return (float)(sqrt(-2.0 * log(a)) * cos(6.283185307179586 * b));
+}
+enum : uint64_t { S_DEG = 1, S_PU = 2, S_QI = 3, S_BU = 4, S_BI = 5, S_POS = 6, S_NOISE = 7, S_SPLIT = 8, S_PERM = 9 };
+}  // namespace
+
+extern "C" cu2b_status cu2b_synth_ratings(int users, int items, int64_t target, int rank,
+                                          float noise, int integer_ratings, float test_fraction,
+                                          uint64_t seed, cu2b_rating *train, int64_t *n_train,
+                                          cu2b_rating *test, int64_t *n_test) {
+    if (users <= 0 || items <= 0 || target < users || rank <= 0 || rank > 64 || !n_train || !n_test)
+        return cu2b_fail(CU2B_ERR_INVALID, "cu2b_synth_ratings: bad argument");
+    // user activity ~ log-normal(sigma 1), at least 1, at most items/2
+    std::vector<double> w(users);
+    double wsum = 0;
+    for (int u = 0; u < users; ++u) { w[u] = exp(1.0 * (double)gauss(seed, S_DEG, (uint64_t)u)); wsum += w[u]; }
+    const int cap = std::max(1, items / 2);
+    std::vector<int> deg(users);
+    double scale = (double)target / wsum;
+    for (int pass = 0; pass < 6; ++pass) {  // re-scale so the capped degrees still sum to target
+        double tot = 0, free_w = 0;
+        for (int u = 0; u < users; ++u) {
+            double d = std::min<double>(cap, std::max(1.0, w[u] * scale));
+            tot += d;
+            if (d > 1.0 && d < cap) free_w += w[u] * scale;
+        }
+        if (free_w <= 0) break;
+        scale *= 1.0 + ((double)target - tot) / free_w;
+    }
+    auto assign_degrees = [&](double sc) {
+        for (int u = 0; u < users; ++u) {
+            double d = std::min<double>(cap, std::max(1.0, w[u] * sc));
+            int di = (int)d;
+            if (u01(h3(seed, S_DEG + 100, (uint64_t)u)) < d - di) ++di;
+            deg[u] = std::min(cap, std::max(1, di));
+        }
+    };
+    assign_degrees(scale);
+    // item popularity ~ Zipf-Mandelbrot: weight(rank) = 1 / (rank + c), c = items/300 + 1
+    std::vector<double> cdf(items);
+    {
+        double c = items / 300.0 + 1.0, acc = 0;
+        for (int i = 0; i < items; ++i) { acc += 1.0 / (i + c); cdf[i] = acc; }
+        for (int i = 0; i < items; ++i) cdf[i] /= acc;
+        cdf[items - 1] = 1.0;
+    }
+    // popularity rank -> item id : pseudo-random permutation
+    std::vector<int> perm(items);
+    {
+        std::vector<std::pair<uint64_t, int>> keys(items);
+        for (int i = 0; i < items; ++i) keys[i] = {h3(seed, S_PERM, (uint64_t)i), i};
+        std::sort(keys.begin(), keys.end());
+        for (int i = 0; i < items; ++i) perm[i] = keys[i].second;
+    }
+    // ground-truth item factors / biases (indexed by item id)
+    const float fstd = powf((float)rank, -0.25f);
+    std::vector<float> Qs((size_t)items * rank), bi(items);
+    for (int i = 0; i < items; ++i) {
+        for (int f = 0; f < rank; ++f) Qs[(size_t)i * rank + f] = fstd * gauss(seed, S_QI, (uint64_t)i * rank + f);
+        bi[i] = 0.3f * gauss(seed, S_BI, (uint64_t)i);
+    }
+    // pass 1: per user, the de-duplicated item list length and its train/test split
+    std::vector<int64_t> off_tr(users + 1), off_te(users + 1);
+    auto gen_user = [&](int u, cu2b_rating *tr, cu2b_rating *te, int64_t *ntr, int64_t *nte) {
+        const int d = deg[u];
+        float pu[64];
+        for (int f = 0; f < rank; ++f) pu[f] = fstd * gauss(seed, S_PU, (uint64_t)u * rank + f);
+        const float bu = 0.3f * gauss(seed, S_BU, (uint64_t)u);
+        int64_t a = 0, b = 0;
+        int prev = -1;
+        const uint64_t ubase = (uint64_t)u << 20;  // d <= items/2 < 2^20 for our shapes
+        for (int j = 0; j < d; ++j) {
+            double x = (j + u01(h3(seed, S_POS, ubase + j))) / d;  // stratified position
+            int rk = (int)(std::lower_bound(cdf.begin(), cdf.end(), x) - cdf.begin());
+            if (rk >= items) rk = items - 1;
+            if (rk == prev) continue;  // adjacent duplicate (popular head) -> drop
+            prev = rk;
+            const int it = perm[rk];
+            const bool to_test = (a > 0) && (u01(h3(seed, S_SPLIT, ubase + j)) < test_fraction);
+            cu2b_rating *dst = to_test ? te : tr;
+            if (dst) {
+                const float *q = &Qs[(size_t)it * rank];
+                float v = 3.5f + bu + bi[it];
+                for (int f = 0; f < rank; ++f) v += pu[f] * q[f];
+                v += noise * gauss(seed, S_NOISE, ubase + j);
+                v = integer_ratings ? roundf(v) : roundf(v * 2.0f) * 0.5f;
+                v = std::min(5.0f, std::max(integer_ratings ? 1.0f : 0.5f, v));
+                cu2b_rating r = {u, it, v};
+                dst[to_test ? b : a] = r;
+            }
+            if (to_test) ++b; else ++a;
+        }
+        *ntr = a;
+        *nte = b;
+    };
+    if (items >= (1 << 21)) return cu2b_fail(CU2B_ERR_UNSUPPORTED, "synthetic generator supports < 2^21 items");
+    off_tr[0] = off_te[0] = 0;
+    {
+        // Dropping adjacent duplicates shrinks heavy users; re-scale the degrees until the
+        // de-duplicated total is within 0.5 % of the target (counting passes only).
+        std::vector<int64_t> ca(users), cb(users);
+        for (int pass = 0; pass < 6; ++pass) {
+#pragma omp parallel for schedule(dynamic, 256)
+            for (int u = 0; u < users; ++u) gen_user(u, nullptr, nullptr, &ca[u], &cb[u]);
+            int64_t tot = 0;
+            for (int u = 0; u < users; ++u) tot += ca[u] + cb[u];
+            if (pass == 5 || llabs(tot - target) <= target / 200) break;
+            scale *= (double)target / (double)tot;
+            assign_degrees(scale);
+        }
+        for (int u = 0; u < users; ++u) { off_tr[u + 1] = off_tr[u] + ca[u]; off_te[u + 1] = off_te[u] + cb[u]; }
+    }
+    const bool count_only = (train == nullptr);
+    if (!count_only) {
+        if (*n_train < off_tr[users] || *n_test < off_te[users])
+            return cu2b_fail(CU2B_ERR_INVALID, "cu2b_synth_ratings: buffers too small (%ld/%ld needed)",
+                             (long)off_tr[users], (long)off_te[users]);
+#pragma omp parallel for schedule(dynamic, 256)
+        for (int u = 0; u < users; ++u) {
+            int64_t a, b;
+            gen_user(u, train + off_tr[u], test ? test + off_te[u] : nullptr, &a, &b);
+        }
+    }
+    *n_train = off_tr[users];
+    *n_test = off_te[users];
+    return CU2B_OK;
+}

@@ -1,0 +1,199 @@
+// Single-pass RMSE / MAE (replaces loss_kernel + two total_loss_kernel launches + host sums,
+// loss.cu:19-35,58-128,150-200). One pass over the rating triplets: the residual is formed
+// with the same lane layout / shuffle reduction as the SGD kernel and accumulated straight
+// into double precision |err| and err^2 sums; nothing is written per rating unless the caller
+// asks for the residual vector (the calculate_loss_gpu contract).
+//
+// Determinism: chunks are assigned statically (chunk = blockIdx.x + i * gridDim.x), lanes and
+// warps are reduced in a fixed order, per-CTA partials are summed by finalize kernels in a
+// fixed order => bitwise reproducible sums for a given model.
+#ifndef CU2B_LOSS_KERNELS_CUH_
+#define CU2B_LOSS_KERNELS_CUH_
+
+#include "sgd_kernels.cuh"
+
+namespace cu2b {
+
+struct LossParams {
+    StreamView sv;  // flat stream over the matrix' COO triplets
+    const float *P, *Q, *user_bias, *item_bias;
+    int kp;
+    float mu;
+    double *partials;  // [gridDim.x][2] = {sum err^2, sum |err|}
+    float *err_out;    // optional residual vector (stream order), may be nullptr
+};
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+template <int L, int V>
+__global__ void __launch_bounds__(kThreads)
+mf_loss_fused(const LossParams p) {
+    __shared__ StreamSmem sm;
+    __shared__ double wsum[kConsumerWarps][2];
+    pipe_init(sm);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == kConsumerWarps) {
+        if (lane == 0) {
+            long long next = blockIdx.x;
+            pipe_produce(
+                sm, p.sv,
+                [&]() -> long long {
+                    const long long c = next;
+                    next += gridDim.x;
+                    return c < p.sv.num_chunks ? c : -1LL;
+                },
+                [](long long, int) {});
+        }
+        return;
+    }
+    constexpr int G = 32 / L;
+    const int g = lane / L, l = lane % L;
+    const int vecs = p.kp >> 2;
+    double sse = 0.0, sae = 0.0;
+    for (int it = 0;; ++it) {
+        const int s = it % kStages;
+        mbar_wait(&sm.full[s], (it / kStages) & 1);
+        const int cnt = sm.count[s];
+        if (cnt < 0) break;
+        const long long c = sm.chunk_id[s];
+        for (int base = warp * G; base < cnt; base += kConsumerWarps * G) {
+            const int j = base + g;
+            const bool ok = j < cnt;
+            const cu2b_rating rt = sm.stage[s][ok ? j : 0];
+            const float4 *prow = reinterpret_cast<const float4 *>(p.P + (size_t)rt.user * p.kp);
+            const float4 *qrow = reinterpret_cast<const float4 *>(p.Q + (size_t)rt.item * p.kp);
+            float acc = 0.f;
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const int idx = v * L + l;
+                if (ok && idx < vecs) {
+                    const float4 a = __ldg(prow + idx), b = __ldg(qrow + idx);
+                    acc = __fmaf_rn(a.x, b.x, acc);
+                    acc = __fmaf_rn(a.y, b.y, acc);
+                    acc = __fmaf_rn(a.z, b.z, acc);
+                    acc = __fmaf_rn(a.w, b.w, acc);
+                }
+            }
+            const float ub = ok ? __ldg(p.user_bias + rt.user) : 0.f;
+            const float ib = ok ? __ldg(p.item_bias + rt.item) : 0.f;
+            const float dot = group_sum<L>(acc);
+            const float pred = __fadd_rn(__fadd_rn(__fadd_rn(p.mu, ub), ib), dot);
+            const float err = __fsub_rn(rt.rating, pred);
+            if (ok && l == 0) {
+                sse += (double)err * (double)err;
+                sae += (double)fabsf(err);
+                if (p.err_out) p.err_out[c * p.sv.chunk + j] = err;  // flat stream: seg_pitch unused
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[s]);
+    }
+    sse = warp_sum_d(sse);
+    sae = warp_sum_d(sae);
+    if (lane == 0) { wsum[warp][0] = sse; wsum[warp][1] = sae; }
+    asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory");  // consumers only
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < kConsumerWarps; ++w) { a += wsum[w][0]; b += wsum[w][1]; }
+        p.partials[2 * blockIdx.x] = a;
+        p.partials[2 * blockIdx.x + 1] = b;
+    }
+}
+
+// get_error_metrics_gpu contract (loss.cu:196-200) on an explicit error vector.
+__global__ void __launch_bounds__(256)
+error_metrics_kernel(const float *__restrict__ err, long long n, double *partials) {
+    __shared__ double wsum[8][2];
+    double sse = 0.0, sae = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float e = __ldg(err + i);
+        sse += (double)e * (double)e;
+        sae += (double)fabsf(e);
+    }
+    sse = warp_sum_d(sse);
+    sae = warp_sum_d(sae);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { wsum[warp][0] = sse; wsum[warp][1] = sae; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < 8; ++w) { a += wsum[w][0]; b += wsum[w][1]; }
+        partials[2 * blockIdx.x] = a;
+        partials[2 * blockIdx.x + 1] = b;
+    }
+}
+
+// Device-resident training state (replaces the host variables of training.cu:95-104 and the
+// nine cudaMemcpyToSymbol calls per learning-rate change, config.cu:24-35).
+struct DevState {
+    float lr;
+    int current_patience;   // training.cu:103 (int copy of the float cfg->patience)
+    int patience0;
+    float lr_decay;
+    float validation_rmse;  // training.cu:102 (starts at FLT_MAX)
+    int n_log;
+    int log_cap;
+    int pad;
+    double sums[4];         // last evaluated {train sse, train sae, test sse, test sae}
+};
+
+// Sums the per-CTA partials of one matrix in a fixed order. One block of 256 threads.
+__device__ __forceinline__ void reduce_partials(const double *partials, int nblk, double *out2,
+                                                double (*sh)[2]) {
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < nblk; i += blockDim.x) { a += partials[2 * i]; b += partials[2 * i + 1]; }
+    sh[threadIdx.x][0] = a;
+    sh[threadIdx.x][1] = b;
+    __syncthreads();
+    for (int w = blockDim.x / 2; w >= 1; w >>= 1) {
+        if ((int)threadIdx.x < w) { sh[threadIdx.x][0] += sh[threadIdx.x + w][0]; sh[threadIdx.x][1] += sh[threadIdx.x + w][1]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out2[0] = sh[0][0]; out2[1] = sh[0][1]; }
+    __syncthreads();
+}
+
+// The check step of training.cu:118-158 on the device: metrics from the partial sums, patience
+// bookkeeping, learning-rate decay, one log row. apply_schedule == 0 => evaluation only.
+__global__ void __launch_bounds__(256)
+loss_finalize_kernel(DevState *st, const double *part_train, int nblk_train, long long n_train,
+                     const double *part_test, int nblk_test, long long n_test, int iteration,
+                     int apply_schedule, cu2b_metrics *log) {
+    __shared__ double sh[256][2];
+    __shared__ double tot[4];
+    reduce_partials(part_train, nblk_train, &tot[0], sh);
+    reduce_partials(part_test, nblk_test, &tot[2], sh);
+    if (threadIdx.x == 0) {
+        st->sums[0] = tot[0]; st->sums[1] = tot[1]; st->sums[2] = tot[2]; st->sums[3] = tot[3];
+        const float train_rmse = (float)sqrt(tot[0] / (double)n_train);
+        const float train_mae = (float)(tot[1] / (double)n_train);
+        const float test_rmse = (float)sqrt(tot[2] / (double)n_test);
+        const float test_mae = (float)(tot[3] / (double)n_test);
+        if (apply_schedule) {
+            const float last = st->validation_rmse;
+            st->validation_rmse = test_rmse;
+            if (last < test_rmse) st->current_patience--;
+            if (st->current_patience <= 0) {
+                st->current_patience = st->patience0;
+                st->lr = st->lr * st->lr_decay;
+            }
+        }
+        if (log && st->n_log < st->log_cap) {
+            cu2b_metrics m;
+            m.iteration = iteration;
+            m.train_mae = train_mae; m.train_rmse = train_rmse;
+            m.test_mae = test_mae; m.test_rmse = test_rmse;
+            m.learning_rate = st->lr;
+            log[st->n_log] = m;
+        }
+        if (log) st->n_log++;
+    }
+}
+
+}  // namespace cu2b
+#endif  // CU2B_LOSS_KERNELS_CUH_

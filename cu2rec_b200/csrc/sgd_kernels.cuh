@@ -1,0 +1,230 @@
+// Hogwild SGD update kernel (replaces the reference's sgd_update, sgd.cu:22-75, one thread per
+// user walking a whole factor row) and the per-user sampler (replaces initCurand + the
+// curand_uniform draw, sgd.cu:11-16,36-37).
+//
+// Mapping: a group of L lanes owns one rating; each lane holds V float4 slices of the P row
+// and of the Q row (L*V*4 >= kp). k=128 -> L=32,V=1: one 128-bit load per lane per row, the
+// whole warp touches one contiguous 512-byte row. Smaller k packs 32/L ratings into a warp.
+// The dot product is reduced with an xor butterfly over the L lanes (every lane ends with the
+// same value), the rating error is formed once, and both rows are written back in place.
+// Update arithmetic is the unfused op sequence of mf_sequential.cu:129-141 so that a
+// sequential replay on the CPU reproduces it bit for bit (oracle flavour KERNEL).
+#ifndef CU2B_SGD_KERNELS_CUH_
+#define CU2B_SGD_KERNELS_CUH_
+
+#include "stream_pipe.cuh"
+
+namespace cu2b {
+
+struct SgdParams {
+    StreamView sv;              // the update stream (device memory)
+    float *P, *Q, *user_bias, *item_bias;
+    int kp;                     // row pitch in floats (multiple of 4)
+    float mu;
+    const float *lr;            // device scalar: current learning rate (decayed on device)
+    float P_reg, Q_reg, ub_reg, ib_reg;
+    int is_train;               // 0 => Q / item_bias frozen
+    unsigned long long *chunk_counter;  // dynamic chunk scheduler, zeroed before launch
+    // Per-user mode ordering gate: gate[j] = number of segments (reference iterations) whose
+    // chunk j is complete. Chunk j of segment a starts only when gate[j] == a, so a user's
+    // updates from consecutive iterations never overlap (the reference separates iterations
+    // by kernel launches, training.cu:107-112). nullptr => ungated flat stream.
+    int *gate;
+    int seg0;                   // absolute index of segment 0 of this launch
+    int serial;                 // 1 => a single group processes the stream strictly in order
+};
+
+#define PHILOX_TAG 0x53474431u
+#define PHILOX_KEY1 0x43553242u
+
+__device__ __forceinline__ uint32_t philox4x32_10_x(uint32_t c0, uint32_t c1, uint32_t c2,
+                                                    uint32_t c3, uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+        uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return c0;
+}
+
+// One draw per (iteration, active user): thread i handles draw i of n_iter * n_active and
+// writes it to segment t = i / n_active of the update stream (segment pitch seg_pitch).
+__global__ void __launch_bounds__(256)
+sample_per_user_kernel(const int *__restrict__ indptr, const cu2b_rating *__restrict__ coo,
+                       const int *__restrict__ active_users, int n_active, uint32_t seed,
+                       int iter0, long long n_draws, cu2b_rating *__restrict__ out,
+                       long long seg_pitch) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n_draws; i += stride) {
+        const int t = (int)(i / n_active);
+        const int a = (int)(i - (long long)t * n_active);
+        const int u = __ldg(&active_users[a]);
+        const int lo = __ldg(&indptr[u]), hi = __ldg(&indptr[u + 1]);
+        const uint32_t r = philox4x32_10_x((uint32_t)u, (uint32_t)(iter0 + t), 0u, PHILOX_TAG, seed, PHILOX_KEY1);
+        const int j = lo + (int)__umulhi(r, (uint32_t)(hi - lo));
+        cu2b_rating v;
+        v.user = u;
+        v.item = __ldg(&coo[j].item);
+        v.rating = __ldg(&coo[j].rating);
+        out[(long long)t * seg_pitch + a] = v;
+    }
+}
+
+template <int L>
+__device__ __forceinline__ float group_sum(float a) {
+#pragma unroll
+    for (int off = L / 2; off >= 1; off >>= 1) a = a + __shfl_xor_sync(0xffffffffu, a, off);
+    return a;
+}
+
+// Processes UNR ratings (one per slot) for this lane's group. `ok[x]` false => slot idle.
+template <int L, int V, int UNR>
+__device__ __forceinline__ void sgd_update_slots(const SgdParams &p, const cu2b_rating *rt,
+                                                 const bool *ok, int l, int vecs, float lr) {
+    float4 pv[UNR][V], qv[UNR][V];
+    float ub[UNR], ib[UNR];
+    float4 *prow[UNR], *qrow[UNR];
+#pragma unroll
+    for (int x = 0; x < UNR; ++x) {
+        prow[x] = reinterpret_cast<float4 *>(p.P + (size_t)rt[x].user * p.kp);
+        qrow[x] = reinterpret_cast<float4 *>(p.Q + (size_t)rt[x].item * p.kp);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const int idx = v * L + l;
+            if (ok[x] && idx < vecs) {
+                pv[x][v] = __ldcg(prow[x] + idx);
+                qv[x][v] = __ldcg(qrow[x] + idx);
+            } else {
+                pv[x][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                qv[x][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        ub[x] = ok[x] ? __ldcg(p.user_bias + rt[x].user) : 0.f;
+        ib[x] = ok[x] ? __ldcg(p.item_bias + rt[x].item) : 0.f;
+    }
+#pragma unroll
+    for (int x = 0; x < UNR; ++x) {
+        float acc = 0.f;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            acc = __fmaf_rn(pv[x][v].x, qv[x][v].x, acc);
+            acc = __fmaf_rn(pv[x][v].y, qv[x][v].y, acc);
+            acc = __fmaf_rn(pv[x][v].z, qv[x][v].z, acc);
+            acc = __fmaf_rn(pv[x][v].w, qv[x][v].w, acc);
+        }
+        const float dot = group_sum<L>(acc);
+        const float pred = __fadd_rn(__fadd_rn(__fadd_rn(p.mu, ub[x]), ib[x]), dot);
+        const float err = __fsub_rn(rt[x].rating, pred);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const int idx = v * L + l;
+            const float4 a = pv[x][v], b = qv[x][v];
+            float4 na, nb;
+            na.x = __fadd_rn(a.x, __fmul_rn(lr, __fsub_rn(__fmul_rn(err, b.x), __fmul_rn(p.P_reg, a.x))));
+            na.y = __fadd_rn(a.y, __fmul_rn(lr, __fsub_rn(__fmul_rn(err, b.y), __fmul_rn(p.P_reg, a.y))));
+            na.z = __fadd_rn(a.z, __fmul_rn(lr, __fsub_rn(__fmul_rn(err, b.z), __fmul_rn(p.P_reg, a.z))));
+            na.w = __fadd_rn(a.w, __fmul_rn(lr, __fsub_rn(__fmul_rn(err, b.w), __fmul_rn(p.P_reg, a.w))));
+            nb.x = __fadd_rn(b.x, __fmul_rn(lr, __fsub_rn(__fmul_rn(err, a.x), __fmul_rn(p.Q_reg, b.x))));
+            nb.y = __fadd_rn(b.y, __fmul_rn(lr, __fsub_rn(__fmul_rn(err, a.y), __fmul_rn(p.Q_reg, b.y))));
+            nb.z = __fadd_rn(b.z, __fmul_rn(lr, __fsub_rn(__fmul_rn(err, a.z), __fmul_rn(p.Q_reg, b.z))));
+            nb.w = __fadd_rn(b.w, __fmul_rn(lr, __fsub_rn(__fmul_rn(err, a.w), __fmul_rn(p.Q_reg, b.w))));
+            if (ok[x] && idx < vecs) {
+                __stcg(prow[x] + idx, na);
+                if (p.is_train) __stcg(qrow[x] + idx, nb);
+            }
+        }
+        if (ok[x] && l == 0) {
+            __stcg(p.user_bias + rt[x].user,
+                   __fadd_rn(ub[x], __fmul_rn(lr, __fsub_rn(err, __fmul_rn(p.ub_reg, ub[x])))));
+            if (p.is_train)
+                __stcg(p.item_bias + rt[x].item,
+                       __fadd_rn(ib[x], __fmul_rn(lr, __fsub_rn(err, __fmul_rn(p.ib_reg, ib[x])))));
+        }
+    }
+}
+
+template <int L, int V, int UNR>
+__global__ void __launch_bounds__(kThreads)
+mf_sgd_hogwild(const SgdParams p) {
+    __shared__ StreamSmem sm;
+    pipe_init(sm);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == kConsumerWarps) {  // producer warp
+        if (lane == 0) {
+            pipe_produce(
+                sm, p.sv,
+                [&]() -> long long {
+                    const unsigned long long c = atomicAdd(p.chunk_counter, 1ULL);
+                    return c < (unsigned long long)p.sv.num_chunks ? (long long)c : -1LL;
+                },
+                [&](long long seg, int j) {
+                    if (p.gate) {
+                        const int want = p.seg0 + (int)seg;
+                        while (ld_acquire_gpu(p.gate + j) < want) __nanosleep(64);
+                    }
+                });
+        }
+        return;
+    }
+    constexpr int G = 32 / L;  // ratings per warp pass
+    const int g = lane / L, l = lane % L;
+    const int vecs = p.kp >> 2;
+    const float lr = __ldg(p.lr);
+    const int groups = kConsumerWarps * G;
+    for (int it = 0;; ++it) {
+        const int s = it % kStages;
+        mbar_wait(&sm.full[s], (it / kStages) & 1);
+        const int cnt = sm.count[s];
+        if (cnt < 0) break;
+        if (p.serial) {
+            // strictly sequential replay (grid of one CTA): warp 0 / group 0 applies one rating
+            // at a time; __syncwarp orders lane 0's bias store before the next rating's loads.
+            if (warp == 0) {
+                const bool ok = (g == 0);
+                for (int j = 0; j < cnt; ++j) {
+                    const cu2b_rating rt = sm.stage[s][j];
+                    sgd_update_slots<L, V, 1>(p, &rt, &ok, l, vecs, lr);
+                    __syncwarp();
+                }
+            }
+        } else {
+            // all lanes of a warp run the same trip count (the shuffles are warp-wide)
+            for (int base = warp * G; base < cnt; base += groups * UNR) {
+                cu2b_rating rt[UNR];
+                bool ok[UNR];
+#pragma unroll
+                for (int x = 0; x < UNR; ++x) {
+                    const int j = base + x * groups + g;
+                    ok[x] = j < cnt;
+                    rt[x] = sm.stage[s][ok[x] ? j : 0];
+                }
+                sgd_update_slots<L, V, UNR>(p, rt, ok, l, vecs, lr);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            if (p.gate) {
+                // last consumer warp out publishes "chunk j of this segment is complete"
+                __threadfence();
+                if (atomicAdd(&sm.done[s], 1) == kConsumerWarps - 1) {
+                    sm.done[s] = 0;
+                    const long long c = sm.chunk_id[s];
+                    const long long seg = c / p.sv.chunks_per_seg;
+                    const int j = (int)(c - seg * p.sv.chunks_per_seg);
+                    __threadfence();
+                    st_release_gpu(p.gate + j, p.seg0 + (int)seg + 1);
+                }
+            }
+            mbar_arrive(&sm.empty[s]);
+        }
+    }
+}
+
+}  // namespace cu2b
+#endif  // CU2B_SGD_KERNELS_CUH_

@@ -1,0 +1,229 @@
+/* cu2b.h -- C ABI of libcu2b.so: a B200-native (sm_100a) drop-in for the SGD
+ * matrix-factorisation training path of nickgreenquist/cu2rec.
+ *
+ * Plain C: pointers and sizes only, integer status codes, no exceptions and no
+ * allocation ownership crossing the boundary except through cu2b_free(). Each entry
+ * point cites the reference interface it replaces as file:line relative to the
+ * reference repository's matrix_factorization/ directory.
+ *
+ * Conventions
+ *   - every function returning cu2b_status returns CU2B_OK (0) on success; on failure
+ *     cu2b_last_error() returns a thread-local human readable message
+ *     (reference: CHECK_CUDA throws std::runtime_error, util.h:27-34);
+ *   - "host" pointers are ordinary process memory; entry points ending in _dev take
+ *     device pointers on the current CUDA device;
+ *   - factor matrices are dense row-major [rows x n_factors] float32 (matrix.h:20-28),
+ *     ids are 0-based int32 (util.cu:31), ratings float32;
+ *   - there is NO CPU fallback: if the CUDA device or the sm_100a image is unavailable the
+ *     call fails with CU2B_ERR_CUDA.
+ */
+#ifndef CU2B_H_
+#define CU2B_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CU2B_VERSION 100
+
+typedef enum cu2b_status {
+    CU2B_OK = 0,
+    CU2B_ERR_INVALID = 1,     /* bad argument */
+    CU2B_ERR_IO = 2,          /* file could not be opened / parsed */
+    CU2B_ERR_CUDA = 3,        /* CUDA runtime error, no device, wrong architecture */
+    CU2B_ERR_NOMEM = 4,
+    CU2B_ERR_UNSUPPORTED = 5  /* e.g. n_factors > 512 */
+} cu2b_status;
+
+const char *cu2b_last_error(void);
+int cu2b_version(void);
+void cu2b_free(void *p); /* releases memory returned by cu2b_read_csv / cu2b_read_array */
+
+/* ------------------------------------------------------------------------------------
+ * Hyper-parameters. Mirrors config::Config (config.h:20-58) field for field; the
+ * __constant__ mirror (config.h:9-18, config.cu:24-48) is replaced by kernel parameters.
+ * Fields after learning_rate_decay are extensions with reference-neutral defaults.
+ * ---------------------------------------------------------------------------------- */
+enum { CU2B_MODE_HOGWILD = 0, CU2B_MODE_DETERMINISTIC = 1 };
+enum { CU2B_SAMPLER_PER_USER = 0, CU2B_SAMPLER_PER_RATING = 1 };
+
+typedef struct cu2b_config {
+    int cur_iterations;        /* config.h:23 */
+    int total_iterations;      /* config.h:25  default 5000 */
+    int n_factors;             /* config.h:27  default 50 */
+    float learning_rate;       /* config.h:29  default 0.01 */
+    int seed;                  /* config.h:31  default 42 (sampler seed, sgd.cu:11-16) */
+    float P_reg;               /* config.h:33  default 0.02 */
+    float Q_reg;               /* config.h:35 */
+    float user_bias_reg;       /* config.h:37 */
+    float item_bias_reg;       /* config.h:39 */
+    int is_train;              /* config.h:41  0 => Q and item_bias frozen (predict.cu:105) */
+    int n_threads;             /* config.h:43  kept for file/print compatibility; unused */
+    int check_error;           /* config.h:45  default 500 */
+    float patience;            /* config.h:48  default 2 */
+    float learning_rate_decay; /* config.h:51  default 0.2 */
+    /* extensions */
+    int mode;     /* CU2B_MODE_*: Hogwild (default) or deterministic conflict-free blocks */
+    int sampler;  /* CU2B_SAMPLER_*: per_user = the reference's one-rating-per-user-per-
+                     iteration distribution (sgd.cu:27-37, default); per_rating = shuffled
+                     pass over the rating list */
+    int n_blocks; /* deterministic mode: B of the BxB block grid, 0 = automatic */
+    int n_gpus;   /* DSGD width, 0/1 = single GPU */
+} cu2b_config;
+
+void cu2b_config_default(cu2b_config *cfg);
+/* config.cu:7-13: nine whitespace separated positional tokens; a short file keeps defaults.
+ * Optional tokens 10.. (n_threads patience learning_rate_decay check_error mode sampler
+ * n_blocks n_gpus) are an add-only extension (config.h TODO / create_config.py:16-17). */
+cu2b_status cu2b_config_read(const char *path, cu2b_config *cfg);
+/* config.cu:15-22: writes the nine reference tokens on one line. */
+cu2b_status cu2b_config_write(const char *path, const cu2b_config *cfg);
+/* config.cu:50-64 print_config: formats the same block of lines into buf; returns the
+ * length that was (or would have been) written. */
+int cu2b_config_format(const cu2b_config *cfg, char *buf, int cap);
+
+/* ------------------------------------------------------------------------------------
+ * Ratings IO (host side).
+ * ---------------------------------------------------------------------------------- */
+typedef struct cu2b_rating { /* util.h:19-24 struct Rating; also the device stream element */
+    int32_t user;
+    int32_t item;
+    float rating;
+} cu2b_rating;
+
+/* util.cu:17-45 readCSV: header line skipped, rows "int <c> int <c> float", 1-based ids stored
+ * 0-based, *rows = max userId, *cols = max itemId, *global_bias = mean rating (double sum).
+ * *ratings is allocated by the library (cu2b_free). */
+cu2b_status cu2b_read_csv(const char *path, cu2b_rating **ratings, int64_t *n, int *rows,
+                          int *cols, float *global_bias);
+/* util.cu:152-179 createSparseMatrix (host part): ratings grouped by ascending user -> CSR;
+ * missing users repeat indptr. indptr has rows+1 entries. */
+cu2b_status cu2b_build_csr(const cu2b_rating *ratings, int64_t n, int rows, int *indptr,
+                           int *indices, float *data);
+/* util.cu:52-76 read_array: comma separated float matrix; *n_cols accumulates over all rows
+ * exactly like the reference (util.cu:61-66), *n_elems is the element count. */
+cu2b_status cu2b_read_array(const char *path, float **data, int *n_rows, int *n_cols);
+/* util.cu:86-97 writeCSV: "%f" text, comma separated, one matrix row per line. */
+cu2b_status cu2b_write_csv(const char *path, const float *data, int rows, int cols);
+/* util.cu:99-103 writeToFile: <parent>/<base>_f<factors>_<component>.<ext>. */
+cu2b_status cu2b_write_component(const char *parent_dir, const char *base, const char *ext,
+                                 const char *component, const float *data, int rows, int cols,
+                                 int factors);
+/* util.cu:124-144 initialize_normal_array: mt19937(seed), N(mean, stddev / n_factors). */
+void cu2b_init_normal(float *out, int64_t size, int n_factors, float mean, float stddev,
+                      int seed);
+
+/* Synthetic low-rank-plus-noise ratings of a given shape; used by the
+ * tests, smoke and bench only. Rows come out grouped by ascending user, ids 0-based, every
+ * user has >= 1 train rating. Two calls: with train == NULL it only reports the counts. */
+cu2b_status cu2b_synth_ratings(int users, int items, int64_t target_ratings, int rank,
+                               float noise, int integer_ratings, float test_fraction,
+                               uint64_t seed, cu2b_rating *train, int64_t *n_train,
+                               cu2b_rating *test, int64_t *n_test);
+
+/* ------------------------------------------------------------------------------------
+ * CSR view (matrix.h:11-19 CudaCSRMatrix). on_device selects host or device pointers.
+ * ---------------------------------------------------------------------------------- */
+typedef struct cu2b_csr {
+    int rows, cols, nonzeros;
+    const int *indptr;  /* rows + 1 */
+    const int *indices; /* nonzeros */
+    const float *data;  /* nonzeros */
+    int on_device;
+} cu2b_csr;
+
+/* ------------------------------------------------------------------------------------
+ * Kernel-level entry points, host buffers in / host buffers out (copies inside).
+ * ---------------------------------------------------------------------------------- */
+/* loss.cu:40-49 calculate_loss_gpu + loss.cu:196-200 get_error_metrics_gpu in ONE pass:
+ * mae = sum|err|/n, rmse = sqrt(sum err^2/n), double accumulation, float results. */
+cu2b_status cu2b_loss(const cu2b_csr *m, const float *P, const float *Q, const float *user_bias,
+                      const float *item_bias, float global_bias, int n_factors, float *mae,
+                      float *rmse);
+/* loss.cu:40-49 calculate_loss_gpu: err[i] = data[i] - prediction(i). */
+cu2b_status cu2b_residuals(const cu2b_csr *m, const float *P, const float *Q,
+                           const float *user_bias, const float *item_bias, float global_bias,
+                           int n_factors, float *err);
+/* loss.cu:196-200 get_error_metrics_gpu on an explicit error vector. */
+cu2b_status cu2b_error_metrics(const float *err, int64_t n, float *mae, float *rmse);
+/* sgd.cu:27-37 sampling step only: for iterations [iter0, iter0 + n_iter) one uniformly drawn
+ * rating per user that has any, ascending user order. out must hold n_iter * (active users). */
+cu2b_status cu2b_sample_per_user(const cu2b_csr *m, int seed, int iter0, int n_iter,
+                                 cu2b_rating *out, int64_t *n_out);
+/* sgd.cu:40-72 update arithmetic (in place Q / item_bias as mf_sequential.cu:114-141) applied
+ * to an explicit stream of ratings. order: 0 = Hogwild (parallel, racy by design),
+ * 1 = strictly sequential in stream order (one update in flight; for bit-exact checks). */
+cu2b_status cu2b_sgd_apply(const cu2b_rating *stream, int64_t n, float *P, int rows, float *Q,
+                           int cols, float *user_bias, float *item_bias, float global_bias,
+                           const cu2b_config *cfg, int order);
+/* Deterministic conflict-free mode: one pass over the ratings in the block-diagonal schedule
+ * (B x B blocks, round s runs blocks (b,(b+s) mod B) concurrently, each block serially). The
+ * result equals a sequential replay in round-major / user-block / original order. */
+cu2b_status cu2b_sgd_blocked(const cu2b_rating *coo, int64_t n, float *P, int rows, float *Q,
+                             int cols, float *user_bias, float *item_bias, float global_bias,
+                             const cu2b_config *cfg, int n_blocks, int n_passes);
+
+/* ------------------------------------------------------------------------------------
+ * Training (training.h:12-15 train()).
+ * ---------------------------------------------------------------------------------- */
+typedef struct cu2b_metrics { /* one row per loss check (training.cu:118-158) */
+    int iteration;            /* 1-based, as printed by training.cu:135 */
+    float train_mae, train_rmse, test_mae, test_rmse;
+    float learning_rate;      /* after the patience / decay step of this check */
+} cu2b_metrics;
+
+typedef struct cu2b_stats {
+    double sgd_ms;          /* device time inside SGD kernels (CUDA events) */
+    double loss_ms;         /* device time inside loss kernels */
+    double sampler_ms;      /* device time inside sampler kernels */
+    double total_ms;        /* device time of the whole enqueued loop */
+    int64_t updates;        /* rating updates performed */
+    int64_t kernel_launches;
+    int64_t sgd_launches;
+} cu2b_stats;
+
+/* One call = the reference's train(): uploads the matrices, trains cfg->total_iterations
+ * iterations with the loss cadence / patience / decay of training.cu:107-170 entirely on the
+ * device (no per-iteration host round trip), downloads the result.
+ *   init_item_side != 0 : training.cu:208-217 (8-argument overload) -- Q and item_bias are
+ *                         initialised here (N(0,1/k), seed 42);
+ *   init_item_side == 0 : training.cu:21 (10-argument overload) -- Q / item_bias are inputs.
+ * P [rows x k] and user_bias [rows] are always initialised inside (training.cu:28,54).
+ * cfg is in-out (learning_rate, cur_iterations; training.cu:151,170). losses may be NULL; else
+ * it has total_iterations floats: validation RMSE at check iterations, NaN elsewhere
+ * (training.cu:158). log may be NULL. */
+cu2b_status cu2b_train(const cu2b_csr *train, const cu2b_csr *test, cu2b_config *cfg, float *P,
+                       float *Q, float *user_bias, float *item_bias, float global_bias,
+                       int init_item_side, float *losses, cu2b_metrics *log, int log_cap,
+                       int *n_log, cu2b_stats *stats);
+
+/* Resident-data session: the same loop with explicit lifetime, for callers that keep the
+ * model on the device between calls (bench, multi-segment training). */
+typedef struct cu2b_session cu2b_session;
+cu2b_status cu2b_session_create(cu2b_session **out, int device, const cu2b_csr *train,
+                                const cu2b_csr *test, const cu2b_config *cfg, const float *P,
+                                const float *Q, const float *user_bias, const float *item_bias,
+                                float global_bias);
+/* Runs n_iterations more iterations (continuing cur_iterations); blocks until done. The
+ * "last iteration" check of training.cu:118 fires at cfg.total_iterations. */
+cu2b_status cu2b_session_run(cu2b_session *s, int n_iterations);
+cu2b_status cu2b_session_eval(cu2b_session *s, float *train_mae, float *train_rmse,
+                              float *test_mae, float *test_rmse);
+cu2b_status cu2b_session_log(cu2b_session *s, cu2b_metrics *out, int cap, int *n);
+cu2b_status cu2b_session_download(cu2b_session *s, float *P, float *Q, float *user_bias,
+                                  float *item_bias);
+cu2b_status cu2b_session_get_config(cu2b_session *s, cu2b_config *out);
+cu2b_status cu2b_session_stats(cu2b_session *s, cu2b_stats *out, int reset);
+void cu2b_session_destroy(cu2b_session *s);
+
+/* Device introspection used by bench / CLI ("Free memory: %ld", mf.cu:35-37). */
+cu2b_status cu2b_device_info(int device, char *name, int name_cap, int *sm_count,
+                             int *cc_major, int *cc_minor, int64_t *free_bytes,
+                             int64_t *total_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CU2B_H_ */

@@ -1,0 +1,415 @@
+"""GPU parity tests (run on the B200 box with -m gpu). Every call goes through the C ABI of
+libcu2b.so; the CPU oracle (tests/oracle.py) and the prebuilt unmodified reference binaries
+(oracle/_ref, compiled for sm_100a) are the checkers.
+
+Bars: bit-exact for integer / index work (sampler, CSR) and for the deterministic replay of the
+update arithmetic against the oracle's KERNEL flavour; fp32 tolerances, stated per test, for
+comparisons against the reference's op order; 1e-5 relative for the loss; 0.5 % for final RMSE."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import cu2rec_b200 as cu
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+KS = [1, 2, 3, 7, 16, 32, 50, 64, 100, 128, 200, 256, 300, 512]
+
+
+def _model(rng, U, I, k, scale=None):
+    s = scale if scale is not None else 1.0 / np.sqrt(k)
+    P = (rng.standard_normal((U, k)) * s).astype(np.float32)
+    Q = (rng.standard_normal((I, k)) * s).astype(np.float32)
+    ub = (rng.standard_normal(U) * 0.1).astype(np.float32)
+    ib = (rng.standard_normal(I) * 0.1).astype(np.float32)
+    return P, Q, ub, ib
+
+
+def _random_matrix(rng, U, I, max_deg, empty_frac=0.1):
+    deg = rng.randint(1, max_deg + 1, U)
+    deg[rng.rand(U) < empty_frac] = 0
+    rows = []
+    for u in range(U):
+        for i in rng.choice(I, min(deg[u], I), replace=False):
+            rows.append((u, i, float(rng.randint(1, 11)) / 2))
+    r = np.array(rows, dtype=cu.RATING_DTYPE)
+    return r, cu.createSparseMatrix(r, U, I)
+
+
+# ---------------------------------------------------------------------------------------------
+# loss (loss.cu)
+# ---------------------------------------------------------------------------------------------
+def test_loss_golden_74(fixtures_dir):
+    # tests/test_loss.cu:23-90
+    r, rows, cols, _ = cu.readCSV(os.path.join(fixtures_dir, "test_ratings.csv"))
+    m = cu.createSparseMatrix(r, rows, cols)
+    k = 2
+    P, Q = np.ones((rows, k), np.float32), np.ones((cols, k), np.float32)
+    ub, ib = np.ones(rows, np.float32), np.ones(cols, np.float32)
+    err = cu.calculate_loss_gpu(P, Q, k, m, ub, ib, 1.0)
+    loss = np.float32(0)
+    for e in err:
+        loss = np.float32(loss + e * e)
+    assert loss == 74.0
+    mae, rmse = cu.loss(P, Q, k, m, ub, ib, 1.0)
+    assert rmse == np.float32(np.sqrt(74.0 / 18)) and mae == np.float32(np.abs(err).astype(np.float64).sum() / 18)
+
+
+@pytest.mark.parametrize("n", [1, 33, 1 << 10, 1 << 16, (1 << 20) + 7])
+def test_total_loss_all_ones(n):
+    # tests/test_loss.cu:106-147 (the grid/block sweep is a launch detail of the reference kernel)
+    mae, rmse = cu.get_error_metrics_gpu(np.ones(n, np.float32))
+    assert mae == 1 and rmse == 1
+
+
+@pytest.mark.parametrize("k", KS)
+def test_residuals_and_metrics_vs_oracle(k):
+    rng = np.random.RandomState(100 + k)
+    U, I = 300, 200
+    r, m = _random_matrix(rng, U, I, 40)
+    P, Q, ub, ib = _model(rng, U, I, k)
+    mu = 3.3
+    err = cu.calculate_loss_gpu(P, Q, k, m, ub, ib, mu)
+    want_k = O.residuals(m.indptr, m.indices, m.data, P, Q, ub, ib, mu, k, O.FLAVOUR_KERNEL)
+    assert err.view(np.uint32).tolist() == want_k.view(np.uint32).tolist()  # same op order => same bits
+    want_r = O.residuals(m.indptr, m.indices, m.data, P, Q, ub, ib, mu, k, O.FLAVOUR_REF)
+    np.testing.assert_allclose(err, want_r, rtol=0, atol=2e-5)  # reference op order: fp32 rounding only
+    mae, rmse = cu.loss(P, Q, k, m, ub, ib, mu)
+    omae, ormse, _, _ = O.loss(m.indptr, m.indices, m.data, P, Q, ub, ib, mu, k, O.FLAVOUR_REF)
+    assert abs(mae - omae) / omae < 1e-5 and abs(rmse - ormse) / ormse < 1e-5
+    mae2, rmse2 = cu.get_error_metrics_gpu(err)
+    assert mae2 == mae and rmse2 == rmse
+    assert (mae, rmse) == cu.loss(P, Q, k, m, ub, ib, mu)  # bitwise reproducible
+
+
+def test_loss_large_ragged_matrix_vs_oracle():
+    rng = np.random.RandomState(9)
+    tr, _ = cu.synth_ratings(20000, 3000, 1500000, integer_ratings=True)
+    m = cu.createSparseMatrix(tr, 20000, 3000)
+    k = 128
+    P, Q, ub, ib = _model(rng, 20000, 3000, k)
+    mae, rmse = cu.loss(P, Q, k, m, ub, ib, 3.6)
+    omae, ormse, _, _ = O.loss(m.indptr, m.indices, m.data, P, Q, ub, ib, 3.6, k, O.FLAVOUR_REF)
+    assert abs(mae - omae) / omae < 1e-5 and abs(rmse - ormse) / ormse < 1e-5
+
+
+@pytest.mark.skipif(O.ref_binary("ref_harness") is None, reason="oracle/_ref not built")
+@pytest.mark.parametrize("k", [2, 32, 50, 128])
+def test_loss_vs_reference_gpu_kernels(tmp_path, k):
+    """Our fused loss vs the UNMODIFIED reference loss_kernel + total_loss_kernel (loss.cu) running
+    on this GPU: 1e-5 relative on mae / rmse, fp32 rounding on the residuals."""
+    rng = np.random.RandomState(200 + k)
+    U, I = 500, 300
+    r, m = _random_matrix(rng, U, I, 60)
+    P, Q, ub, ib = _model(rng, U, I, k)
+    mu = np.float32(3.4)
+    with open(tmp_path / "in.bin", "wb") as f:
+        np.array([U, I, m.nonzeros, k], np.int32).tofile(f)
+        np.array([mu], np.float32).tofile(f)
+        for a in (m.indptr, m.indices, m.data, P, Q, ub, ib):
+            a.tofile(f)
+    subprocess.run([O.ref_binary("ref_harness"), "loss_gpu", str(tmp_path / "in.bin"), str(tmp_path / "out.bin")],
+                   check=True, capture_output=True)
+    out = np.fromfile(tmp_path / "out.bin", dtype=np.float32)
+    ref_err, ref_mae, ref_rmse = out[:-2], out[-2], out[-1]
+    err = cu.calculate_loss_gpu(P, Q, k, m, ub, ib, mu)
+    np.testing.assert_allclose(err, ref_err, rtol=0, atol=2e-5)
+    mae, rmse = cu.loss(P, Q, k, m, ub, ib, mu)
+    assert abs(mae - ref_mae) / ref_mae < 1e-5 and abs(rmse - ref_rmse) / ref_rmse < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# sampler (sgd.cu:27-37)
+# ---------------------------------------------------------------------------------------------
+def test_sampler_bit_exact_vs_oracle():
+    rng = np.random.RandomState(1)
+    r, m = _random_matrix(rng, 700, 500, 30, empty_frac=0.2)
+    for seed, it0, n in [(42, 0, 5), (7, 1000, 3), (-3, 2 ** 20, 2)]:
+        got = cu.sample_per_user(m, seed, it0, n)
+        want = O.sample_per_user(m.indptr, m.indices, m.data, seed, it0, n)
+        assert got.tobytes() == want.tobytes()
+    assert len(cu.sample_per_user(m, 1, 0, 0)) == 0
+
+
+# ---------------------------------------------------------------------------------------------
+# update arithmetic (sgd.cu:40-72 / mf_sequential.cu:114-141)
+# ---------------------------------------------------------------------------------------------
+def _stream(rng, U, I, n):
+    s = np.zeros(n, dtype=cu.RATING_DTYPE)
+    s["user"], s["item"] = rng.randint(0, U, n), rng.randint(0, I, n)
+    s["rating"] = rng.randint(1, 6, n)
+    return s
+
+
+@pytest.mark.parametrize("k", KS)
+def test_serial_replay_bit_exact_vs_oracle(k):
+    rng = np.random.RandomState(300 + k)
+    U, I, n = 50, 40, 1500  # heavy reuse of rows: every update depends on earlier ones
+    P, Q, ub, ib = _model(rng, U, I, k)
+    s = _stream(rng, U, I, n)
+    cfg = cu.Config(n_factors=k, learning_rate=0.02, P_reg=0.03, Q_reg=0.04, user_bias_reg=0.05, item_bias_reg=0.06)
+    got = cu.sgd_apply(s, P, Q, ub, ib, 3.5, cfg, order=1)
+    want = O.sgd_apply_stream(s, P.ravel(), Q.ravel(), ub, ib, 3.5, O.hyper_from_cfg(cfg), O.FLAVOUR_KERNEL)
+    for g, w in zip(got, want):
+        assert g.ravel().view(np.uint32).tolist() == w.view(np.uint32).tolist()
+    ref = O.sgd_apply_stream(s, P.ravel(), Q.ravel(), ub, ib, 3.5, O.hyper_from_cfg(cfg), O.FLAVOUR_REF)
+    for g, w in zip(got, ref):  # mf_sequential op order: only the dot-product order differs
+        np.testing.assert_allclose(g.ravel(), w, rtol=0, atol=5e-5)
+
+
+def test_single_update_known_answer():
+    # the tests/test_sgd.cu setup, pinned numerically
+    f = np.float32
+    mu = f(64.0 / 18.0)
+    cfg = cu.Config(n_factors=1, learning_rate=0.07, P_reg=0.1, Q_reg=0.1, user_bias_reg=0.1, item_bias_reg=0.1)
+    for r in (1.0, 3.0, 5.0):
+        s = np.array([(0, 0, r)], dtype=cu.RATING_DTYPE)
+        P, Q, ub, ib = cu.sgd_apply(s, [1], [1], [1], [1], mu, cfg, order=0)
+        err = f(r) - f(f(f(mu + f(1)) + f(1)) + f(1))
+        want = f(1) + f(0.07) * f(err - f(f(0.1) * f(1)))
+        assert [P[0], Q[0], ub[0], ib[0]] == [want] * 4
+
+
+@pytest.mark.parametrize("k", [1, 7, 32, 50, 128, 256, 300])
+def test_hogwild_conflict_free_stream_bit_exact(k):
+    # distinct users and items => no races => the parallel kernel must equal the sequential oracle
+    rng = np.random.RandomState(400 + k)
+    n = 5000
+    P, Q, ub, ib = _model(rng, n, n, k)
+    s = np.zeros(n, dtype=cu.RATING_DTYPE)
+    s["user"], s["item"] = rng.permutation(n), rng.permutation(n)
+    s["rating"] = rng.randint(1, 6, n)
+    cfg = cu.Config(n_factors=k, learning_rate=0.05)
+    got = cu.sgd_apply(s, P, Q, ub, ib, 3.5, cfg, order=0)
+    want = O.sgd_apply_stream(s, P.ravel(), Q.ravel(), ub, ib, 3.5, O.hyper_from_cfg(cfg), O.FLAVOUR_KERNEL)
+    for g, w in zip(got, want):
+        assert g.ravel().view(np.uint32).tolist() == w.view(np.uint32).tolist()
+
+
+def test_hogwild_is_train_false_freezes_items():
+    rng = np.random.RandomState(5)
+    P, Q, ub, ib = _model(rng, 100, 80, 16)
+    s = _stream(rng, 100, 80, 3000)
+    cfg = cu.Config(n_factors=16, is_train=0)
+    P2, Q2, ub2, ib2 = cu.sgd_apply(s, P, Q, ub, ib, 3.5, cfg, order=0)
+    assert np.array_equal(Q2.reshape(Q.shape), Q) and np.array_equal(ib2, ib)
+    assert not np.array_equal(P2.reshape(P.shape), P)
+
+
+def test_hogwild_with_conflicts_stays_close_to_sequential():
+    rng = np.random.RandomState(6)
+    U, I, k, n = 4000, 600, 32, 40000
+    P, Q, ub, ib = _model(rng, U, I, k)
+    s = _stream(rng, U, I, n)
+    cfg = cu.Config(n_factors=k, learning_rate=0.01)
+    got = cu.sgd_apply(s, P, Q, ub, ib, 3.5, cfg, order=0)
+    want = O.sgd_apply_stream(s, P.ravel(), Q.ravel(), ub, ib, 3.5, O.hyper_from_cfg(cfg), O.FLAVOUR_KERNEL)
+    for g, w in zip(got, want):
+        assert np.all(np.isfinite(g))
+        assert np.sqrt(np.mean((g.ravel() - w) ** 2)) < 0.02  # racy by design: statistical closeness only
+    empty = cu.sgd_apply(s[:0], P, Q, ub, ib, 3.5, cfg, order=0)
+    assert np.array_equal(empty[0].reshape(P.shape), P)
+
+
+@pytest.mark.skipif(O.ref_binary("ref_harness") is None, reason="oracle/_ref not built")
+@pytest.mark.parametrize("k", [1, 8, 50])
+def test_update_vs_reference_sgd_kernel(tmp_path, k):
+    """One launch of the UNMODIFIED reference sgd_update (sgd.cu:22-75) on an input where it is
+    deterministic: every active user has exactly one rating, all items distinct, and the first 32
+    users are empty so the grid's surplus threads (sgd.cu:27-28) hit no rating. Its
+    P / Q_target / biases must match our update arithmetic to fp32 rounding (nvcc contracts the
+    reference's expressions into FMAs; ours are unfused like mf_sequential)."""
+    rng = np.random.RandomState(500 + k)
+    U, I = 32 + 200, 200
+    r = np.zeros(200, dtype=cu.RATING_DTYPE)
+    r["user"], r["item"] = 32 + np.arange(200), rng.permutation(200)
+    r["rating"] = rng.randint(1, 6, 200)
+    m = cu.createSparseMatrix(r, U, I)
+    P, Q, ub, ib = _model(rng, U, I, k)
+    mu, lr, regs = np.float32(3.5), np.float32(0.07), np.float32([0.1, 0.05, 0.02, 0.03])
+    with open(tmp_path / "in.bin", "wb") as f:
+        np.array([U, I, m.nonzeros, k], np.int32).tofile(f)
+        np.array([mu], np.float32).tofile(f)
+        for a in (m.indptr, m.indices, m.data, P, Q, ub, ib):
+            a.tofile(f)
+        np.array([lr, *regs], np.float32).tofile(f)
+        np.array([1, 0], np.int32).tofile(f)
+    subprocess.run([O.ref_binary("ref_harness"), "sgd_gpu", str(tmp_path / "in.bin"), str(tmp_path / "out.bin")],
+                   check=True, capture_output=True)
+    out = np.fromfile(tmp_path / "out.bin", dtype=np.float32)
+    rP, rQ, rub, rib = np.split(out, np.cumsum([U * k, I * k, U]))
+    cfg = cu.Config(n_factors=k, learning_rate=float(lr), P_reg=float(regs[0]), Q_reg=float(regs[1]),
+                    user_bias_reg=float(regs[2]), item_bias_reg=float(regs[3]))
+    got = cu.sgd_apply(r, P, Q, ub, ib, mu, cfg, order=0)
+    for g, w in zip(got, (rP, rQ, rub, rib)):
+        np.testing.assert_allclose(g.ravel(), w, rtol=0, atol=2e-6)
+
+
+# ---------------------------------------------------------------------------------------------
+# training loop (training.cu)
+# ---------------------------------------------------------------------------------------------
+def test_training_loop_reference_test(fixtures_dir):
+    # tests/test_training.cu:21-45
+    r, rows, cols, gb = cu.readCSV(os.path.join(fixtures_dir, "test_ratings.csv"))
+    m = cu.createSparseMatrix(r, rows, cols)
+    cfg = cu.Config(total_iterations=10, seed=42, n_factors=2, learning_rate=1e-3, P_reg=0.1, Q_reg=0.1,
+                    user_bias_reg=0.1, item_bias_reg=0.1)
+    out = cu.train(m, m, cfg, gb)
+    assert out["losses"][0] >= out["losses"][9]
+    assert [row["iteration"] for row in out["log"]] == [1, 10]
+    assert np.all(np.isnan(out["losses"][1:9]))
+    assert cfg.cur_iterations == 10
+    for name in ("P", "Q", "user_bias", "item_bias"):
+        assert np.all(np.isfinite(out[name]))
+    # A6: every array starts from mt19937(42) => epoch-0 state shares the oracle's init
+    assert out["P"].shape == (rows, 2) and out["Q"].shape == (cols, 2)
+
+
+def _small_problem(U=1500, I=400, n=60000, seed=11):
+    tr, te = cu.synth_ratings(U, I, n, rank=4, noise=0.3, integer_ratings=True, seed=seed)
+    return tr, te, cu.createSparseMatrix(tr, U, I), cu.createSparseMatrix(te, U, I), np.float32(tr["rating"].astype(np.float64).mean())
+
+
+@pytest.mark.parametrize("k", [8, 32, 50])
+def test_training_rmse_parity_vs_oracle_trainer(k):
+    """Hogwild GPU training vs the sequential CPU restatement (pinned to the compiled mf_cpu in
+    tests/test_oracle_pins.py) at equal iterations, same sampler stream, same init: final and
+    intermediate TEST RMSE within 0.5 %, and the first check (1 iteration) within 1e-4."""
+    tr, te, mtr, mte, mu = _small_problem()
+    U, I = mtr.rows, mtr.cols
+    iters, ce = 300, 100
+    cfg = cu.Config(total_iterations=iters, n_factors=k, check_error=ce)
+    out = cu.train(mtr, mte, cfg, mu)
+    init = lambda n: O.init_normal(n, k)
+    *_, olog = O.train((mtr.indptr, mtr.indices, mtr.data), (mte.indptr, mte.indices, mte.data), init(U * k), init(I * k),
+                       init(U), init(I), mu, O.hyper(k), 42, iters, check_error=ce)
+    assert [r["iteration"] for r in out["log"]] == [r["iteration"] for r in olog] == [1, 100, 200, 300]
+    for g, w in zip(out["log"], olog):
+        for key in ("train_rmse", "test_rmse", "train_mae", "test_mae"):
+            assert abs(g[key] - w[key]) / w[key] < 0.005, (key, g, w)
+    assert abs(out["log"][0]["test_rmse"] - olog[0]["test_rmse"]) < 1e-4
+    assert out["log"][-1]["test_rmse"] < out["log"][0]["test_rmse"]
+    assert out["stats"]["updates"] == iters * U
+
+
+def test_training_schedule_decay_matches_oracle():
+    tr, te, mtr, mte, mu = _small_problem(U=600, I=200, n=20000)
+    U, I, k = mtr.rows, mtr.cols, 8
+    cfg = cu.Config(total_iterations=60, n_factors=k, check_error=10, learning_rate=0.15)
+    out = cu.train(mtr, mte, cfg, mu)
+    init = lambda n: O.init_normal(n, k)
+    h = O.hyper(k, lr=0.15)
+    *_, olog = O.train((mtr.indptr, mtr.indices, mtr.data), (mte.indptr, mte.indices, mte.data), init(U * k), init(I * k),
+                       init(U), init(I), mu, h, 42, 60, check_error=10)
+    assert [r["learning_rate"] for r in out["log"]] == [np.float32(r["learning_rate"]) for r in olog]
+    assert out["log"][-1]["learning_rate"] < 0.15  # the schedule really fired
+    assert cfg.learning_rate == np.float32(olog[-1]["learning_rate"])
+
+
+def test_session_resume_equals_single_run():
+    tr, te, mtr, mte, mu = _small_problem(U=500, I=150, n=15000)
+    U, I, k = mtr.rows, mtr.cols, 16
+    init = lambda n: cu.initialize_normal_array(n, k)
+    P, Q, ub, ib = init(U * k), init(I * k), init(U), init(I)
+    cfg = cu.Config(total_iterations=40, n_factors=k, check_error=10)
+    with cu.Session(mtr, mte, cfg, P, Q, ub, ib, mu) as s:
+        s.run(40)
+        log_a, ev_a = s.log(), s.eval()
+    with cu.Session(mtr, mte, cfg, P, Q, ub, ib, mu) as s:
+        s.run(13); s.run(27)
+        log_b, ev_b = s.log(), s.eval()
+        assert s.config().cur_iterations == 40
+    assert [r["iteration"] for r in log_a] == [r["iteration"] for r in log_b] == [1, 10, 20, 30, 40]
+    for a, b in zip(log_a, log_b):
+        assert abs(a["test_rmse"] - b["test_rmse"]) / a["test_rmse"] < 2e-3  # Hogwild: not bit-identical
+    assert abs(ev_a["test_rmse"] - log_a[-1]["test_rmse"]) < 1e-6
+
+
+def test_train_edge_cases():
+    # one user, one rating; users without ratings; empty test matrix is rejected only if oversized
+    r = np.array([(2, 1, 4.0)], dtype=cu.RATING_DTYPE)
+    m = cu.createSparseMatrix(r, 4, 3)
+    cfg = cu.Config(total_iterations=5, n_factors=3, check_error=2)
+    out = cu.train(m, m, cfg, 4.0)
+    assert [row["iteration"] for row in out["log"]] == [1, 2, 4, 5] and out["stats"]["updates"] == 5
+    big = cu.createSparseMatrix(np.array([(0, 5, 1.0)], dtype=cu.RATING_DTYPE), 1, 6)
+    with pytest.raises(cu._lib.Cu2bError):
+        cu.train(m, big, cu.Config(total_iterations=1, n_factors=3), 4.0)
+    with pytest.raises(cu._lib.Cu2bError):
+        cu.train(m, m, cu.Config(total_iterations=1, n_factors=600), 4.0)
+
+
+@pytest.mark.skipif(O.ref_binary("mf") is None, reason="oracle/_ref not built")
+def test_training_vs_reference_gpu_binary(tmp_path):
+    """End to end against the UNMODIFIED reference `mf` (sm_100a build) on the same CSV + cfg.
+    The reference GPU path has its own quirks (early-bird gate, Q ping-pong) which
+    move its RMSE by about +-0.5 % against its CPU path, so the bar here is 2 %."""
+    tr, te, mtr, mte, mu = _small_problem(U=3000, I=500, n=150000, seed=5)
+    def write(path, r):
+        with open(path, "w") as f:
+            f.write("userId,itemId,rating\n")
+            f.write("".join("%d,%d,%.1f\n" % (u + 1, i + 1, x) for u, i, x in r))
+    write(tmp_path / "train.csv", tr)
+    write(tmp_path / "test.csv", te)
+    (tmp_path / "c.cfg").write_text("0 600 16 0.01 42 0.02 0.02 0.02 0.02")
+    outp = subprocess.run([O.ref_binary("mf"), "-c", str(tmp_path / "c.cfg"), str(tmp_path / "train.csv"),
+                           str(tmp_path / "test.csv")], capture_output=True, text=True, check=True).stdout
+    ref_final = float([l for l in outp.splitlines() if l.startswith("TEST:")][-1].split()[-1])
+    cfg = cu.Config()
+    cfg.read_config(tmp_path / "c.cfg")
+    r2, rows, cols, gb = cu.readCSV(tmp_path / "train.csv")
+    out = cu.train(mtr, mte, cfg, gb)
+    assert abs(out["log"][-1]["test_rmse"] - ref_final) / ref_final < 0.02, (out["log"][-1], ref_final)
+
+
+@pytest.mark.skipif(O.ref_binary("test_loss") is None, reason="oracle/_ref not built")
+def test_reference_own_tests_pass_on_this_gpu(tmp_path, fixtures_dir):
+    """Sanity for the GPU oracle: the reference's assert-based test binaries run green here."""
+    d = tmp_path / "data" / "test"
+    d.mkdir(parents=True)
+    for f in os.listdir(fixtures_dir):
+        (d / f).write_bytes(open(os.path.join(fixtures_dir, f), "rb").read())
+    cwd = tmp_path / "matrix_factorization" / "tests"
+    cwd.mkdir(parents=True)
+    for name in ("test_loss", "test_sgd", "test_training"):
+        p = subprocess.run([O.ref_binary(name)], cwd=cwd, capture_output=True, text=True)
+        assert p.returncode == 0 and "PASSED" in p.stdout, (name, p.stdout[-300:], p.stderr[-300:])
+
+
+# ---------------------------------------------------------------------------------------------
+# full-size, size-independent properties (MovieLens-20M shape, k=64; Netflix shape in bench)
+# ---------------------------------------------------------------------------------------------
+def test_full_size_properties_ml20m_shape():
+    U, I, k = 138493, 26744, 64
+    tr, te = cu.synth_ratings(U, I, 20000263, integer_ratings=False)
+    assert abs(len(tr) + len(te) - 20000263) < 0.01 * 20000263
+    mtr, mte = cu.createSparseMatrix(tr, U, I), cu.createSparseMatrix(te, U, I)
+    mu = np.float32(tr["rating"].astype(np.float64).mean())
+    init = lambda n: cu.initialize_normal_array(n, k)
+    P, Q, ub, ib = init(U * k), init(I * k), init(U), init(I)
+    # (1) sampler: integer work, every draw is one of the user's own ratings, one per user
+    s = cu.sample_per_user(mtr, 42, 17, 2)
+    assert s["user"].reshape(2, U).tolist() == [list(range(U))] * 2
+    key_all = set((tr["user"].astype(np.int64) * I + tr["item"]).tolist())
+    assert set((s["user"].astype(np.int64) * I + s["item"]).tolist()) <= key_all
+    # (2) loss: linearity over a split of the matrix (checksum of checksums) and reproducibility
+    mae, rmse = cu.loss(P, Q, k, mtr, ub, ib, mu)
+    half = int(mtr.indptr[U // 2])
+    a = cu.createSparseMatrix(tr[:half], U, I)
+    b = cu.createSparseMatrix(tr[half:], U, I)
+    (mae_a, rmse_a), (mae_b, rmse_b) = cu.loss(P, Q, k, a, ub, ib, mu), cu.loss(P, Q, k, b, ub, ib, mu)
+    na, nb = half, len(tr) - half
+    assert abs((mae_a * na + mae_b * nb) / (na + nb) - mae) / mae < 1e-6
+    assert abs(np.sqrt((rmse_a ** 2 * na + rmse_b ** 2 * nb) / (na + nb)) - rmse) / rmse < 1e-6
+    assert (mae, rmse) == cu.loss(P, Q, k, mtr, ub, ib, mu)
+    # (3) training: loss goes down, model stays finite, update count is iterations x users
+    cfg = cu.Config(total_iterations=300, n_factors=k, check_error=100)
+    out = cu.train(mtr, mte, cfg, mu)
+    rm = [r["test_rmse"] for r in out["log"]]
+    assert rm[-1] < rm[0] and np.isfinite(rm).all()
+    assert out["stats"]["updates"] == 300 * U
+    assert np.all(np.isfinite(out["P"])) and np.all(np.isfinite(out["Q"]))

@@ -1,0 +1,231 @@
+"""Host side of the drop-in boundary (libcu2b host functions; no GPU needed): config file,
+ratings CSV ingest, CSR build, matrix reader/writer, initialisation -- against the reference's
+golden values, the reference's own outputs (tests/golden) and the CPU oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import cu2rec_b200 as cu
+import oracle as O
+
+
+@pytest.fixture(scope="module")
+def ref_tests(golden_dir):
+    return json.load(open(os.path.join(golden_dir, "reference_tests.json")))
+
+
+def test_read_csv_reference_goldens(golden_dir, fixtures_dir, ref_tests):
+    gold = json.load(open(os.path.join(golden_dir, "ref_read_csv.json")))
+    for name, g in gold.items():
+        r, rows, cols, gb = cu.readCSV(os.path.join(fixtures_dir, name))
+        assert (len(r), rows, cols) == (g["n"], g["rows"], g["cols"]), name
+        assert int(np.float32(gb).view(np.uint32)) == g["global_bias_bits"], name
+        assert r["user"].tolist() == g["users"] and r["item"].tolist() == g["items"]
+        assert r["rating"].tolist() == g["ratings"]
+    g = ref_tests["test_util.cu:28-31"]  # tests/test_util.cu:28-31
+    r, rows, cols, gb = cu.readCSV(os.path.join(fixtures_dir, "test_ratings.csv"))
+    assert rows == 6 and cols == 5 and len(r) == 18 and abs(gb - g["global_bias"]) < g["tol"]
+
+
+@pytest.mark.parametrize("fname,key", [("test_ratings.csv", "test_util.cu:123-125"),
+                                       ("test_missing_user_ratings.csv", "test_util.cu:170-172")])
+def test_create_sparse_matrix_goldens(fixtures_dir, ref_tests, fname, key):
+    r, rows, cols, _ = cu.readCSV(os.path.join(fixtures_dir, fname))
+    m = cu.createSparseMatrix(r, rows, cols)
+    g = ref_tests[key]
+    assert m.indptr.tolist() == g["indptr"]
+    assert m.indices.tolist() == g["indices"]
+    assert m.data.tolist() == [float(x) for x in g["data"]]
+
+
+def test_csr_rejects_unsorted_and_out_of_range():
+    bad = np.array([(1, 0, 1.0), (0, 0, 1.0)], dtype=cu.RATING_DTYPE)
+    with pytest.raises(cu._lib.Cu2bError):
+        cu.createSparseMatrix(bad, 2, 1)
+    with pytest.raises(cu._lib.Cu2bError):
+        cu.createSparseMatrix(np.array([(5, 0, 1.0)], dtype=cu.RATING_DTYPE), 2, 1)
+    empty = cu.createSparseMatrix(np.zeros(0, dtype=cu.RATING_DTYPE), 3, 2)
+    assert empty.indptr.tolist() == [0, 0, 0, 0]
+
+
+def _random_csv(path, rng, n, style):
+    users = np.sort(rng.randint(1, 400, n))
+    items = rng.randint(1, 5000, n)
+    with open(path, "w") as f:
+        f.write("userId,itemId,rating\n")
+        for u, i in zip(users, items):
+            if style == "half":
+                r = "%.1f" % (rng.randint(1, 11) / 2)
+            elif style == "int":
+                r = "%d" % rng.randint(1, 6)
+            elif style == "long":
+                r = repr(float(rng.rand() * 5))
+            else:
+                r = "%.3e" % (rng.rand() * 5)
+            sep = rng.choice([",", ", ", " ,", "\t", ";"]) if style == "messy" else ","
+            f.write("%d%s%d%s%s%s" % (u, sep, i, sep, r, "\r\n" if style == "messy" else "\n"))
+
+
+@pytest.mark.parametrize("style", ["half", "int", "long", "exp", "messy"])
+def test_read_csv_matches_oracle_on_random_files(tmp_path, style):
+    rng = np.random.RandomState(hash(style) % 1000)
+    p = tmp_path / "r.csv"
+    _random_csv(p, rng, 3000, style)
+    a, rows, cols, gb = cu.readCSV(p)
+    b, rows2, cols2, gb2 = O.read_csv(p)
+    assert (rows, cols, len(a)) == (rows2, cols2, len(b))
+    assert a.tobytes() == b.tobytes()
+    assert np.float32(gb).view(np.uint32) == np.float32(gb2).view(np.uint32)
+
+
+def test_read_csv_multithreaded_path_matches_oracle(tmp_path):
+    rng = np.random.RandomState(5)
+    p = tmp_path / "big.csv"
+    n = 200000  # > 1 MiB => the parallel tokenizer is used
+    users = np.sort(rng.randint(1, 20000, n))
+    items = rng.randint(1, 5000, n)
+    r = rng.randint(1, 11, n) / 2
+    with open(p, "w") as f:
+        f.write("userId,itemId,rating\n")
+        f.write("".join("%d,%d,%.1f\n" % t for t in zip(users, items, r)))
+    assert os.path.getsize(p) > (1 << 20)
+    a, rows, cols, gb = cu.readCSV(p)
+    b, rows2, cols2, gb2 = O.read_csv(p)
+    assert len(a) == n and a.tobytes() == b.tobytes() and (rows, cols) == (rows2, cols2)
+    assert np.float32(gb).view(np.uint32) == np.float32(gb2).view(np.uint32)
+
+
+def test_read_csv_edge_cases(tmp_path):
+    # a fourth column ends the parse after the first row (util.cu:30)
+    p = tmp_path / "four.csv"
+    p.write_text("u,i,r,ts\n1,2,3.0,978300760\n1,3,4.0,978300761\n")
+    a, rows, cols, gb = cu.readCSV(p)
+    b, *_ = O.read_csv(p)
+    assert len(a) == len(b) == 1 and a.tobytes() == b.tobytes()
+    # header only / empty file
+    p2 = tmp_path / "hdr.csv"
+    p2.write_text("userId,itemId,rating\n")
+    a, rows, cols, gb = cu.readCSV(p2)
+    assert len(a) == 0 and rows == 0 and cols == 0
+    (tmp_path / "empty.csv").write_text("")
+    a, rows, cols, gb = cu.readCSV(tmp_path / "empty.csv")
+    assert len(a) == 0
+    with pytest.raises(cu._lib.Cu2bError):
+        cu.readCSV(tmp_path / "does_not_exist.csv")
+    # no trailing newline, like the reference fixtures
+    p3 = tmp_path / "nonl.csv"
+    p3.write_text("h\n1,1,1.0\n2,2,5.0")
+    a, rows, cols, gb = cu.readCSV(p3)
+    assert len(a) == 2 and rows == 2 and a["rating"].tolist() == [1.0, 5.0]
+
+
+def test_config_goldens_and_round_trip(tmp_path, golden_dir, fixtures_dir, ref_tests):
+    cfg = cu.Config()
+    assert (cfg.total_iterations, cfg.n_factors, cfg.check_error, cfg.n_threads) == (5000, 50, 500, 32)  # config.h:25-45
+    assert cfg.learning_rate == np.float32(0.01) and cfg.patience == 2.0 and cfg.learning_rate_decay == np.float32(0.2)
+    cfg.read_config(os.path.join(fixtures_dir, "test_config.cfg"))
+    g = ref_tests["test_config.cu:14-15"]
+    assert cfg.total_iterations == g["total_iterations"] and abs(cfg.P_reg - g["P_reg"]) < g["tol"]
+    ref = json.load(open(os.path.join(golden_dir, "ref_read_config.json")))["fields"]
+    got = [cfg.cur_iterations, cfg.total_iterations, cfg.n_factors, cfg.learning_rate, cfg.seed, cfg.P_reg, cfg.Q_reg,
+           cfg.user_bias_reg, cfg.item_bias_reg]
+    for a, b in zip(got, ref):
+        assert np.float32(a) == np.float32(float(b))
+    # oracle agrees
+    n, v = O.read_config(os.path.join(fixtures_dir, "test_config.cfg"))
+    assert [np.float32(x) for x in v] == [np.float32(x) for x in got]
+    # tests/test_config.cu:19-26 save -> load
+    c2 = cu.Config(total_iterations=100, P_reg=0.2)
+    c2.write_config(tmp_path / "gen.cfg")
+    c3 = cu.Config()
+    c3.read_config(tmp_path / "gen.cfg")
+    assert c3.total_iterations == 100 and abs(c3.P_reg - 0.2) < 1e-4
+    assert len((tmp_path / "gen.cfg").read_text().split()) == 9
+    # short file keeps defaults for the missing fields; optional extension fields parse
+    (tmp_path / "short.cfg").write_text("0 77 12")
+    c4 = cu.Config()
+    c4.read_config(tmp_path / "short.cfg")
+    assert (c4.total_iterations, c4.n_factors, c4.learning_rate) == (77, 12, np.float32(0.01))
+    (tmp_path / "ext.cfg").write_text("0 10 8 0.05 7 0.1 0.2 0.3 0.4 64 3 0.5 25 1 1 16 2")
+    c5 = cu.Config()
+    c5.read_config(tmp_path / "ext.cfg")
+    assert (c5.n_threads, c5.patience, c5.check_error, c5.mode, c5.sampler, c5.n_blocks, c5.n_gpus) == (64, 3.0, 25, 1, 1, 16, 2)
+    with pytest.raises(cu._lib.Cu2bError):
+        cu.Config().read_config(tmp_path / "missing.cfg")
+
+
+def test_print_config_format():
+    txt = cu.Config().format()  # config.cu:50-64
+    assert txt.splitlines() == [
+        "Hyperparameters:", "total_iterations: 5000", "n_factors: 50", "learning_rate: 0.010000", "P_reg: 0.020000",
+        "Q_reg: 0.020000", "user_bias_reg: 0.020000", "item_bias_reg: 0.020000", "is_train: true", "n_threads: 32",
+        "check_error: 500", "patience: 2.000000", "learning_rate_decay: 0.200000"]
+
+
+@pytest.mark.parametrize("size,k", [(64, 2), (1000, 32), (257, 128), (50, 50)])
+def test_initialize_normal_array_bits(golden_dir, size, k):
+    want = np.fromfile(os.path.join(golden_dir, "ref_init_normal_%d_%d.bin" % (size, k)), dtype=np.float32)
+    assert cu.initialize_normal_array(size, k).view(np.uint32).tolist() == want.view(np.uint32).tolist()
+
+
+def test_write_csv_byte_identical_to_reference(tmp_path, golden_dir):
+    mat = np.fromfile(os.path.join(golden_dir, "write_csv_input.bin"), dtype=np.float32)
+    cu.writeCSV(tmp_path / "o.csv", mat, 24, 5)
+    assert (tmp_path / "o.csv").read_bytes() == open(os.path.join(golden_dir, "ref_write_csv.csv"), "rb").read()
+
+
+def test_write_csv_matches_printf_on_random_floats(tmp_path):
+    rng = np.random.RandomState(11)
+    bits = rng.randint(0, 2 ** 32, 200000, dtype=np.uint64).astype(np.uint32)
+    vals = bits.view(np.float32)
+    vals = vals[np.isfinite(vals)]
+    small = (rng.standard_normal(100000) * 10.0 ** rng.randint(-9, 6, 100000)).astype(np.float32)
+    ties = (np.arange(1, 4001, dtype=np.float64) / 2 ** 12).astype(np.float32)  # exact binary fractions
+    allv = np.concatenate([vals, small, ties]).astype(np.float32)
+    allv = allv[: (len(allv) // 7) * 7]
+    cu.writeCSV(tmp_path / "r.csv", allv, len(allv) // 7, 7)
+    got = (tmp_path / "r.csv").read_text().replace("\n", ",").split(",")[:-1]
+    want = ["%f" % float(v) for v in allv]
+    assert got == want
+
+
+def test_write_to_file_naming_and_read_array(tmp_path, golden_dir, fixtures_dir, ref_tests):
+    # tests/test_util.cu:49-92 writes five components; we also read them back (util.cu:52-76)
+    P = np.ones(12, np.float32)
+    cu.writeToFile(tmp_path, "test_ratings", "csv", "p", P, 6, 2, 2)
+    cu.writeToFile(tmp_path, "test_ratings", "csv", "global_bias", np.array([3.5], np.float32), 1, 1, 2)
+    assert (tmp_path / "test_ratings_f2_p.csv").read_text() == "1.000000,1.000000\n" * 6
+    assert (tmp_path / "test_ratings_f2_global_bias.csv").read_text() == "3.500000\n"
+    arr, r, c = cu.read_array(tmp_path / "test_ratings_f2_p.csv")
+    assert r == 6 and c == 12 and arr.tolist() == [1.0] * 12
+    arr, r, c = cu.read_array(os.path.join(fixtures_dir, "test_Q.csv"))
+    g = json.load(open(os.path.join(golden_dir, "ref_read_array.json")))
+    assert (r, c) == (g["n_rows"], g["n_cols"]) and arr.tolist() == g["values"]
+    assert np.allclose(arr[:10], ref_tests["test_util.cu:43"]["read_array_first10"], atol=1e-3)
+    with pytest.raises(cu._lib.Cu2bError):
+        cu.read_array(tmp_path / "nope.csv")
+
+
+def test_synth_ratings_contract():
+    tr, te = cu.synth_ratings(943, 1682, 100000, integer_ratings=False)
+    assert 90000 < len(tr) + len(te) < 110000
+    assert 0.07 < len(te) / (len(tr) + len(te)) < 0.13
+    for part in (tr, te):
+        assert np.all(np.diff(part["user"]) >= 0)  # grouped by ascending user
+        assert part["item"].min() >= 0 and part["item"].max() < 1682
+        assert part["rating"].min() >= 0.5 and part["rating"].max() <= 5.0
+        assert np.all(part["rating"] * 2 == np.round(part["rating"] * 2))
+    assert np.array_equal(np.unique(tr["user"]), np.arange(943))  # every user has a train rating
+    allr = np.concatenate([tr, te])
+    key = allr["user"].astype(np.int64) * 1682 + allr["item"]
+    assert len(np.unique(key)) == len(key)  # (user, item) pairs without replacement
+    tr2, te2 = cu.synth_ratings(943, 1682, 100000, integer_ratings=False)
+    assert tr2.tobytes() == tr.tobytes() and te2.tobytes() == te.tobytes()
+    # popularity and activity are skewed
+    pop = np.sort(np.bincount(allr["item"], minlength=1682))[::-1]
+    act = np.sort(np.bincount(allr["user"], minlength=943))[::-1]
+    assert pop[0] > 8 * np.median(pop) and act[0] > 5 * np.median(act)
+    tri, _ = cu.synth_ratings(200, 300, 5000, integer_ratings=True)
+    assert set(np.unique(tri["rating"])) <= {1.0, 2.0, 3.0, 4.0, 5.0}
