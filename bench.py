@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- SGD rating-updates/s of the matrix-factorisation hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload netflix|ml20m|ml100k] [--k K] [--iters-per-step T]
+
+Workload (BASELINE.json configs[2], the one the metric is quoted on): Netflix-shape synthetic
+low-rank-plus-noise ratings (480 189 users x 17 770 items x ~100.5 M ratings, 90/10 split),
+k = 128, reference hyper-parameters (lr 0.01, all regularisers 0.02, check_error 500).
+A "step" is one check_error segment of the reference loop: T = 500 reference iterations
+(T x U rating updates, one sampled rating per user per iteration, sgd.cu:27-37) followed by
+the train+test loss check (training.cu:118-158).
+
+  value  : updates/s over the timed steps with ratings and model resident in HBM
+           (device time of the whole enqueued loop: sampler + SGD + loss kernels).
+  e2e    : the same metric through the C ABI with HOST (pinned) buffers: session create (H2D of
+           both rating matrices and the initial model) + T iterations + download (D2H of
+           P, Q, biases) + destroy, wall clock.
+  roofline: the SGD kernel alone, algorithmic bytes (16k+12 per update) / its CUDA-event time,
+           against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+  cpu_baseline: the UNMODIFIED reference mf_cpu (oracle/_ref/mf_cpu, single-threaded) on a
+           bounded user-prefix sample of the same workload, timed by its own clock() line.
+
+--impl reference times that CPU reference alone and prints the same JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (users, items, ratings, integer_ratings, default k)
+    "netflix": (480189, 17770, 100480507, True, 128),
+    "ml20m": (138493, 26744, 20000263, False, 64),
+    "ml100k": (943, 1682, 100000, False, 32),
+}
+DATA_SEED = 20240607
+METRIC = "sgd_rating_updates_per_sec"
+UNIT = "updates/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device=0):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------------
+_WORKLOAD_CACHE = {}
+
+
+def make_workload(name, users_prefix=None):
+    import cu2rec_b200 as cu
+    U, I, R, integer, _ = WORKLOADS[name]
+    if name not in _WORKLOAD_CACHE:
+        t0 = time.time()
+        _WORKLOAD_CACHE[name] = cu.synth_ratings(U, I, R, integer_ratings=integer, seed=DATA_SEED)
+        log("[bench] generated %s: %d train + %d test ratings in %.1fs" % (
+            name, len(_WORKLOAD_CACHE[name][0]), len(_WORKLOAD_CACHE[name][1]), time.time() - t0))
+    tr, te = _WORKLOAD_CACHE[name]
+    if users_prefix is not None and users_prefix < U:
+        tr = tr[: int(np.searchsorted(tr["user"], users_prefix))]
+        te = te[: int(np.searchsorted(te["user"], users_prefix))]
+        U = users_prefix
+    return tr, te, U, I
+
+
+class _Keep(np.ndarray):
+    pass
+
+
+def pin(a):
+    try:
+        import torch
+        t = torch.empty(max(1, a.nbytes), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+        out = t.numpy()[: a.nbytes].view(a.dtype).reshape(a.shape).view(_Keep)
+        out._owner = t
+        out[...] = a
+        return out
+    except Exception as e:  # pragma: no cover
+        log("[bench] pinned allocation failed (%s); using pageable memory" % e)
+        return np.ascontiguousarray(a)
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference CPU arm (oracle/_ref/mf_cpu, else the oracle port)
+# ---------------------------------------------------------------------------------------------
+def write_csv(path, r):
+    with open(path, "w") as f:
+        f.write("userId,itemId,rating\n")
+        u, i, x = r["user"] + 1, r["item"] + 1, r["rating"]
+        step = 1 << 18
+        for s in range(0, len(r), step):
+            f.write("".join("%d,%d,%.1f\n" % t for t in zip(u[s:s + step].tolist(), i[s:s + step].tolist(), x[s:s + step].tolist())))
+
+
+class CpuReference:
+    """Times the reference's own CPU implementation on a bounded sample of the workload."""
+
+    def __init__(self, workload, k, sample_users=10000, budget_s=12.0):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle as O
+        self.O = O
+        self.k = k
+        self.workload = workload
+        self.sample_users = min(sample_users, WORKLOADS[workload][0])
+        self.budget_s = budget_s
+        self.binary = O.ref_binary("mf_cpu")
+        self.kind = "reference" if self.binary else "port"
+        self.tmp = tempfile.mkdtemp(prefix="cu2b_ref_")
+        self.tr, self.te, self.U, self.I = make_workload(workload, users_prefix=self.sample_users)
+        if self.binary:
+            write_csv(os.path.join(self.tmp, "train.csv"), self.tr)
+            write_csv(os.path.join(self.tmp, "test.csv"), self.te)
+        # ~21 us per update for the reference (std::random_device per update, mf_sequential.cu:109)
+        per_update = 21e-6 if self.binary else 0.4e-6 * max(1.0, k / 32)
+        self.iters = int(max(2, min(2000, budget_s / (per_update * self.U))))
+
+    def sample_desc(self):
+        return ("first %d users of the %s-shape workload (%d train ratings, all %d items), k=%d, %d iterations = "
+                "%d updates per step, incl. the reference's loss checks at iterations 1 and %d" %
+                (self.U, self.workload, len(self.tr), self.I, self.k, self.iters, self.iters * self.U, self.iters))
+
+    def run_once(self):
+        """-> (updates, seconds, final test rmse)"""
+        updates = self.iters * self.U
+        if self.binary:
+            cfg = os.path.join(self.tmp, "c.cfg")
+            open(cfg, "w").write("0 %d %d 0.01 42 0.02 0.02 0.02 0.02" % (self.iters, self.k))
+            out = subprocess.run([self.binary, "-c", cfg, os.path.join(self.tmp, "train.csv"), os.path.join(self.tmp, "test.csv")],
+                                 capture_output=True, text=True, check=True).stdout
+            secs = float(re.search(r"Time taken for \d+ of iterations is ([0-9.eE+-]+)", out).group(1))
+            rmse = float([l for l in out.splitlines() if l.startswith("TEST:")][-1].split()[-1])
+            return updates, secs, rmse
+        O, k = self.O, self.k
+        import cu2rec_b200 as cu
+        mtr, mte = cu.createSparseMatrix(self.tr, self.U, self.I), cu.createSparseMatrix(self.te, self.U, self.I)
+        mu = np.float32(self.tr["rating"].astype(np.float64).mean())
+        init = lambda n: O.init_normal(n, k)
+        P, Q, ub, ib = init(self.U * k), init(self.I * k), init(self.U), init(self.I)
+        t0 = time.perf_counter()
+        *_, lg = O.train((mtr.indptr, mtr.indices, mtr.data), (mte.indptr, mte.indices, mte.data), P, Q, ub, ib, mu,
+                         O.hyper(k), 42, self.iters, use_decay=False)
+        return updates, time.perf_counter() - t0, lg[-1]["test_rmse"]
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    k = args.k or WORKLOADS[args.workload][4]
+    total = max(1, args.steps + args.warmup)
+    ref = CpuReference(args.workload, k, budget_s=min(12.0, 150.0 / total))
+    for _ in range(args.warmup):
+        ref.run_once()
+    ups, secs, rmse = 0, 0.0, None
+    for _ in range(args.steps):
+        u, s, rmse = ref.run_once()
+        ups += u
+        secs += s
+    value = ups / secs
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, args.steps), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args, k),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": ref.kind, "sample": ref.sample_desc(),
+                         "host_cores_available": os.cpu_count(), "final_test_rmse": rmse},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def config_dict(args, k):
+    U, I, R, _, _ = WORKLOADS[args.workload]
+    return {"workload": "%s-shape synthetic low-rank+noise (%d users x %d items x ~%d ratings, 90/10 split), k=%d, "
+                        "hogwild, per_user sampler (one sampled rating per user per iteration)" % (args.workload, U, I, R, k),
+            "n_factors": k, "iters_per_step": args.iters_per_step, "updates_per_step": args.iters_per_step * U,
+            "step": "T reference iterations + one train/test loss check (training.cu:118)",
+            "l2": "inputs larger than L2 (P %d MB + rating/update streams >> 126 MB)" % (U * k * 4 >> 20),
+            "lr": 0.01, "reg": 0.02, "check_error": args.iters_per_step}
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def traffic_from_profiles(k):
+    p = os.path.join(ROOT, "profiles", "sgd_traffic.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return d.get(str(k))
+        except Exception:
+            return None
+    return None
+
+
+def run_ours(args):
+    import cu2rec_b200 as cu
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus != 1 or world != 1:
+        raise SystemExit("multi-GPU DSGD bench is not wired in this build; run with --gpus 1")
+    k = args.k or WORKLOADS[args.workload][4]
+    T = args.iters_per_step
+    info = cu.device_info(0)
+    log("[bench] device: %s, %d SMs" % (info["name"], info["sm_count"]))
+    tr, te, U, I = make_workload(args.workload)
+    mtr, mte = cu.createSparseMatrix(tr, U, I), cu.createSparseMatrix(te, U, I)
+    mu = np.float32(tr["rating"].astype(np.float64).sum() / len(tr))
+    init = lambda n: cu.initialize_normal_array(n, k)
+    P0, Q0, ub0, ib0 = init(U * k), init(I * k), init(U), init(I)
+    total_iters = (args.steps + args.warmup) * T
+    cfg = cu.Config(total_iterations=total_iters, n_factors=k, check_error=T)
+
+    # ---- resident-data throughput ------------------------------------------------------------
+    sess = cu.Session(mtr, mte, cfg, P0, Q0, ub0, ib0, mu)
+    for _ in range(args.warmup):
+        sess.run(T)
+    sess.stats(reset=True)
+    clocks = ClockSampler()
+    clocks.start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sess.run(T)  # each call ends with a stream synchronize
+    wall = time.perf_counter() - t0
+    clk = clocks.stop()
+    st = sess.stats()
+    lg = sess.log()
+    sess.close()
+    updates = st["updates"]
+    dev_s = st["total_ms"] / 1e3
+    value = updates / dev_s
+    bytes_per_update = 16 * k + 12
+    sgd_gbs = updates * bytes_per_update / (st["sgd_ms"] / 1e3) / 1e9
+    peak, peak_src = peaks()
+    roofline = {"bound": "hbm", "kernel": "mf_sgd_hogwild", "achieved": sgd_gbs, "peak": peak, "unit": "GB/s",
+                "frac": sgd_gbs / peak, "traffic": traffic_from_profiles(k), "peak_source": peak_src,
+                "algorithmic_bytes_per_update": bytes_per_update, "kernel_ms_per_step": st["sgd_ms"] / args.steps,
+                "kernel_updates_per_s": updates / (st["sgd_ms"] / 1e3)}
+
+    # ---- end to end through the C ABI with pinned host buffers --------------------------------
+    hp = {n: pin(getattr(mtr, n)) for n in ("indptr", "indices", "data")}
+    hq = {n: pin(getattr(mte, n)) for n in ("indptr", "indices", "data")}
+    ptr = cu.CSRMatrix(U, I, hp["indptr"], hp["indices"], hp["data"])
+    pte = cu.CSRMatrix(U, I, hq["indptr"], hq["indices"], hq["data"])
+    hP, hQ, hub, hib = pin(P0), pin(Q0), pin(ub0), pin(ib0)
+    cfg_e = cu.Config(total_iterations=T, n_factors=k, check_error=T)
+    h2d = sum(a.nbytes for a in list(hp.values()) + list(hq.values()) + [hP, hQ, hub, hib])
+    d2h = sum(a.nbytes for a in (hP, hQ, hub, hib))
+    e2e_steps = max(1, min(args.steps, 3))
+
+    def e2e_once():
+        with cu.Session(ptr, pte, cfg_e, hP, hQ, hub, hib, mu) as s:
+            s.run(T)
+            out = s.download()
+            rm = s.log()[-1]["test_rmse"]
+        return out, rm
+
+    e2e_once()  # warm-up
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        _, e2e_rmse = e2e_once()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e = {"value": T * U / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "ms_per_step": 1e3 * e2e_s, "steps": e2e_steps,
+           "what": "cu2b_session_create(host CSR + model, pinned) + %d iterations + download + destroy" % T}
+
+    # ---- CPU baseline (rank 0, bounded sample) -----------------------------------------------
+    cpu = None
+    if not args.no_cpu_baseline:
+        ref = CpuReference(args.workload, k, budget_s=args.cpu_budget)
+        u, s, r_rmse = ref.run_once()
+        cpu = {"value": u / s, "unit": UNIT, "cores": 1, "kind": ref.kind, "sample": ref.sample_desc(),
+               "host_cores_available": os.cpu_count(), "seconds": s, "final_test_rmse": r_rmse}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dev_s / args.steps, "wall_ms_per_step": 1e3 * wall / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args, k), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        "gpu_launches": int(st["kernel_launches"]), "clocks": clk,
+        "breakdown_ms_per_step": {"sgd": st["sgd_ms"] / args.steps, "sampler": st["sampler_ms"] / args.steps,
+                                  "loss_check": st["loss_ms"] / args.steps},
+        "test_rmse": [round(r["test_rmse"], 5) for r in lg], "e2e_test_rmse": e2e_rmse,
+        "epochs_per_step": T * U / float(mtr.nonzeros),
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="netflix", choices=sorted(WORKLOADS))
+    ap.add_argument("--k", type=int, default=0)
+    ap.add_argument("--iters-per-step", type=int, default=500)
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        log("[bench] note: fewer than 3 warm-up steps requested")
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

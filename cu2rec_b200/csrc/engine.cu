@@ -17,6 +17,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -194,21 +195,28 @@ cu2b_status layout_for(int kp, int *L, int *V) {
     return CU2B_OK;
 }
 
-SgdKernel pick_sgd(int L, int V) {
+template <bool A>
+SgdKernel pick_sgd_t(int L, int V) {
     switch (L) {
-        case 1: return mf_sgd_hogwild<1, 1, 2>;
-        case 2: return mf_sgd_hogwild<2, 1, 2>;
-        case 4: return mf_sgd_hogwild<4, 1, 2>;
-        case 8: return mf_sgd_hogwild<8, 1, 2>;
-        case 16: return mf_sgd_hogwild<16, 1, 2>;
+        case 1: return mf_sgd_hogwild<1, 1, 2, A>;
+        case 2: return mf_sgd_hogwild<2, 1, 2, A>;
+        case 4: return mf_sgd_hogwild<4, 1, 2, A>;
+        case 8: return mf_sgd_hogwild<8, 1, 2, A>;
+        case 16: return mf_sgd_hogwild<16, 1, 2, A>;
         default:
             switch (V) {
-                case 1: return mf_sgd_hogwild<32, 1, 2>;
-                case 2: return mf_sgd_hogwild<32, 2, 2>;
-                case 3: return mf_sgd_hogwild<32, 3, 1>;
-                default: return mf_sgd_hogwild<32, 4, 1>;
+                case 1: return mf_sgd_hogwild<32, 1, 2, A>;
+                case 2: return mf_sgd_hogwild<32, 2, 2, A>;
+                case 3: return mf_sgd_hogwild<32, 3, 1, A>;
+                default: return mf_sgd_hogwild<32, 4, 1, A>;
             }
     }
+}
+// Item-side updates as L2 atomic adds unless CU2B_ATOMIC_Q=0 (A/B switch for profiling).
+SgdKernel pick_sgd(int L, int V) {
+    const char *e = getenv("CU2B_ATOMIC_Q");
+    const bool atomq = !(e && e[0] == '0');
+    return atomq ? pick_sgd_t<true>(L, V) : pick_sgd_t<false>(L, V);
 }
 LossKernel pick_loss(int L, int V) {
     switch (L) {

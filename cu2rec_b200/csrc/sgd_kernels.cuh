@@ -84,7 +84,18 @@ __device__ __forceinline__ float group_sum(float a) {
 }
 
 // Processes UNR ratings (one per slot) for this lane's group. `ok[x]` false => slot idle.
-template <int L, int V, int UNR>
+// 128-bit fire-and-forget float add at L2 (SASS REDG.E.ADD.F32x4): concurrent Hogwild updates of
+// one item row accumulate instead of overwriting each other.
+__device__ __forceinline__ void red_add_v4(float4 *addr, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+// ATOMQ: item-side updates (Q row, item_bias) are applied as atomic adds of the SGD step
+// instead of read-modify-write stores. Same arithmetic (q + step, one rounding) when an item is
+// touched by one update at a time; under contention no step is lost.
+template <int L, int V, int UNR, bool ATOMQ>
 __device__ __forceinline__ void sgd_update_slots(const SgdParams &p, const cu2b_rating *rt,
                                                  const bool *ok, int l, int vecs, float lr) {
     float4 pv[UNR][V], qv[UNR][V];
@@ -130,26 +141,36 @@ __device__ __forceinline__ void sgd_update_slots(const SgdParams &p, const cu2b_
             na.y = __fadd_rn(a.y, __fmul_rn(lr, __fsub_rn(__fmul_rn(err, b.y), __fmul_rn(p.P_reg, a.y))));
             na.z = __fadd_rn(a.z, __fmul_rn(lr, __fsub_rn(__fmul_rn(err, b.z), __fmul_rn(p.P_reg, a.z))));
             na.w = __fadd_rn(a.w, __fmul_rn(lr, __fsub_rn(__fmul_rn(err, b.w), __fmul_rn(p.P_reg, a.w))));
-            nb.x = __fadd_rn(b.x, __fmul_rn(lr, __fsub_rn(__fmul_rn(err, a.x), __fmul_rn(p.Q_reg, b.x))));
-            nb.y = __fadd_rn(b.y, __fmul_rn(lr, __fsub_rn(__fmul_rn(err, a.y), __fmul_rn(p.Q_reg, b.y))));
-            nb.z = __fadd_rn(b.z, __fmul_rn(lr, __fsub_rn(__fmul_rn(err, a.z), __fmul_rn(p.Q_reg, b.z))));
-            nb.w = __fadd_rn(b.w, __fmul_rn(lr, __fsub_rn(__fmul_rn(err, a.w), __fmul_rn(p.Q_reg, b.w))));
+            nb.x = __fmul_rn(lr, __fsub_rn(__fmul_rn(err, a.x), __fmul_rn(p.Q_reg, b.x)));
+            nb.y = __fmul_rn(lr, __fsub_rn(__fmul_rn(err, a.y), __fmul_rn(p.Q_reg, b.y)));
+            nb.z = __fmul_rn(lr, __fsub_rn(__fmul_rn(err, a.z), __fmul_rn(p.Q_reg, b.z)));
+            nb.w = __fmul_rn(lr, __fsub_rn(__fmul_rn(err, a.w), __fmul_rn(p.Q_reg, b.w)));
             if (ok[x] && idx < vecs) {
                 __stcg(prow[x] + idx, na);
-                if (p.is_train) __stcg(qrow[x] + idx, nb);
+                if (p.is_train) {
+                    if (ATOMQ) {
+                        red_add_v4(qrow[x] + idx, nb);
+                    } else {
+                        nb.x = __fadd_rn(b.x, nb.x); nb.y = __fadd_rn(b.y, nb.y);
+                        nb.z = __fadd_rn(b.z, nb.z); nb.w = __fadd_rn(b.w, nb.w);
+                        __stcg(qrow[x] + idx, nb);
+                    }
+                }
             }
         }
         if (ok[x] && l == 0) {
             __stcg(p.user_bias + rt[x].user,
                    __fadd_rn(ub[x], __fmul_rn(lr, __fsub_rn(err, __fmul_rn(p.ub_reg, ub[x])))));
-            if (p.is_train)
-                __stcg(p.item_bias + rt[x].item,
-                       __fadd_rn(ib[x], __fmul_rn(lr, __fsub_rn(err, __fmul_rn(p.ib_reg, ib[x])))));
+            if (p.is_train) {
+                const float step = __fmul_rn(lr, __fsub_rn(err, __fmul_rn(p.ib_reg, ib[x])));
+                if (ATOMQ) atomicAdd(p.item_bias + rt[x].item, step);
+                else __stcg(p.item_bias + rt[x].item, __fadd_rn(ib[x], step));
+            }
         }
     }
 }
 
-template <int L, int V, int UNR>
+template <int L, int V, int UNR, bool ATOMQ>
 __global__ void __launch_bounds__(kThreads)
 mf_sgd_hogwild(const SgdParams p) {
     __shared__ StreamSmem sm;
@@ -189,7 +210,7 @@ mf_sgd_hogwild(const SgdParams p) {
                 const bool ok = (g == 0);
                 for (int j = 0; j < cnt; ++j) {
                     const cu2b_rating rt = sm.stage[s][j];
-                    sgd_update_slots<L, V, 1>(p, &rt, &ok, l, vecs, lr);
+                    sgd_update_slots<L, V, 1, false>(p, &rt, &ok, l, vecs, lr);
                     __syncwarp();
                 }
             }
@@ -204,7 +225,7 @@ mf_sgd_hogwild(const SgdParams p) {
                     ok[x] = j < cnt;
                     rt[x] = sm.stage[s][ok[x] ? j : 0];
                 }
-                sgd_update_slots<L, V, UNR>(p, rt, ok, l, vecs, lr);
+                sgd_update_slots<L, V, UNR, ATOMQ>(p, rt, ok, l, vecs, lr);
             }
         }
         __syncwarp();
