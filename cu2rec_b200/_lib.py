@@ -66,6 +66,7 @@ SYMBOLS = {
     "cu2b_sample_per_user": (C.c_int, [C.POINTER(Csr), C.c_int, C.c_int, C.c_int, _P, C.POINTER(C.c_int64)]),
     "cu2b_sgd_apply": (C.c_int, [_P, C.c_int64, _P, C.c_int, _P, C.c_int, _P, _P, C.c_float, C.POINTER(Config), C.c_int]),
     "cu2b_sgd_blocked": (C.c_int, [_P, C.c_int64, _P, C.c_int, _P, C.c_int, _P, _P, C.c_float, C.POINTER(Config), C.c_int, C.c_int]),
+    "cu2b_block_schedule_order": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, C.c_int, _P, C.POINTER(C.c_int)]),
     "cu2b_train": (C.c_int, [C.POINTER(Csr), C.POINTER(Csr), C.POINTER(Config), _P, _P, _P, _P, C.c_float, C.c_int,
                              _P, C.POINTER(Metrics), C.c_int, C.POINTER(C.c_int), C.POINTER(Stats)]),
     "cu2b_session_create": (C.c_int, [C.POINTER(_P), C.c_int, C.POINTER(Csr), C.POINTER(Csr), C.POINTER(Config),

@@ -235,6 +235,15 @@ def sgd_blocked(coo, P, Q, user_bias, item_bias, global_bias, cfg, n_blocks, n_p
     return P, Q, ub, ib
 
 
+def block_schedule_order(coo, rows, cols, n_blocks=0):
+    """Canonical sequential order of the deterministic schedule -> (permutation, B used)."""
+    coo = np.ascontiguousarray(coo, dtype=RATING_DTYPE)
+    order = np.empty(coo.shape[0], dtype=np.int64)
+    used = C.c_int()
+    check(_lib.load().cu2b_block_schedule_order(_ptr(coo), coo.shape[0], rows, cols, n_blocks, _ptr(order), C.byref(used)))
+    return order, used.value
+
+
 # ------------------------------------------------------------------------------------------
 # training.h
 # ------------------------------------------------------------------------------------------

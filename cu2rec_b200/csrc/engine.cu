@@ -22,6 +22,7 @@
 #include <memory>
 #include <vector>
 
+#include "blocked_kernels.cuh"
 #include "cu2b_internal.h"
 #include "loss_kernels.cuh"
 #include "sgd_kernels.cuh"
@@ -184,6 +185,7 @@ cu2b_status download_dense(cudaStream_t st, float *dst, const float *src, int ro
 // ---------------------------------------------------------------------------------------
 typedef void (*SgdKernel)(const SgdParams);
 typedef void (*LossKernel)(const LossParams);
+typedef void (*BlockedKernel)(const BlockedParams);
 
 cu2b_status layout_for(int kp, int *L, int *V) {
     const int vecs = kp / 4;
@@ -195,28 +197,37 @@ cu2b_status layout_for(int kp, int *L, int *V) {
     return CU2B_OK;
 }
 
-template <bool A>
+// Hogwild kernel variants. WMODE 3 (item AND user rows updated with 128-bit L2 atomic adds) is
+// the default: on B200 the red.v4.f32 path is 2-3x faster than read-modify-write stores to the
+// same rows (profiles/r1_sweep1.jsonl) and no SGD step is lost under contention. One rating per
+// group in flight (UNR 1) with >= 5 CTAs/SM beat deeper unrolling at lower occupancy for
+// k = 128 (profiles/r1_sweep2.jsonl). CU2B_WMODE=0..3 switches the write path for A/B profiling.
+template <int W>
 SgdKernel pick_sgd_t(int L, int V) {
     switch (L) {
-        case 1: return mf_sgd_hogwild<1, 1, 2, A>;
-        case 2: return mf_sgd_hogwild<2, 1, 2, A>;
-        case 4: return mf_sgd_hogwild<4, 1, 2, A>;
-        case 8: return mf_sgd_hogwild<8, 1, 2, A>;
-        case 16: return mf_sgd_hogwild<16, 1, 2, A>;
+        case 1: return mf_sgd_hogwild<1, 1, 2, W>;
+        case 2: return mf_sgd_hogwild<2, 1, 2, W>;
+        case 4: return mf_sgd_hogwild<4, 1, 2, W>;
+        case 8: return mf_sgd_hogwild<8, 1, 2, W>;
+        case 16: return mf_sgd_hogwild<16, 1, 2, W>;
         default:
             switch (V) {
-                case 1: return mf_sgd_hogwild<32, 1, 2, A>;
-                case 2: return mf_sgd_hogwild<32, 2, 2, A>;
-                case 3: return mf_sgd_hogwild<32, 3, 1, A>;
-                default: return mf_sgd_hogwild<32, 4, 1, A>;
+                case 1: return mf_sgd_hogwild<32, 1, 1, W, 5>;
+                case 2: return mf_sgd_hogwild<32, 2, 1, W>;
+                case 3: return mf_sgd_hogwild<32, 3, 1, W>;
+                default: return mf_sgd_hogwild<32, 4, 1, W>;
             }
     }
 }
-// Item-side updates as L2 atomic adds unless CU2B_ATOMIC_Q=0 (A/B switch for profiling).
 SgdKernel pick_sgd(int L, int V) {
-    const char *e = getenv("CU2B_ATOMIC_Q");
-    const bool atomq = !(e && e[0] == '0');
-    return atomq ? pick_sgd_t<true>(L, V) : pick_sgd_t<false>(L, V);
+    int w = 3;
+    if (const char *e = getenv("CU2B_WMODE")) w = atoi(e) & 3;
+    switch (w) {
+        case 0: return pick_sgd_t<0>(L, V);
+        case 1: return pick_sgd_t<1>(L, V);
+        case 2: return pick_sgd_t<2>(L, V);
+        default: return pick_sgd_t<3>(L, V);
+    }
 }
 LossKernel pick_loss(int L, int V) {
     switch (L) {
@@ -233,6 +244,57 @@ LossKernel pick_loss(int L, int V) {
                 default: return mf_loss_fused<32, 4>;
             }
     }
+}
+
+BlockedKernel pick_blocked(int L, int V) {
+    switch (L) {
+        case 1: return mf_sgd_blocked_round<1, 1>;
+        case 2: return mf_sgd_blocked_round<2, 1>;
+        case 4: return mf_sgd_blocked_round<4, 1>;
+        case 8: return mf_sgd_blocked_round<8, 1>;
+        case 16: return mf_sgd_blocked_round<16, 1>;
+        default:
+            switch (V) {
+                case 1: return mf_sgd_blocked_round<32, 1>;
+                case 2: return mf_sgd_blocked_round<32, 2>;
+                case 3: return mf_sgd_blocked_round<32, 3>;
+                default: return mf_sgd_blocked_round<32, 4>;
+            }
+    }
+}
+
+// Host side of the deterministic mode: stable counting sort of the ratings by
+// (round, user block) where round = (item block - user block) mod B.
+struct BlockSchedule {
+    int B = 0;
+    std::vector<cu2b_rating> sched;
+    std::vector<int> ptr;  // B*B + 1
+};
+
+int auto_blocks(int rows, int cols) { return std::max(1, std::min(std::min(rows, cols), 2048)); }
+
+cu2b_status build_block_schedule(const cu2b_rating *coo, int64_t n, int rows, int cols, int B, BlockSchedule *out,
+                                 int64_t *order = nullptr) {
+    if (B < 1 || (int64_t)B * B > (1LL << 28)) return cu2b_fail(CU2B_ERR_INVALID, "n_blocks must be in [1, 16384]");
+    const int ubs = std::max(1, (rows + B - 1) / B), ibs = std::max(1, (cols + B - 1) / B);
+    out->B = B;
+    out->ptr.assign((size_t)B * B + 1, 0);
+    auto bucket = [&](const cu2b_rating &r) {
+        const int ub = r.user / ubs, ib = r.item / ibs;
+        const int s = ((ib - ub) % B + B) % B;
+        return (size_t)s * B + ub;
+    };
+    for (int64_t t = 0; t < n; ++t) out->ptr[bucket(coo[t]) + 1]++;
+    for (size_t b = 0; b < (size_t)B * B; ++b) out->ptr[b + 1] += out->ptr[b];
+    std::vector<int> cursor(out->ptr.begin(), out->ptr.end() - 1);
+    out->sched.resize((size_t)n);
+    if (order) {
+        for (int64_t t = 0; t < n; ++t) order[cursor[bucket(coo[t])]++] = t;
+        for (int64_t t = 0; t < n; ++t) out->sched[(size_t)t] = coo[order[t]];
+    } else {
+        for (int64_t t = 0; t < n; ++t) out->sched[(size_t)cursor[bucket(coo[t])]++] = coo[t];
+    }
+    return CU2B_OK;
 }
 
 StreamView flat_view(const cu2b_rating *base, long long n, int chunk) {
@@ -319,6 +381,15 @@ struct cu2b_session {
     int loss_chunk = kChunkMax;
     SgdKernel sgd_kernel = nullptr;
     LossKernel loss_kernel = nullptr;
+    BlockedKernel blocked_kernel = nullptr;
+    // deterministic mode: block schedule on the device + "updates owed" accumulator
+    cu2b_rating *sched = nullptr;
+    int *bucket_ptr = nullptr;
+    int B = 0;
+    long long blocked_budget = 0;
+    // experiment switches (environment): CU2B_TUNE_GATE=0 drops the per-user ordering gate,
+    // CU2B_TUNE_CHUNK overrides the chunk size
+    bool no_gate = false;
     int sm_count = 0;
     int iter_done = 0;  // the reference loop variable i (training.cu:107)
     Timing timing;
@@ -377,11 +448,54 @@ cu2b_status launch_sgd(cu2b_session *s, const StreamView &sv, int *gate, int seg
     sp.gate = gate;
     sp.seg0 = seg0;
     sp.serial = serial;
+    if (s->no_gate) sp.gate = nullptr;
     const int grid = serial ? 1 : (int)std::max<long long>(1, std::min<long long>(sv.num_chunks, s->sgd_grid_max));
     s->sgd_kernel<<<grid, kThreads, 0, s->stream>>>(sp);
     CUDA_TRY(cudaGetLastError());
     s->stats.kernel_launches++;
     s->stats.sgd_launches++;
+    return CU2B_OK;
+}
+
+// One deterministic pass over all training ratings: B rounds, one launch per round.
+cu2b_status enqueue_blocked_pass(cu2b_session *s, const cu2b_rating *sched, const int *bucket_ptr, int B) {
+    constexpr int kBlockedThreads = 256;
+    const int G = 32 / s->L;
+    const int warps = (B + G - 1) / G;
+    const int grid = std::max(1, (warps + kBlockedThreads / 32 - 1) / (kBlockedThreads / 32));
+    BlockedParams bp;
+    bp.sched = sched;
+    bp.B = B;
+    SgdParams &sp = bp.model;
+    memset(&sp, 0, sizeof(sp));
+    sp.P = s->P; sp.Q = s->Q; sp.user_bias = s->ub; sp.item_bias = s->ib;
+    sp.kp = s->kp;
+    sp.mu = s->mu;
+    sp.lr = &s->state->lr;
+    sp.P_reg = s->cfg.P_reg; sp.Q_reg = s->cfg.Q_reg;
+    sp.ub_reg = s->cfg.user_bias_reg; sp.ib_reg = s->cfg.item_bias_reg;
+    sp.is_train = s->cfg.is_train;
+    for (int r = 0; r < B; ++r) {
+        bp.bucket_ptr = bucket_ptr + (size_t)r * B;
+        s->blocked_kernel<<<grid, kBlockedThreads, 0, s->stream>>>(bp);
+    }
+    CUDA_TRY(cudaGetLastError());
+    s->stats.kernel_launches += B;
+    s->stats.sgd_launches += B;
+    return CU2B_OK;
+}
+
+// Deterministic mode inside the training loop: iterations are converted to whole passes at
+// equal update counts (n_seg * n_active updates are owed; a pass pays train.nnz of them).
+cu2b_status enqueue_blocked_iterations(cu2b_session *s, int n_seg) {
+    s->blocked_budget += (long long)n_seg * s->n_active;
+    while (s->train.nnz > 0 && s->blocked_budget >= s->train.nnz) {
+        const int id = s->timing.begin(Timing::SGD, s->stream);
+        CU2B_TRY(enqueue_blocked_pass(s, s->sched, s->bucket_ptr, s->B));
+        s->timing.end(id, s->stream);
+        s->blocked_budget -= s->train.nnz;
+        s->stats.updates += s->train.nnz;
+    }
     return CU2B_OK;
 }
 
@@ -439,8 +553,10 @@ extern "C" cu2b_status cu2b_session_create(cu2b_session **out, int device, const
                          "matrix with max(train, test)", test->rows, test->cols, train->rows, train->cols);
     if (cfg->n_factors < 1) return cu2b_fail(CU2B_ERR_INVALID, "n_factors must be >= 1");
     if (cfg->check_error < 1) return cu2b_fail(CU2B_ERR_INVALID, "check_error must be >= 1");
-    if (cfg->mode != CU2B_MODE_HOGWILD || cfg->sampler != CU2B_SAMPLER_PER_USER)
-        return cu2b_fail(CU2B_ERR_UNSUPPORTED, "session supports mode=hogwild, sampler=per_user in this build");
+    if (cfg->mode != CU2B_MODE_HOGWILD && cfg->mode != CU2B_MODE_DETERMINISTIC)
+        return cu2b_fail(CU2B_ERR_INVALID, "unknown mode %d", cfg->mode);
+    if (cfg->sampler != CU2B_SAMPLER_PER_USER)
+        return cu2b_fail(CU2B_ERR_UNSUPPORTED, "sampler=per_rating is not available in this build");
     CUDA_TRY(cudaSetDevice(device));
     CU2B_TRY(check_device());
     cu2b_session *s = new cu2b_session();
@@ -490,9 +606,11 @@ extern "C" cu2b_status cu2b_session_create(cu2b_session **out, int device, const
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s->loss_kernel, kThreads, 0));
     s->loss_grid_max = std::max(1, occ) * s->sm_count;
 
+    if (const char *e = getenv("CU2B_TUNE_GATE")) s->no_gate = e[0] == '0';
     // update stream geometry: one segment per reference iteration
     s->seg_pitch = ((long long)s->n_active + 3) & ~3LL;
     s->chunk = pick_chunk(s->n_active, s->sgd_grid_max);
+    if (const char *e = getenv("CU2B_TUNE_CHUNK")) s->chunk = std::max(32, std::min(kChunkMax, atoi(e) & ~3));
     s->chunks_per_seg = std::max(1, (s->n_active + s->chunk - 1) / s->chunk);
     const long long cap_ratings = 48LL << 20;  // <= 576 MB of triplets per batch
     s->max_batch_segs = (int)std::max<long long>(1, std::min<long long>(cap_ratings / std::max<long long>(1, s->seg_pitch), 4096));
@@ -501,6 +619,23 @@ extern "C" cu2b_status cu2b_session_create(cu2b_session **out, int device, const
     CUDA_TRY(cudaMemsetAsync(s->gate, 0, (size_t)s->chunks_per_seg * sizeof(int), s->stream));
     s->counter_slots = 256;
     CU2B_TRY(s->pool.alloc(&s->counters, (size_t)s->counter_slots));
+
+    if (cfg->mode == CU2B_MODE_DETERMINISTIC && s->train.nnz > 0) {
+        // block schedule: built on the host from the CSR order, uploaded once
+        std::vector<cu2b_rating> coo((size_t)s->train.nnz);
+        CUDA_TRY(cudaMemcpyAsync(coo.data(), s->train.coo, coo.size() * sizeof(cu2b_rating), cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        BlockSchedule bs;
+        CU2B_TRY(build_block_schedule(coo.data(), (int64_t)coo.size(), s->rows, s->cols,
+                                      cfg->n_blocks > 0 ? cfg->n_blocks : auto_blocks(s->rows, s->cols), &bs));
+        s->B = bs.B;
+        CU2B_TRY(s->pool.alloc(&s->sched, bs.sched.size()));
+        CU2B_TRY(s->pool.alloc(&s->bucket_ptr, bs.ptr.size()));
+        CUDA_TRY(cudaMemcpyAsync(s->sched, bs.sched.data(), bs.sched.size() * sizeof(cu2b_rating), cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(cudaMemcpyAsync(s->bucket_ptr, bs.ptr.data(), bs.ptr.size() * sizeof(int), cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        s->blocked_kernel = pick_blocked(s->L, s->V);
+    }
 
     // loss scratch + device-resident schedule state
     CU2B_TRY(s->pool.alloc(&s->part_train, (size_t)2 * s->loss_grid_max));
@@ -537,8 +672,12 @@ extern "C" cu2b_status cu2b_session_run(cu2b_session *s, int n_iterations) {
         int j = i;
         while (j < end && !is_check(j)) ++j;  // next check iteration (or end)
         const int seg_end = std::min(j + 1, end);
-        if (s->n_active > 0)
-            CU2B_TRY(enqueue_sgd_iterations(s, s->cfg.cur_iterations + i, seg_end - i));
+        if (s->n_active > 0) {
+            if (s->cfg.mode == CU2B_MODE_DETERMINISTIC)
+                CU2B_TRY(enqueue_blocked_iterations(s, seg_end - i));
+            else
+                CU2B_TRY(enqueue_sgd_iterations(s, s->cfg.cur_iterations + i, seg_end - i));
+        }
         if (j < end) CU2B_TRY(enqueue_check(s, j + 1, 1, true));
         i = seg_end;
     }
@@ -842,9 +981,49 @@ extern "C" cu2b_status cu2b_sgd_apply(const cu2b_rating *stream, int64_t n, floa
     return CU2B_OK;
 }
 
-extern "C" cu2b_status cu2b_sgd_blocked(const cu2b_rating *, int64_t, float *, int, float *, int, float *,
-                                        float *, float, const cu2b_config *, int, int) {
-    return cu2b_fail(CU2B_ERR_UNSUPPORTED, "cu2b_sgd_blocked: not built yet");
+extern "C" cu2b_status cu2b_sgd_blocked(const cu2b_rating *coo, int64_t n, float *P, int rows, float *Q, int cols,
+                                        float *ub, float *ib, float mu, const cu2b_config *cfg, int n_blocks,
+                                        int n_passes) {
+    if ((!coo && n > 0) || n < 0 || !P || !Q || !ub || !ib || !cfg || rows < 0 || cols < 0 || n_passes < 0)
+        return cu2b_fail(CU2B_ERR_INVALID, "cu2b_sgd_blocked: bad argument");
+    for (int64_t t = 0; t < n; ++t)
+        if (coo[t].user < 0 || coo[t].user >= rows || coo[t].item < 0 || coo[t].item >= cols)
+            return cu2b_fail(CU2B_ERR_INVALID, "cu2b_sgd_blocked: rating %ld out of range", (long)t);
+    Scratch sc;
+    CU2B_TRY(sc.init(rows, cols, cfg->n_factors, P, Q, ub, ib, mu, cfg));
+    cu2b_session &s = sc.s;
+    if (n > 0 && n_passes > 0) {
+        BlockSchedule bs;
+        CU2B_TRY(build_block_schedule(coo, n, rows, cols, n_blocks > 0 ? n_blocks : auto_blocks(rows, cols), &bs));
+        cu2b_rating *sched;
+        int *ptr;
+        CU2B_TRY(s.pool.alloc(&sched, bs.sched.size()));
+        CU2B_TRY(s.pool.alloc(&ptr, bs.ptr.size()));
+        CUDA_TRY(cudaMemcpyAsync(sched, bs.sched.data(), bs.sched.size() * sizeof(cu2b_rating), cudaMemcpyHostToDevice, s.stream));
+        CUDA_TRY(cudaMemcpyAsync(ptr, bs.ptr.data(), bs.ptr.size() * sizeof(int), cudaMemcpyHostToDevice, s.stream));
+        s.blocked_kernel = pick_blocked(s.L, s.V);
+        for (int pass = 0; pass < n_passes; ++pass) CU2B_TRY(enqueue_blocked_pass(&s, sched, ptr, bs.B));
+    }
+    CU2B_TRY(download_dense(s.stream, P, s.P, rows, s.k, s.kp));
+    CU2B_TRY(download_dense(s.stream, Q, s.Q, cols, s.k, s.kp));
+    CUDA_TRY(cudaMemcpyAsync(ub, s.ub, (size_t)rows * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(cudaMemcpyAsync(ib, s.ib, (size_t)cols * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
+    return CU2B_OK;
+}
+
+extern "C" cu2b_status cu2b_block_schedule_order(const cu2b_rating *coo, int64_t n, int rows, int cols, int n_blocks,
+                                                 int64_t *order, int *n_blocks_used) {
+    if ((!coo && n > 0) || n < 0 || !order || rows < 0 || cols < 0)
+        return cu2b_fail(CU2B_ERR_INVALID, "cu2b_block_schedule_order: bad argument");
+    for (int64_t t = 0; t < n; ++t)
+        if (coo[t].user < 0 || coo[t].user >= rows || coo[t].item < 0 || coo[t].item >= cols)
+            return cu2b_fail(CU2B_ERR_INVALID, "cu2b_block_schedule_order: rating %ld out of range", (long)t);
+    BlockSchedule bs;
+    const int B = n_blocks > 0 ? n_blocks : auto_blocks(rows, cols);
+    CU2B_TRY(build_block_schedule(coo, n, rows, cols, B, &bs, order));
+    if (n_blocks_used) *n_blocks_used = B;
+    return CU2B_OK;
 }
 
 extern "C" cu2b_status cu2b_device_info(int device, char *name, int name_cap, int *sm_count, int *cc_major,

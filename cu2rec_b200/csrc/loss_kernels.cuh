@@ -46,7 +46,7 @@ mf_loss_fused(const LossParams p) {
                     next += gridDim.x;
                     return c < p.sv.num_chunks ? c : -1LL;
                 },
-                [](long long, int) {});
+                [](long long, int, int) {});
         }
         return;
     }

@@ -83,34 +83,41 @@ __device__ __forceinline__ float group_sum(float a) {
     return a;
 }
 
-// Processes UNR ratings (one per slot) for this lane's group. `ok[x]` false => slot idle.
 // 128-bit fire-and-forget float add at L2 (SASS REDG.E.ADD.F32x4): concurrent Hogwild updates of
-// one item row accumulate instead of overwriting each other.
+// one row accumulate instead of overwriting each other.
 __device__ __forceinline__ void red_add_v4(float4 *addr, float4 v) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y),
                  "f"(v.z), "f"(v.w)
                  : "memory");
 }
-
-// ATOMQ: item-side updates (Q row, item_bias) are applied as atomic adds of the SGD step
-// instead of read-modify-write stores. Same arithmetic (q + step, one rounding) when an item is
-// touched by one update at a time; under contention no step is lost.
-template <int L, int V, int UNR, bool ATOMQ>
+__device__ __forceinline__ void red_add_f32(float *addr, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+// Model rows are read-write data shared by every SM: they are read with ld.global.cg and, on
+// the non-atomic path, written with st.global.cg (L2 only; SASS LDG/STG .STRONG.GPU) so that no
+// stale copy can sit in the non-coherent L1. Measured on B200 (profiles/r1_sweep2.jsonl): weak
+// L1::no_allocate loads are ~18 % slower, weak stores change nothing.
+// Processes UNR ratings (one per slot) for this lane's group. `ok[x]` false => slot idle.
+// WMODE bit 0: item-side updates (Q row, item_bias) are applied as atomic adds of the SGD step
+// instead of read-modify-write stores; bit 1: the same for the user side (P row, user_bias).
+// Same arithmetic (x + step, one rounding) when a row is touched by one update at a time;
+// under contention no step is lost.
+template <int L, int V, int UNR, int WMODE>
 __device__ __forceinline__ void sgd_update_slots(const SgdParams &p, const cu2b_rating *rt,
                                                  const bool *ok, int l, int vecs, float lr) {
+    constexpr bool ATOMQ = (WMODE & 1) != 0, ATOMP = (WMODE & 2) != 0;
     float4 pv[UNR][V], qv[UNR][V];
     float ub[UNR], ib[UNR];
-    float4 *prow[UNR], *qrow[UNR];
+    float4 *const Pv = reinterpret_cast<float4 *>(p.P);
+    float4 *const Qv = reinterpret_cast<float4 *>(p.Q);
 #pragma unroll
     for (int x = 0; x < UNR; ++x) {
-        prow[x] = reinterpret_cast<float4 *>(p.P + (size_t)rt[x].user * p.kp);
-        qrow[x] = reinterpret_cast<float4 *>(p.Q + (size_t)rt[x].item * p.kp);
+        const size_t po = (size_t)rt[x].user * vecs + l, qo = (size_t)rt[x].item * vecs + l;
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-            const int idx = v * L + l;
-            if (ok[x] && idx < vecs) {
-                pv[x][v] = __ldcg(prow[x] + idx);
-                qv[x][v] = __ldcg(qrow[x] + idx);
+            if (ok[x] && v * L + l < vecs) {
+                pv[x][v] = __ldcg(Pv + po + v * L);
+                qv[x][v] = __ldcg(Qv + qo + v * L);
             } else {
                 pv[x][v] = make_float4(0.f, 0.f, 0.f, 0.f);
                 qv[x][v] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -132,46 +139,53 @@ __device__ __forceinline__ void sgd_update_slots(const SgdParams &p, const cu2b_
         const float dot = group_sum<L>(acc);
         const float pred = __fadd_rn(__fadd_rn(__fadd_rn(p.mu, ub[x]), ib[x]), dot);
         const float err = __fsub_rn(rt[x].rating, pred);
+        const size_t po = (size_t)rt[x].user * vecs + l, qo = (size_t)rt[x].item * vecs + l;
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-            const int idx = v * L + l;
             const float4 a = pv[x][v], b = qv[x][v];
             float4 na, nb;
-            na.x = __fadd_rn(a.x, __fmul_rn(lr, __fsub_rn(__fmul_rn(err, b.x), __fmul_rn(p.P_reg, a.x))));
-            na.y = __fadd_rn(a.y, __fmul_rn(lr, __fsub_rn(__fmul_rn(err, b.y), __fmul_rn(p.P_reg, a.y))));
-            na.z = __fadd_rn(a.z, __fmul_rn(lr, __fsub_rn(__fmul_rn(err, b.z), __fmul_rn(p.P_reg, a.z))));
-            na.w = __fadd_rn(a.w, __fmul_rn(lr, __fsub_rn(__fmul_rn(err, b.w), __fmul_rn(p.P_reg, a.w))));
+            na.x = __fmul_rn(lr, __fsub_rn(__fmul_rn(err, b.x), __fmul_rn(p.P_reg, a.x)));
+            na.y = __fmul_rn(lr, __fsub_rn(__fmul_rn(err, b.y), __fmul_rn(p.P_reg, a.y)));
+            na.z = __fmul_rn(lr, __fsub_rn(__fmul_rn(err, b.z), __fmul_rn(p.P_reg, a.z)));
+            na.w = __fmul_rn(lr, __fsub_rn(__fmul_rn(err, b.w), __fmul_rn(p.P_reg, a.w)));
             nb.x = __fmul_rn(lr, __fsub_rn(__fmul_rn(err, a.x), __fmul_rn(p.Q_reg, b.x)));
             nb.y = __fmul_rn(lr, __fsub_rn(__fmul_rn(err, a.y), __fmul_rn(p.Q_reg, b.y)));
             nb.z = __fmul_rn(lr, __fsub_rn(__fmul_rn(err, a.z), __fmul_rn(p.Q_reg, b.z)));
             nb.w = __fmul_rn(lr, __fsub_rn(__fmul_rn(err, a.w), __fmul_rn(p.Q_reg, b.w)));
-            if (ok[x] && idx < vecs) {
-                __stcg(prow[x] + idx, na);
+            if (ok[x] && v * L + l < vecs) {
+                if (ATOMP) {
+                    red_add_v4(Pv + po + v * L, na);
+                } else {
+                    na.x = __fadd_rn(a.x, na.x); na.y = __fadd_rn(a.y, na.y);
+                    na.z = __fadd_rn(a.z, na.z); na.w = __fadd_rn(a.w, na.w);
+                    __stcg(Pv + po + v * L, na);
+                }
                 if (p.is_train) {
                     if (ATOMQ) {
-                        red_add_v4(qrow[x] + idx, nb);
+                        red_add_v4(Qv + qo + v * L, nb);
                     } else {
                         nb.x = __fadd_rn(b.x, nb.x); nb.y = __fadd_rn(b.y, nb.y);
                         nb.z = __fadd_rn(b.z, nb.z); nb.w = __fadd_rn(b.w, nb.w);
-                        __stcg(qrow[x] + idx, nb);
+                        __stcg(Qv + qo + v * L, nb);
                     }
                 }
             }
         }
         if (ok[x] && l == 0) {
-            __stcg(p.user_bias + rt[x].user,
-                   __fadd_rn(ub[x], __fmul_rn(lr, __fsub_rn(err, __fmul_rn(p.ub_reg, ub[x])))));
+            const float ustep = __fmul_rn(lr, __fsub_rn(err, __fmul_rn(p.ub_reg, ub[x])));
+            if (ATOMP) red_add_f32(p.user_bias + rt[x].user, ustep);
+            else __stcg(p.user_bias + rt[x].user, __fadd_rn(ub[x], ustep));
             if (p.is_train) {
                 const float step = __fmul_rn(lr, __fsub_rn(err, __fmul_rn(p.ib_reg, ib[x])));
-                if (ATOMQ) atomicAdd(p.item_bias + rt[x].item, step);
+                if (ATOMQ) red_add_f32(p.item_bias + rt[x].item, step);
                 else __stcg(p.item_bias + rt[x].item, __fadd_rn(ib[x], step));
             }
         }
     }
 }
 
-template <int L, int V, int UNR, bool ATOMQ>
-__global__ void __launch_bounds__(kThreads)
+template <int L, int V, int UNR, int WMODE, int OCC = 1>
+__global__ void __launch_bounds__(kThreads, OCC)
 mf_sgd_hogwild(const SgdParams p) {
     __shared__ StreamSmem sm;
     pipe_init(sm);
@@ -184,10 +198,10 @@ mf_sgd_hogwild(const SgdParams p) {
                     const unsigned long long c = atomicAdd(p.chunk_counter, 1ULL);
                     return c < (unsigned long long)p.sv.num_chunks ? (long long)c : -1LL;
                 },
-                [&](long long seg, int j) {
+                [&](long long seg, int j, int) {
                     if (p.gate) {
                         const int want = p.seg0 + (int)seg;
-                        while (ld_acquire_gpu(p.gate + j) < want) __nanosleep(64);
+                        while (ld_acquire_gpu(p.gate + j) < want) __nanosleep(32);
                     }
                 });
         }
@@ -210,7 +224,7 @@ mf_sgd_hogwild(const SgdParams p) {
                 const bool ok = (g == 0);
                 for (int j = 0; j < cnt; ++j) {
                     const cu2b_rating rt = sm.stage[s][j];
-                    sgd_update_slots<L, V, 1, false>(p, &rt, &ok, l, vecs, lr);
+                    sgd_update_slots<L, V, 1, 0>(p, &rt, &ok, l, vecs, lr);
                     __syncwarp();
                 }
             }
@@ -225,20 +239,20 @@ mf_sgd_hogwild(const SgdParams p) {
                     ok[x] = j < cnt;
                     rt[x] = sm.stage[s][ok[x] ? j : 0];
                 }
-                sgd_update_slots<L, V, UNR, ATOMQ>(p, rt, ok, l, vecs, lr);
+                sgd_update_slots<L, V, UNR, WMODE>(p, rt, ok, l, vecs, lr);
             }
         }
         __syncwarp();
         if (lane == 0) {
             if (p.gate) {
-                // last consumer warp out publishes "chunk j of this segment is complete"
-                __threadfence();
-                if (atomicAdd(&sm.done[s], 1) == kConsumerWarps - 1) {
+                // Last consumer warp out publishes "chunk j of this segment is complete".
+                // Release chain: each warp's row updates -> (acq_rel at CTA scope on the shared
+                // counter) -> the last warp -> st.release.gpu on the gate word (cumulative).
+                if (atom_add_acq_rel_cta_shared(&sm.done[s], 1) == kConsumerWarps - 1) {
                     sm.done[s] = 0;
                     const long long c = sm.chunk_id[s];
                     const long long seg = c / p.sv.chunks_per_seg;
                     const int j = (int)(c - seg * p.sv.chunks_per_seg);
-                    __threadfence();
                     st_release_gpu(p.gate + j, p.seg0 + (int)seg + 1);
                 }
             }

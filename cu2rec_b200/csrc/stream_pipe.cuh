@@ -93,11 +93,16 @@ __device__ __forceinline__ void st_release_gpu(int *p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ int atom_add_acq_rel_cta_shared(int *p, int v) {
+    int old;
+    asm volatile("atom.acq_rel.cta.shared.add.s32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+    return old;
+}
 // Call with all threads of the CTA before the role split.
 __device__ __forceinline__ void pipe_init(StreamSmem &sm) {
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
-            mbar_init(&sm.full[s], 1);
+            mbar_init(&sm.full[s], 2);  // TMA issue (+ tx bytes) and the ordering gate
             mbar_init(&sm.empty[s], kConsumerWarps);
             sm.done[s] = 0;
         }
@@ -107,7 +112,9 @@ __device__ __forceinline__ void pipe_init(StreamSmem &sm) {
 }
 
 // Producer loop (one lane). next_chunk() yields the next chunk index for this CTA or -1;
-// gate(seg, j) blocks until chunk j of segment `seg` may be processed (no-op when ungated).
+// gate(seg, j, cnt) blocks until chunk j of segment `seg` may be processed (no-op when
+// ungated). The triplet copy is issued BEFORE the gate is polled so its latency overlaps the
+// wait; consumers are released by the second arrival on the stage's full barrier.
 template <typename NextChunk, typename Gate>
 __device__ __forceinline__ void pipe_produce(StreamSmem &sm, const StreamView &sv,
                                              NextChunk next_chunk, Gate gate) {
@@ -119,6 +126,7 @@ __device__ __forceinline__ void pipe_produce(StreamSmem &sm, const StreamView &s
         if (c < 0) {
             sm.count[s] = -1;
             mbar_arrive(&sm.full[s]);
+            mbar_arrive(&sm.full[s]);
             break;
         }
         const long long seg = c / sv.chunks_per_seg;
@@ -126,11 +134,12 @@ __device__ __forceinline__ void pipe_produce(StreamSmem &sm, const StreamView &s
         const int left = sv.seg_len - j * sv.chunk;
         const int cnt = left < sv.chunk ? left : sv.chunk;
         sm.count[s] = cnt;
-        gate(seg, j);
         const uint32_t bytes = (uint32_t)(((cnt + 3) & ~3) * (int)sizeof(cu2b_rating));
         mbar_arrive_expect_tx(&sm.full[s], bytes);
         tma_load_1d(&sm.stage[s][0], sv.base + seg * sv.seg_pitch + (long long)j * sv.chunk, bytes,
                     &sm.full[s]);
+        gate(seg, j, cnt);
+        mbar_arrive(&sm.full[s]);
     }
 }
 

@@ -165,6 +165,11 @@ cu2b_status cu2b_sgd_blocked(const cu2b_rating *coo, int64_t n, float *P, int ro
                              int cols, float *user_bias, float *item_bias, float global_bias,
                              const cu2b_config *cfg, int n_blocks, int n_passes);
 
+/* Host-only helper: the canonical sequential order of that schedule (a permutation of [0,n));
+ * n_blocks == 0 selects the automatic B, reported through n_blocks_used. No GPU needed. */
+cu2b_status cu2b_block_schedule_order(const cu2b_rating *coo, int64_t n, int rows, int cols,
+                                      int n_blocks, int64_t *order, int *n_blocks_used);
+
 /* ------------------------------------------------------------------------------------
  * Training (training.h:12-15 train()).
  * ---------------------------------------------------------------------------------- */

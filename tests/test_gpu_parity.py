@@ -257,6 +257,47 @@ def test_update_vs_reference_sgd_kernel(tmp_path, k):
 
 
 # ---------------------------------------------------------------------------------------------
+# deterministic conflict-free mode vs the mf_sequential update on the same ordering
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k,B", [(1, 4), (8, 16), (32, 7), (50, 64), (128, 32), (256, 16), (300, 8)])
+def test_blocked_mode_bit_exact_vs_sequential_replay(k, B):
+    """cu2b_sgd_blocked == sequential replay of the same ratings in the schedule's canonical order
+    with the oracle's KERNEL flavour, bit for bit (two passes, heavy row reuse); and within a
+    stated fp32 tolerance (5e-5 abs) of the mf_sequential.cu:114-141 op order (REF flavour)."""
+    rng = np.random.RandomState(600 + k)
+    U, I, n = 300, 200, 20000
+    coo = np.zeros(n, dtype=cu.RATING_DTYPE)
+    coo["user"], coo["item"], coo["rating"] = np.sort(rng.randint(0, U, n)), rng.randint(0, I, n), rng.randint(1, 6, n)
+    P, Q, ub, ib = _model(rng, U, I, k)
+    cfg = cu.Config(n_factors=k, learning_rate=0.02, P_reg=0.03, Q_reg=0.04, user_bias_reg=0.05, item_bias_reg=0.06)
+    got = cu.sgd_blocked(coo, P, Q, ub, ib, 3.5, cfg, B, n_passes=2)
+    order = O.block_schedule_order(coo, U, I, B)
+    replay = np.concatenate([coo[order], coo[order]])
+    want = O.sgd_apply_stream(replay, P.ravel(), Q.ravel(), ub, ib, 3.5, O.hyper_from_cfg(cfg), O.FLAVOUR_KERNEL)
+    for g, w in zip(got, want):
+        assert g.ravel().view(np.uint32).tolist() == w.view(np.uint32).tolist()
+    ref = O.sgd_apply_stream(replay, P.ravel(), Q.ravel(), ub, ib, 3.5, O.hyper_from_cfg(cfg), O.FLAVOUR_REF)
+    for g, w in zip(got, ref):
+        np.testing.assert_allclose(g.ravel(), w, rtol=0, atol=5e-5)
+    again = cu.sgd_blocked(coo, P, Q, ub, ib, 3.5, cfg, B, n_passes=2)
+    for g, a in zip(got, again):
+        assert np.array_equal(g, a)  # run-to-run reproducible
+
+
+def test_blocked_mode_training_is_reproducible_and_converges():
+    tr, te, mtr, mte, mu = _small_problem(U=800, I=300, n=40000)
+    outs = []
+    for _ in range(2):
+        cfg = cu.Config(total_iterations=200, n_factors=16, check_error=50, mode=cu.MODE_DETERMINISTIC, n_blocks=32)
+        outs.append(cu.train(mtr, mte, cfg, mu))
+    a, b = outs
+    assert [r["test_rmse"] for r in a["log"]] == [r["test_rmse"] for r in b["log"]]
+    assert np.array_equal(a["P"], b["P"]) and np.array_equal(a["Q"], b["Q"])
+    assert a["log"][-1]["test_rmse"] < a["log"][0]["test_rmse"]
+    assert a["stats"]["updates"] == (200 * 800 // mtr.nonzeros) * mtr.nonzeros  # whole passes only
+
+
+# ---------------------------------------------------------------------------------------------
 # training loop (training.cu)
 # ---------------------------------------------------------------------------------------------
 def test_training_loop_reference_test(fixtures_dir):
@@ -306,21 +347,26 @@ def test_training_rmse_parity_vs_oracle_trainer(k):
 
 def test_training_schedule_on_device_follows_reference_rule():
     """training.cu:129,146-155 evaluated on the device: replaying the rule on the validation RMSE
-    sequence the run itself logged must reproduce the logged learning rates exactly."""
+    sequence the run itself logged must reproduce the logged learning rates exactly. The
+    validation set holds the training pairs with inverted ratings, so fitting the training set
+    makes validation worse and the schedule is guaranteed to fire."""
     tr, te, mtr, mte, mu = _small_problem(U=600, I=200, n=20000)
-    cfg = cu.Config(total_iterations=400, n_factors=8, check_error=20, learning_rate=0.2, patience=1.0)
-    out = cu.train(mtr, mte, cfg, mu)
+    inv = tr.copy()
+    inv["rating"] = 6.0 - inv["rating"]
+    minv = cu.createSparseMatrix(inv, mtr.rows, mtr.cols)
+    cfg = cu.Config(total_iterations=200, n_factors=8, check_error=20, learning_rate=0.05, patience=2.0)
+    out = cu.train(mtr, minv, cfg, mu)
     f = np.float32
-    lr, patience, val = f(0.2), 1, np.finfo(np.float32).max
+    lr, patience, val = f(0.05), 2, np.finfo(np.float32).max
     for row in out["log"]:
         last, val = val, f(row["test_rmse"])
         if last < val:
             patience -= 1
         if patience <= 0:
-            patience, lr = 1, f(lr * f(0.2))
+            patience, lr = 2, f(lr * f(0.2))
         assert row["learning_rate"] == lr, row
-    assert out["log"][-1]["learning_rate"] < f(0.2)  # the schedule really fired
-    assert cfg.learning_rate == out["log"][-1]["learning_rate"] and cfg.cur_iterations == 400
+    assert out["log"][-1]["learning_rate"] < f(0.05) * f(0.2) * 1.01  # fired at least once
+    assert cfg.learning_rate == out["log"][-1]["learning_rate"] and cfg.cur_iterations == 200
 
 
 def test_session_resume_equals_single_run():

@@ -229,3 +229,25 @@ def test_synth_ratings_contract():
     assert pop[0] > 8 * np.median(pop) and act[0] > 5 * np.median(act)
     tri, _ = cu.synth_ratings(200, 300, 5000, integer_ratings=True)
     assert set(np.unique(tri["rating"])) <= {1.0, 2.0, 3.0, 4.0, 5.0}
+
+
+@pytest.mark.parametrize("B", [1, 2, 7, 16, 64])
+def test_block_schedule_matches_oracle_and_is_conflict_free(B):
+    rng = np.random.RandomState(B)
+    U, I, n = 97, 61, 5000
+    coo = np.zeros(n, dtype=cu.RATING_DTYPE)
+    coo["user"], coo["item"], coo["rating"] = np.sort(rng.randint(0, U, n)), rng.randint(0, I, n), rng.randint(1, 6, n)
+    order, used = cu.block_schedule_order(coo, U, I, B)
+    assert used == B and sorted(order.tolist()) == list(range(n))
+    assert order.tolist() == O.block_schedule_order(coo, U, I, B).tolist()
+    # blocks that share a round never share a user block or an item block
+    ubs, ibs = -(-U // B), -(-I // B)
+    ub, ib = coo["user"][order] // ubs, coo["item"][order] // ibs
+    rnd = (ib - ub) % B
+    assert np.all(np.diff(rnd) >= 0)  # round-major
+    for s in range(B):
+        sel = rnd == s
+        pairs = set(zip(ub[sel].tolist(), ib[sel].tolist()))
+        assert len({a for a, _ in pairs}) == len(pairs) == len({b for _, b in pairs})
+    _, auto = cu.block_schedule_order(coo, U, I, 0)
+    assert auto == min(U, I)
