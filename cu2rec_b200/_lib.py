@@ -78,10 +78,20 @@ SYMBOLS = {
     "cu2b_session_get_config": (C.c_int, [_P, C.POINTER(Config)]),
     "cu2b_session_stats": (C.c_int, [_P, C.POINTER(Stats), C.c_int]),
     "cu2b_session_destroy": (None, [_P]),
+    "cu2b_dsgd_partition": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
+    "cu2b_dsgd_extract_strip": (C.c_int, [_P, C.c_int64, _P, _P, _P, C.c_int, _P, C.POINTER(C.c_int64)]),
+    "cu2b_dsgd_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, C.POINTER(Csr), C.POINTER(Csr),
+                                   C.POINTER(Config), _P, _P, _P, _P, C.c_float, _P, _P, C.c_int64, C.c_int64, C.c_int64, _P]),
+    "cu2b_dsgd_connect": (C.c_int, [_P, _P]),
+    "cu2b_dsgd_run": (C.c_int, [_P, C.c_int]),
+    "cu2b_dsgd_session": (_P, [_P]),
+    "cu2b_dsgd_local_sums": (C.c_int, [_P, C.POINTER(C.c_double)]),
+    "cu2b_dsgd_destroy": (None, [_P]),
     "cu2b_device_info": (C.c_int, [C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                    C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
 }
 
+DSGD_HANDLE_BYTES = 512
 _lib = None
 
 

@@ -346,6 +346,142 @@ class Session:
             pass
 
 
+# ------------------------------------------------------------------------------------------
+# multi-GPU DSGD
+# ------------------------------------------------------------------------------------------
+@dataclass
+class DsgdPartition:
+    world: int
+    user_block: np.ndarray       # [U] block of original user
+    user_local: np.ndarray       # [U] index inside its block
+    users_per_block: np.ndarray  # [G]
+    item_new: np.ndarray         # [I] renumbered item id
+    item_block_ptr: np.ndarray   # [G+1]
+    block_nnz: np.ndarray        # [G, G]
+
+
+def dsgd_partition(train, rows, cols, world):
+    """LPT-balanced user / item blocks for DSGD (host only)."""
+    train = np.ascontiguousarray(train, dtype=RATING_DTYPE)
+    ub, ul = np.empty(rows, np.int32), np.empty(rows, np.int32)
+    upb = np.empty(world, np.int32)
+    inew, iptr = np.empty(cols, np.int32), np.empty(world + 1, np.int32)
+    nnz = np.empty(world * world, np.int64)
+    check(_lib.load().cu2b_dsgd_partition(_ptr(train), train.shape[0], rows, cols, world, _ptr(ub), _ptr(ul), _ptr(upb),
+                                          _ptr(inew), _ptr(iptr), _ptr(nnz)))
+    return DsgdPartition(world, ub, ul, upb, inew, iptr, nnz.reshape(world, world))
+
+
+def dsgd_extract_strip(ratings, part, rank):
+    """Ratings of one rank: local user ids, renumbered items, original per-user order."""
+    lib = _lib.load()
+    ratings = np.ascontiguousarray(ratings, dtype=RATING_DTYPE)
+    n = C.c_int64()
+    args = (_ptr(ratings), ratings.shape[0], _ptr(part.user_block), _ptr(part.user_local), _ptr(part.item_new), rank)
+    check(lib.cu2b_dsgd_extract_strip(*args, None, C.byref(n)))
+    out = np.empty(n.value, dtype=RATING_DTYPE)
+    check(lib.cu2b_dsgd_extract_strip(*args, _ptr(out), C.byref(n)))
+    return out
+
+
+@dataclass
+class DsgdRankInputs:
+    train: "CSRMatrix"
+    test: "CSRMatrix"
+    P: np.ndarray
+    Q: np.ndarray
+    user_bias: np.ndarray
+    item_bias: np.ndarray
+    user_ids: np.ndarray
+    n_train_global: int
+    n_test_global: int
+    n_active_global: int
+
+
+def dsgd_rank_inputs(train, test, rows, cols, part, rank, P, Q, user_bias, item_bias):
+    """Slices the global problem (original ids) into what rank `rank` owns."""
+    k = P.size // rows
+    users = np.flatnonzero(part.user_block == rank).astype(np.int32)  # ascending == local order
+    tr, te = dsgd_extract_strip(train, part, rank), dsgd_extract_strip(test, part, rank)
+    n_local = len(users)
+    inv = np.empty(cols, np.int64)
+    inv[part.item_new] = np.arange(cols)
+    n_active = int(len(np.unique(np.ascontiguousarray(train)["user"])))
+    return DsgdRankInputs(createSparseMatrix(tr, n_local, cols), createSparseMatrix(te, n_local, cols),
+                          _f32(P).reshape(rows, k)[users].copy(), _f32(Q).reshape(cols, k)[inv].copy(),
+                          _f32(user_bias)[users].copy(), _f32(item_bias)[inv].copy(), users,
+                          int(len(train)), int(len(test)), n_active)
+
+
+class Dsgd:
+    """One DSGD rank (cu2b_dsgd_*). Exchange `handle` between ranks, then connect() and run()."""
+
+    def __init__(self, rank, world, inputs, part, cfg, global_bias, device=0):
+        self.lib = _lib.load()
+        self.h = C.c_void_p()
+        self.rank, self.world, self.cfg = rank, world, cfg
+        self.k = cfg.n_factors
+        self.rows, self.cols = inputs.train.rows, inputs.train.cols
+        self._keep = inputs
+        blob = C.create_string_buffer(_lib.DSGD_HANDLE_BYTES)
+        tm, te = inputs.train.c(), inputs.test.c()
+        iptr = np.ascontiguousarray(part.item_block_ptr, dtype=np.int32)
+        check(self.lib.cu2b_dsgd_create(C.byref(self.h), device, rank, world, C.byref(tm), C.byref(te), C.byref(cfg.c),
+                                        _ptr(inputs.P), _ptr(inputs.Q), _ptr(inputs.user_bias), _ptr(inputs.item_bias),
+                                        float(global_bias), _ptr(inputs.user_ids), _ptr(iptr), inputs.n_train_global,
+                                        inputs.n_test_global, inputs.n_active_global, blob))
+        self.handle = blob.raw
+
+    def connect(self, handles):
+        """handles: list of `world` blobs in rank order."""
+        buf = b"".join(handles)
+        assert len(buf) == self.world * _lib.DSGD_HANDLE_BYTES
+        check(self.lib.cu2b_dsgd_connect(self.h, buf))
+
+    def run(self, n_iterations):
+        check(self.lib.cu2b_dsgd_run(self.h, n_iterations))
+
+    def _session(self):
+        return C.c_void_p(self.lib.cu2b_dsgd_session(self.h))
+
+    def log(self):
+        cap = self.cfg.total_iterations // max(1, self.cfg.check_error) + 8
+        buf = (Metrics * cap)()
+        n = C.c_int()
+        check(self.lib.cu2b_session_log(self._session(), buf, cap, C.byref(n)))
+        return _metrics_rows(buf, min(cap, n.value))
+
+    def stats(self, reset=False):
+        st = Stats()
+        check(self.lib.cu2b_session_stats(self._session(), C.byref(st), int(reset)))
+        return _stats_dict(st)
+
+    def local_sums(self):
+        out = (C.c_double * 4)()
+        check(self.lib.cu2b_dsgd_local_sums(self.h, out))
+        return list(out)
+
+    def download(self):
+        """-> (P strip, Q in renumbered item order, user_bias strip, item_bias renumbered)."""
+        P = np.empty((self.rows, self.k), dtype=np.float32)
+        Q = np.empty((self.cols, self.k), dtype=np.float32)
+        ub = np.empty(self.rows, dtype=np.float32)
+        ib = np.empty(self.cols, dtype=np.float32)
+        check(self.lib.cu2b_session_download(self._session(), _ptr(P), _ptr(Q), _ptr(ub), _ptr(ib)))
+        return P, Q, ub, ib
+
+    def close(self):
+        if self.h:
+            self.lib.cu2b_dsgd_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def device_info(device=0):
     lib = _lib.load()
     name = C.create_string_buffer(256)

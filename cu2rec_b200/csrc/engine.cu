@@ -24,6 +24,7 @@
 
 #include "blocked_kernels.cuh"
 #include "cu2b_internal.h"
+#include "dsgd_kernels.cuh"
 #include "loss_kernels.cuh"
 #include "sgd_kernels.cuh"
 
@@ -364,6 +365,7 @@ struct cu2b_session {
     float *P = nullptr, *Q = nullptr, *ub = nullptr, *ib = nullptr;
     int *active = nullptr;
     int n_active = 0;
+    int *user_ids = nullptr;  // DSGD: original user id of each local user (sampler key), else null
     // update stream
     cu2b_rating *stream_buf = nullptr;
     long long seg_pitch = 0;
@@ -401,6 +403,15 @@ struct cu2b_session {
 
 namespace {
 
+cu2b_status check_device_error(cu2b_session *s) {
+    DevState st;
+    CUDA_TRY(cudaMemcpy(&st, s->state, sizeof(st), cudaMemcpyDeviceToHost));
+    if (st.error)
+        return cu2b_fail(CU2B_ERR_CUDA, "device-side wait timed out (code %d): %s", st.error,
+                         st.error == 2 ? "per-user ordering gate" : "DSGD peer did not deliver");
+    return CU2B_OK;
+}
+
 cu2b_status launch_loss(cu2b_session *s, const DevMatrix &m, double *partials, int *nblk, float *err_out) {
     LossParams lp;
     lp.sv = flat_view(m.coo, m.nnz, s->loss_chunk);
@@ -431,7 +442,8 @@ cu2b_status enqueue_check(cu2b_session *s, int iteration_1based, int apply_sched
     return CU2B_OK;
 }
 
-cu2b_status launch_sgd(cu2b_session *s, const StreamView &sv, int *gate, int seg0, int serial) {
+cu2b_status launch_sgd(cu2b_session *s, const StreamView &sv, int *gate, int seg0, int serial,
+                       const int *dyn_range = nullptr) {
     SgdParams sp;
     sp.sv = sv;
     sp.P = s->P; sp.Q = s->Q; sp.user_bias = s->ub; sp.item_bias = s->ib;
@@ -448,8 +460,11 @@ cu2b_status launch_sgd(cu2b_session *s, const StreamView &sv, int *gate, int seg
     sp.gate = gate;
     sp.seg0 = seg0;
     sp.serial = serial;
+    sp.dyn_range = dyn_range;
+    sp.error_flag = &s->state->error;
     if (s->no_gate) sp.gate = nullptr;
-    const int grid = serial ? 1 : (int)std::max<long long>(1, std::min<long long>(sv.num_chunks, s->sgd_grid_max));
+    const int grid = serial ? 1 : dyn_range ? s->sgd_grid_max
+                                            : (int)std::max<long long>(1, std::min<long long>(sv.num_chunks, s->sgd_grid_max));
     s->sgd_kernel<<<grid, kThreads, 0, s->stream>>>(sp);
     CUDA_TRY(cudaGetLastError());
     s->stats.kernel_launches++;
@@ -468,6 +483,8 @@ cu2b_status enqueue_blocked_pass(cu2b_session *s, const cu2b_rating *sched, cons
     bp.B = B;
     SgdParams &sp = bp.model;
     memset(&sp, 0, sizeof(sp));
+    sp.dyn_range = nullptr;
+    sp.error_flag = nullptr;
     sp.P = s->P; sp.Q = s->Q; sp.user_bias = s->ub; sp.item_bias = s->ib;
     sp.kp = s->kp;
     sp.mu = s->mu;
@@ -510,7 +527,7 @@ cu2b_status enqueue_sgd_iterations(cu2b_session *s, int iter_abs, int n_seg) {
             const int grid = (int)std::min<long long>((draws + 255) / 256, (long long)s->sm_count * 16);
             sample_per_user_kernel<<<grid, 256, 0, s->stream>>>(
                 s->train.indptr, s->train.coo, s->active, s->n_active, (uint32_t)s->cfg.seed, iter_abs,
-                draws, s->stream_buf, s->seg_pitch);
+                draws, s->stream_buf, s->seg_pitch, s->user_ids);
             CUDA_TRY(cudaGetLastError());
             s->stats.kernel_launches++;
             s->timing.end(id, s->stream);
@@ -684,6 +701,7 @@ extern "C" cu2b_status cu2b_session_run(cu2b_session *s, int n_iterations) {
     s->timing.end(tot_id, s->stream);
     CUDA_TRY(cudaStreamSynchronize(s->stream));  // the only host sync of the loop
     s->iter_done = end;
+    CU2B_TRY(check_device_error(s));
     double ms[Timing::NKIND] = {0, 0, 0, 0};
     s->timing.collect(ms);
     s->stats.sgd_ms += ms[Timing::SGD];
@@ -949,7 +967,7 @@ extern "C" cu2b_status cu2b_sample_per_user(const cu2b_csr *m, int seed, int ite
     CUDA_TRY(cudaMemcpy(act_dev, active.data(), active.size() * sizeof(int), cudaMemcpyHostToDevice));
     const int grid = (int)std::min<long long>((draws + 255) / 256, 148 * 16);
     sample_per_user_kernel<<<grid, 256, 0, st>>>(dm.indptr, dm.coo, act_dev, (int)active.size(), (uint32_t)seed,
-                                                 iter0, draws, out_dev, (long long)active.size());
+                                                 iter0, draws, out_dev, (long long)active.size(), nullptr);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpy(out, out_dev, (size_t)draws * sizeof(cu2b_rating), cudaMemcpyDeviceToHost));
     return CU2B_OK;
@@ -1043,3 +1061,5 @@ extern "C" cu2b_status cu2b_device_info(int device, char *name, int name_cap, in
     }
     return CU2B_OK;
 }
+
+#include "dsgd.inc"

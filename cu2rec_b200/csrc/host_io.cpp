@@ -627,3 +627,87 @@ extern "C" cu2b_status cu2b_synth_ratings(int users, int items, int64_t target, 
     *n_test = off_te[users];
     return CU2B_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// DSGD partitioning (host side; no reference counterpart -- cu2rec is single GPU)
+// ------------------------------------------------------------------------------------------
+namespace {
+// Longest-processing-time assignment of weighted elements to `world` bins; ties broken by index
+// so the result is deterministic. bin_of[e] = bin, and elements keep ascending original order
+// inside a bin.
+void lpt_assign(const std::vector<int64_t> &weight, int world, std::vector<int> *bin_of) {
+    const int n = (int)weight.size();
+    std::vector<int> order(n);
+    for (int i = 0; i < n; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return weight[a] > weight[b]; });
+    std::vector<int64_t> load(world, 0);
+    std::vector<int> count(world, 0);
+    bin_of->assign(n, 0);
+    for (int e : order) {
+        int best = 0;
+        for (int b = 1; b < world; ++b)
+            if (load[b] < load[best] || (load[b] == load[best] && count[b] < count[best])) best = b;
+        (*bin_of)[e] = best;
+        load[best] += weight[e];
+        count[best]++;
+    }
+}
+}  // namespace
+
+extern "C" cu2b_status cu2b_dsgd_partition(const cu2b_rating *train, int64_t n, int rows, int cols, int world,
+                                           int *user_block, int *user_local, int *users_per_block,
+                                           int *item_new, int *item_block_ptr, int64_t *block_nnz) {
+    if ((!train && n > 0) || rows < 0 || cols < 0 || world < 1 || !user_block || !user_local || !users_per_block ||
+        !item_new || !item_block_ptr)
+        return cu2b_fail(CU2B_ERR_INVALID, "cu2b_dsgd_partition: bad argument");
+    std::vector<int64_t> udeg(rows, 0), ideg(cols, 0);
+    for (int64_t t = 0; t < n; ++t) {
+        if (train[t].user < 0 || train[t].user >= rows || train[t].item < 0 || train[t].item >= cols)
+            return cu2b_fail(CU2B_ERR_INVALID, "cu2b_dsgd_partition: rating %ld out of range", (long)t);
+        udeg[train[t].user]++;
+        ideg[train[t].item]++;
+    }
+    std::vector<int> ub, ibk;
+    lpt_assign(udeg, world, &ub);
+    lpt_assign(ideg, world, &ibk);
+    std::vector<int> ucount(world, 0), icount(world, 0);
+    for (int u = 0; u < rows; ++u) {
+        user_block[u] = ub[u];
+        user_local[u] = ucount[ub[u]]++;
+    }
+    for (int g = 0; g < world; ++g) users_per_block[g] = ucount[g];
+    for (int i = 0; i < cols; ++i) icount[ibk[i]]++;
+    item_block_ptr[0] = 0;
+    for (int g = 0; g < world; ++g) item_block_ptr[g + 1] = item_block_ptr[g] + icount[g];
+    std::vector<int> cursor(item_block_ptr, item_block_ptr + world);
+    for (int i = 0; i < cols; ++i) item_new[i] = cursor[ibk[i]]++;
+    if (block_nnz) {
+        for (int b = 0; b < world * world; ++b) block_nnz[b] = 0;
+        for (int64_t t = 0; t < n; ++t) block_nnz[(size_t)ub[train[t].user] * world + ibk[train[t].item]]++;
+    }
+    return CU2B_OK;
+}
+
+// Ratings of one rank: users of block `rank` with local ids, items renumbered, original
+// per-user order preserved (so the per-user sampler draws the same rating as on one GPU).
+extern "C" cu2b_status cu2b_dsgd_extract_strip(const cu2b_rating *ratings, int64_t n, const int *user_block,
+                                               const int *user_local, const int *item_new, int rank,
+                                               cu2b_rating *out, int64_t *n_out) {
+    if ((!ratings && n > 0) || !user_block || !user_local || !item_new || !n_out)
+        return cu2b_fail(CU2B_ERR_INVALID, "cu2b_dsgd_extract_strip: bad argument");
+    int64_t w = 0;
+    // input is grouped by ascending user and local ids ascend with the original ids inside a
+    // block, so a single filtered pass keeps the strip grouped by ascending local user
+    for (int64_t t = 0; t < n; ++t) {
+        const int u = ratings[t].user;
+        if (user_block[u] != rank) continue;
+        if (out) {
+            out[w].user = user_local[u];
+            out[w].item = item_new[ratings[t].item];
+            out[w].rating = ratings[t].rating;
+        }
+        ++w;
+    }
+    *n_out = w;
+    return CU2B_OK;
+}

@@ -138,7 +138,7 @@ struct DevState {
     float validation_rmse;  // training.cu:102 (starts at FLT_MAX)
     int n_log;
     int log_cap;
-    int pad;
+    int error;              // set by a device-side wait that timed out (never hang the GPU)
     double sums[4];         // last evaluated {train sse, train sae, test sse, test sae}
 };
 

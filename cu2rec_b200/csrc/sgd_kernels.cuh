@@ -32,6 +32,10 @@ struct SgdParams {
     int *gate;
     int seg0;                   // absolute index of segment 0 of this launch
     int serial;                 // 1 => a single group processes the stream strictly in order
+    // DSGD: the stream range {first rating, count} is only known on the device (bucket sizes of
+    // a sampled round). When set, sv.base / seg_len / chunk counts are derived from it in-kernel.
+    const int *dyn_range;
+    int *error_flag;            // DevState::error
 };
 
 #define PHILOX_TAG 0x53474431u
@@ -58,7 +62,7 @@ __global__ void __launch_bounds__(256)
 sample_per_user_kernel(const int *__restrict__ indptr, const cu2b_rating *__restrict__ coo,
                        const int *__restrict__ active_users, int n_active, uint32_t seed,
                        int iter0, long long n_draws, cu2b_rating *__restrict__ out,
-                       long long seg_pitch) {
+                       long long seg_pitch, const int *__restrict__ user_ids) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; i < n_draws; i += stride) {
@@ -66,7 +70,9 @@ sample_per_user_kernel(const int *__restrict__ indptr, const cu2b_rating *__rest
         const int a = (int)(i - (long long)t * n_active);
         const int u = __ldg(&active_users[a]);
         const int lo = __ldg(&indptr[u]), hi = __ldg(&indptr[u + 1]);
-        const uint32_t r = philox4x32_10_x((uint32_t)u, (uint32_t)(iter0 + t), 0u, PHILOX_TAG, seed, PHILOX_KEY1);
+        // the counter is keyed by the ORIGINAL user id (DSGD strips renumber users locally)
+        const uint32_t uid = user_ids ? (uint32_t)__ldg(&user_ids[u]) : (uint32_t)u;
+        const uint32_t r = philox4x32_10_x(uid, (uint32_t)(iter0 + t), 0u, PHILOX_TAG, seed, PHILOX_KEY1);
         const int j = lo + (int)__umulhi(r, (uint32_t)(hi - lo));
         cu2b_rating v;
         v.user = u;
@@ -186,8 +192,16 @@ __device__ __forceinline__ void sgd_update_slots(const SgdParams &p, const cu2b_
 
 template <int L, int V, int UNR, int WMODE, int OCC = 1>
 __global__ void __launch_bounds__(kThreads, OCC)
-mf_sgd_hogwild(const SgdParams p) {
+mf_sgd_hogwild(const SgdParams p_in) {
     __shared__ StreamSmem sm;
+    SgdParams p = p_in;
+    if (p.dyn_range) {
+        const int first = __ldg(p.dyn_range), cnt = __ldg(p.dyn_range + 1);
+        p.sv.base += first;
+        p.sv.seg_len = cnt;
+        p.sv.chunks_per_seg = (cnt + p.sv.chunk - 1) / p.sv.chunk;
+        p.sv.num_chunks = p.sv.chunks_per_seg;
+    }
     pipe_init(sm);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == kConsumerWarps) {  // producer warp
@@ -201,7 +215,14 @@ mf_sgd_hogwild(const SgdParams p) {
                 [&](long long seg, int j, int) {
                     if (p.gate) {
                         const int want = p.seg0 + (int)seg;
-                        while (ld_acquire_gpu(p.gate + j) < want) __nanosleep(32);
+                        const long long t0 = clock64();
+                        while (ld_acquire_gpu(p.gate + j) < want) {
+                            __nanosleep(32);
+                            if (clock64() - t0 > (8LL << 30)) {  // ~4 s: report, never hang
+                                if (p.error_flag) atomicExch(p.error_flag, 2);
+                                break;
+                            }
+                        }
                     }
                 });
         }

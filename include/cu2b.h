@@ -223,6 +223,51 @@ cu2b_status cu2b_session_get_config(cu2b_session *s, cu2b_config *out);
 cu2b_status cu2b_session_stats(cu2b_session *s, cu2b_stats *out, int reset);
 void cu2b_session_destroy(cu2b_session *s);
 
+/* ------------------------------------------------------------------------------------
+ * Multi-GPU: DSGD 2-D stratification on one NVLink/NVSwitch box (no reference counterpart;
+ * cu2rec is single GPU). Users and items are cut into `world` blocks; rank g owns P / user_bias
+ * of user block g and that block's ratings; sub-epoch s of a round runs rating block
+ * (g, (g+s) mod world) on rank g; item blocks (Q rows + item_bias) rotate g -> g-1 through peer
+ * memory (P2P stores over NVLink + a release flag), never through the host.
+ * ---------------------------------------------------------------------------------- */
+/* Host only. LPT-balanced block assignment by rating count. user_block[u] / user_local[u]: block
+ * and index inside the block of original user u; item_new[i]: renumbered item id such that item
+ * block b is the contiguous range [item_block_ptr[b], item_block_ptr[b+1]). block_nnz (optional)
+ * receives the world x world rating counts. */
+cu2b_status cu2b_dsgd_partition(const cu2b_rating *train, int64_t n, int rows, int cols, int world,
+                                int *user_block, int *user_local, int *users_per_block,
+                                int *item_new, int *item_block_ptr, int64_t *block_nnz);
+/* Host only. The ratings of one rank (local user ids, renumbered items, original order kept).
+ * out == NULL only counts. */
+cu2b_status cu2b_dsgd_extract_strip(const cu2b_rating *ratings, int64_t n, const int *user_block,
+                                    const int *user_local, const int *item_new, int rank,
+                                    cu2b_rating *out, int64_t *n_out);
+
+#define CU2B_DSGD_HANDLE_BYTES 512
+typedef struct cu2b_dsgd cu2b_dsgd;
+/* One context per rank (one process per GPU, or several contexts in one process). The strips use
+ * local user ids and renumbered item ids; Q / item_bias are full size in the renumbered order;
+ * user_ids[rows] are the ORIGINAL user ids of the strip's users (they key the per-user sampler so
+ * that every rank draws exactly what a single GPU would draw). handle_out receives an opaque
+ * blob (CU2B_DSGD_HANDLE_BYTES) to be exchanged between ranks by any host transport. */
+cu2b_status cu2b_dsgd_create(cu2b_dsgd **out, int device, int rank, int world,
+                             const cu2b_csr *train_strip, const cu2b_csr *test_strip,
+                             const cu2b_config *cfg, const float *P_strip, const float *Q,
+                             const float *user_bias_strip, const float *item_bias, float global_bias,
+                             const int *user_ids, const int *item_block_ptr, int64_t n_train_global,
+                             int64_t n_test_global, int64_t n_active_global, void *handle_out);
+/* handles: world blobs in rank order (own blob included). Maps the peers' buffers (CUDA IPC
+ * across processes, direct peer access inside one process). */
+cu2b_status cu2b_dsgd_connect(cu2b_dsgd *d, const void *handles);
+/* Collective: every rank calls it with the same n_iterations. Blocks until this rank is done. */
+cu2b_status cu2b_dsgd_run(cu2b_dsgd *d, int n_iterations);
+/* The rank-local session (log / stats / download of the strip / config); owned by the context. */
+cu2b_session *cu2b_dsgd_session(cu2b_dsgd *d);
+/* This rank's latest local loss sums {train sse, train sae, test sse, test sae} (for
+ * cross-checking the peer-memory combine against an NCCL / gloo all-reduce). */
+cu2b_status cu2b_dsgd_local_sums(cu2b_dsgd *d, double out[4]);
+void cu2b_dsgd_destroy(cu2b_dsgd *d);
+
 /* Device introspection used by bench / CLI ("Free memory: %ld", mf.cu:35-37). */
 cu2b_status cu2b_device_info(int device, char *name, int name_cap, int *sm_count,
                              int *cc_major, int *cc_minor, int64_t *free_bytes,

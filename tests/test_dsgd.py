@@ -1,0 +1,177 @@
+"""Multi-GPU DSGD path. CPU: partitioning / strip extraction and the N>1 host plumbing over a
+world_size-2 gloo group. GPU: several logical ranks on ONE device (one context + one host thread
+per rank, peer pointers inside the process) against the single-GPU session and the oracle."""
+import os
+import subprocess
+import sys
+import threading
+
+import numpy as np
+import pytest
+
+import cu2rec_b200 as cu
+import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _problem(U=1200, I=300, n=40000, seed=21):
+    tr, te = cu.synth_ratings(U, I, n, rank=4, noise=0.3, integer_ratings=True, seed=seed)
+    return tr, te, U, I
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_partition_and_strips_cover_the_problem_exactly(world):
+    tr, te, U, I = _problem()
+    part = cu.dsgd_partition(tr, U, I, world)
+    assert part.users_per_block.sum() == U and part.item_block_ptr[-1] == I
+    assert sorted(part.item_new.tolist()) == list(range(I))
+    # balanced by rating count (LPT): every block row / column within 2 % of the mean
+    assert part.block_nnz.sum() == len(tr)
+    for marg in (part.block_nnz.sum(0), part.block_nnz.sum(1)):
+        assert marg.max() <= 1.02 * marg.mean() + 1
+    got_train = []
+    for r in range(world):
+        strip = cu.dsgd_extract_strip(tr, part, r)
+        assert np.all(np.diff(strip["user"]) >= 0) and strip["user"].max() < part.users_per_block[r]
+        users = np.flatnonzero(part.user_block == r)
+        inv = np.empty(I, np.int64)
+        inv[part.item_new] = np.arange(I)
+        back = np.zeros(len(strip), dtype=cu.RATING_DTYPE)
+        back["user"], back["item"], back["rating"] = users[strip["user"]], inv[strip["item"]], strip["rating"]
+        got_train.append(back)
+        # per-user order is preserved (the sampler relies on it)
+        u0 = users[0]
+        assert np.array_equal(back[back["user"] == u0], tr[tr["user"] == u0])
+        # item blocks are contiguous ranges in the renumbered space
+        blk = np.searchsorted(part.item_block_ptr, strip["item"], side="right") - 1
+        assert np.array_equal(np.bincount(blk, minlength=world), part.block_nnz[r])
+    allr = np.sort(np.concatenate(got_train), order=["user", "item"])
+    assert np.array_equal(allr, np.sort(tr, order=["user", "item"]))
+
+
+_GLOO_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import numpy as np, torch, torch.distributed as dist
+import cu2rec_b200 as cu, oracle as O
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank, world = dist.get_rank(), dist.get_world_size()
+tr, te = cu.synth_ratings(600, 200, 15000, rank=4, noise=0.3, seed=5)
+U, I, k = 600, 200, 8
+part = cu.dsgd_partition(tr, U, I, world)          # every rank computes the same partition
+chk = torch.tensor([int(part.item_new.astype(np.int64).sum() * 7 + part.user_block.astype(np.int64).dot(np.arange(U)))])
+both = [torch.zeros_like(chk) for _ in range(world)]
+dist.all_gather(both, chk)
+assert both[0].item() == both[1].item(), "partition differs between ranks"
+init = lambda n: cu.initialize_normal_array(n, k)
+P, Q, ub, ib = init(U * k), init(I * k), init(U), init(I)
+inp = cu.dsgd_rank_inputs(tr, te, U, I, part, rank, P, Q, ub, ib)
+mu = np.float32(tr["rating"].astype(np.float64).mean())
+# rank-local loss sums on the strip (CPU oracle) + all-reduce == loss of the whole problem
+_, _, sse, sae = O.loss(inp.train.indptr, inp.train.indices, inp.train.data, inp.P, inp.Q, inp.user_bias, inp.item_bias, mu, k)
+t = torch.tensor([sse, sae, float(inp.train.nonzeros)], dtype=torch.float64)
+dist.all_reduce(t)
+full = cu.createSparseMatrix(tr, U, I)
+_, _, gsse, gsae = O.loss(full.indptr, full.indices, full.data, P, Q, ub, ib, mu, k)
+assert abs(t[0].item() - gsse) / gsse < 1e-12 and abs(t[1].item() - gsae) / gsae < 1e-12 and int(t[2].item()) == len(tr)
+# the handle exchange used by bench.py: fixed-size blobs all-gathered in rank order
+blob = bytes([rank + 1]) * cu._lib.DSGD_HANDLE_BYTES
+g = [torch.zeros(cu._lib.DSGD_HANDLE_BYTES, dtype=torch.uint8) for _ in range(world)]
+dist.all_gather(g, torch.frombuffer(bytearray(blob), dtype=torch.uint8))
+assert [bytes(x.numpy().tobytes())[0] for x in g] == [1, 2]
+# the per-user sampler is keyed by ORIGINAL user ids: the union of both ranks' draws is the single-GPU draw
+s_local = O.sample_per_user(inp.train.indptr, inp.train.indices, inp.train.data, 42, 0, 1)
+print("OK", rank, len(s_local))
+dist.destroy_process_group()
+'''
+
+
+def test_world2_gloo_host_logic(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300) for p in procs]
+    for p, (o, e) in zip(procs, outs):
+        assert p.returncode == 0 and "OK" in o, e[-2000:]
+
+
+def _run_logical_ranks(world, tr, te, U, I, k, iters, ce, device=0):
+    part = cu.dsgd_partition(tr, U, I, world)
+    init = lambda n: cu.initialize_normal_array(n, k)
+    P, Q, ub, ib = init(U * k), init(I * k), init(U), init(I)
+    mu = np.float32(tr["rating"].astype(np.float64).mean())
+    ranks = []
+    for r in range(world):
+        inp = cu.dsgd_rank_inputs(tr, te, U, I, part, r, P, Q, ub, ib)
+        cfg = cu.Config(total_iterations=iters, n_factors=k, check_error=ce)
+        ranks.append(cu.Dsgd(r, world, inp, part, cfg, mu, device=device))
+    handles = [d.handle for d in ranks]
+    for d in ranks:
+        d.connect(handles)
+    errs = []
+
+    def work(d):
+        try:
+            d.run(iters)
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(d,)) for d in ranks]
+    [t.start() for t in th]
+    [t.join(timeout=240) for t in th]
+    assert not errs, errs
+    assert not any(t.is_alive() for t in th), "DSGD ranks did not finish"
+    return part, ranks, (P, Q, ub, ib, mu)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_dsgd_logical_ranks_match_single_gpu_training(world):
+    tr, te, U, I = _problem(U=3000, I=400, n=120000)
+    k, iters, ce = 16, 120, 40
+    part, ranks, (P, Q, ub, ib, mu) = _run_logical_ranks(world, tr, te, U, I, k, iters, ce)
+    logs = [d.log() for d in ranks]
+    for lg in logs[1:]:
+        assert lg == logs[0]  # every rank combines the partial sums in rank order: identical bits
+    assert [r["iteration"] for r in logs[0]] == [1, 40, 80, 120]
+    assert sum(d.stats()["updates"] for d in ranks) == iters * U
+    # single-GPU session on the same problem / init / sampler stream
+    mtr, mte = cu.createSparseMatrix(tr, U, I), cu.createSparseMatrix(te, U, I)
+    cfg = cu.Config(total_iterations=iters, n_factors=k, check_error=ce)
+    with cu.Session(mtr, mte, cfg, P, Q, ub, ib, mu) as s:
+        s.run(iters)
+        ref = s.log()
+    for a, b in zip(logs[0], ref):
+        for key in ("train_rmse", "test_rmse"):
+            assert abs(a[key] - b[key]) / b[key] < 0.01, (key, a, b)
+    assert abs(logs[0][-1]["test_rmse"] - ref[-1]["test_rmse"]) / ref[-1]["test_rmse"] < 0.005
+    # the model gathered from the ranks reproduces the logged loss (oracle, whole problem)
+    Pg, ubg = np.empty((U, k), np.float32), np.empty(U, np.float32)
+    inv = np.empty(I, np.int64)
+    inv[part.item_new] = np.arange(I)
+    Qg = ibg = None
+    for r, d in enumerate(ranks):
+        Ps, Qn, ubs, ibn = d.download()
+        users = np.flatnonzero(part.user_block == r)
+        Pg[users], ubg[users] = Ps, ubs
+        if r == 0:
+            Qg, ibg = Qn[part.item_new], ibn[part.item_new]  # back to original item order
+    _, rmse, _, _ = O.loss(mte.indptr, mte.indices, mte.data, Pg, Qg, ubg, ibg, mu, k)
+    assert abs(rmse - logs[0][-1]["test_rmse"]) / rmse < 1e-4
+    for d in ranks:
+        d.close()
+
+
+@pytest.mark.gpu
+def test_dsgd_local_sums_add_up_to_the_logged_loss():
+    tr, te, U, I = _problem(U=1000, I=200, n=30000)
+    part, ranks, (_, _, _, _, mu) = _run_logical_ranks(2, tr, te, U, I, 8, 20, 20)
+    sums = np.array([d.local_sums() for d in ranks]).sum(0)  # what an NCCL / gloo all-reduce would produce
+    last = ranks[0].log()[-1]
+    assert abs(np.sqrt(sums[0] / len(tr)) - last["train_rmse"]) < 1e-6
+    assert abs(sums[3] / len(te) - last["test_mae"]) < 1e-6
+    for d in ranks:
+        d.close()
