@@ -406,7 +406,7 @@ def dsgd_rank_inputs(train, test, rows, cols, part, rank, P, Q, user_bias, item_
     n_local = len(users)
     inv = np.empty(cols, np.int64)
     inv[part.item_new] = np.arange(cols)
-    n_active = int(len(np.unique(np.ascontiguousarray(train)["user"])))
+    n_active = int(np.count_nonzero(np.bincount(np.ascontiguousarray(train)["user"], minlength=rows)))
     return DsgdRankInputs(createSparseMatrix(tr, n_local, cols), createSparseMatrix(te, n_local, cols),
                           _f32(P).reshape(rows, k)[users].copy(), _f32(Q).reshape(cols, k)[inv].copy(),
                           _f32(user_bias)[users].copy(), _f32(item_bias)[inv].copy(), users,

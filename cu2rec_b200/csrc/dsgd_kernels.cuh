@@ -1,4 +1,4 @@
-// Device side of the multi-GPU DSGD path: bucketing of a sampled round by item block, the
+// Device side of the multi-GPU DSGD path: per-user runs of a sampled round grouped by item block, the
 // peer-memory hand-off of an item block (Q rows + item_bias) to the next rank, and the
 // all-rank combine of the loss partial sums. All inter-rank traffic is P2P stores into the
 // peer's HBM over NVLink followed by a system-scope release flag; receivers poll their own
@@ -42,75 +42,179 @@ __device__ __forceinline__ int item_block_of(int item, const int *sh_ptr, int wo
     return b;
 }
 
-// Pass 1: how many draws of this round fall into each item block.
-__global__ void __launch_bounds__(256)
-dsgd_bucket_count_kernel(const cu2b_rating *__restrict__ stream, long long n_draws, int seg_len,
-                         long long seg_pitch, const int *__restrict__ item_block_ptr, int world,
-                         int *counts) {
-    __shared__ int sh_ptr[kMaxWorld + 1];
-    __shared__ int sh_cnt[kMaxWorld];
-    if (threadIdx.x <= world) sh_ptr[threadIdx.x] = item_block_ptr[threadIdx.x];
-    if (threadIdx.x < world) sh_cnt[threadIdx.x] = 0;
-    __syncthreads();
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_draws;
-         i += (long long)gridDim.x * blockDim.x) {
-        const long long seg = i / seg_len;
-        const int item = __ldg(&stream[seg * seg_pitch + (i - seg * seg_len)].item);
-        atomicAdd(&sh_cnt[item_block_of(item, sh_ptr, world)], 1);
-    }
-    __syncthreads();
-    if (threadIdx.x < world && sh_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], sh_cnt[threadIdx.x]);
-}
+// A sampled draw inside a user's run: the user is implied by the row.
+struct __align__(8) DsgdDraw {
+    int item;
+    float rating;
+};
 
-// Bucket b occupies [ranges[2b], ranges[2b] + ranges[2b+1]) of the bucket buffer; starts are
-// multiples of 4 ratings (TMA alignment). Also resets the scatter cursors and the counts.
-__global__ void dsgd_bucket_scan_kernel(int *counts, int world, int *ranges, int *cursor) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        int off = 0;
-        for (int b = 0; b < world; ++b) {
-            ranges[2 * b] = off;
-            ranges[2 * b + 1] = counts[b];
-            cursor[b] = off;
-            off += (counts[b] + 3) & ~3;
-            counts[b] = 0;
-        }
-    }
-}
-
-// Pass 2: tile-wise scatter; a CTA reserves one contiguous range per bucket for its tile.
-constexpr int kScatterTile = 2048;
+// Sampler of one DSGD round (nb reference iterations): one WARP per active user draws that
+// user's nb ratings (same Philox stream as the single-GPU sampler, keyed by the original user
+// id) and writes them to the user's row of `draws` grouped by item block, iteration order kept
+// inside a block (ballot ranking => deterministic). row_off[a*(world+1)+b] = start of block b
+// inside row a. In sub-epoch b the update kernel walks exactly run [row_off[b], row_off[b+1]).
 __global__ void __launch_bounds__(256)
-dsgd_bucket_scatter_kernel(const cu2b_rating *__restrict__ stream, long long n_draws, int seg_len,
-                           long long seg_pitch, const int *__restrict__ item_block_ptr, int world,
-                           int *cursor, cu2b_rating *__restrict__ out) {
+dsgd_sample_runs_kernel(const int *__restrict__ indptr, const cu2b_rating *__restrict__ coo,
+                        const int *__restrict__ active_users, const int *__restrict__ user_ids,
+                        int n_active, uint32_t seed, int iter0, int nb, int pitch,
+                        const int *__restrict__ item_block_ptr, int world, DsgdDraw *__restrict__ draws,
+                        int *__restrict__ row_off) {
     __shared__ int sh_ptr[kMaxWorld + 1];
-    __shared__ int sh_cnt[kMaxWorld];
-    __shared__ int sh_base[kMaxWorld];
     if (threadIdx.x <= world) sh_ptr[threadIdx.x] = item_block_ptr[threadIdx.x];
-    constexpr int PER = kScatterTile / 256;
-    for (long long tile = blockIdx.x; tile * kScatterTile < n_draws; tile += gridDim.x) {
-        if (threadIdx.x < world) sh_cnt[threadIdx.x] = 0;
-        __syncthreads();
-        cu2b_rating r[PER];
-        int bk[PER], loc[PER];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; a < n_active; a += warps) {
+        const int u = __ldg(&active_users[a]);
+        const uint32_t uid = user_ids ? (uint32_t)__ldg(&user_ids[u]) : (uint32_t)u;
+        const int lo = __ldg(&indptr[u]), n = __ldg(&indptr[u + 1]) - lo;
+        // pass 1: block histogram of the nb draws
+        int cnt[kMaxWorld];
 #pragma unroll
-        for (int e = 0; e < PER; ++e) {
-            const long long i = tile * kScatterTile + e * 256 + threadIdx.x;
-            bk[e] = -1;
-            if (i < n_draws) {
-                const long long seg = i / seg_len;
-                r[e] = stream[seg * seg_pitch + (i - seg * seg_len)];
-                bk[e] = item_block_of(r[e].item, sh_ptr, world);
-                loc[e] = atomicAdd(&sh_cnt[bk[e]], 1);
+        for (int b = 0; b < kMaxWorld; ++b) cnt[b] = 0;
+        for (int t = lane; t < nb; t += 32) {
+            const uint32_t r = philox4x32_10_x(uid, (uint32_t)(iter0 + t), 0u, PHILOX_TAG, seed, PHILOX_KEY1);
+            const int j = lo + (int)__umulhi(r, (uint32_t)n);
+            const int blk = item_block_of(__ldg(&coo[j].item), sh_ptr, world);
+#pragma unroll
+            for (int b = 0; b < kMaxWorld; ++b) cnt[b] += (blk == b);
+        }
+        int off[kMaxWorld + 1];
+        off[0] = 0;
+#pragma unroll
+        for (int b = 0; b < kMaxWorld; ++b) {
+            int c = cnt[b];
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            off[b + 1] = off[b] + c;
+        }
+        if (lane <= world) {
+            int v = 0;
+#pragma unroll
+            for (int b = 0; b <= kMaxWorld; ++b) v = (lane == b) ? off[b] : v;
+            row_off[(size_t)a * (world + 1) + lane] = v;
+        }
+        // pass 2: place the draws, stable inside a block
+        DsgdDraw *row = draws + (size_t)a * pitch;
+        for (int t0 = 0; t0 < nb; t0 += 32) {
+            const int t = t0 + lane;
+            int blk = -1;
+            DsgdDraw d;
+            d.item = 0; d.rating = 0.f;
+            if (t < nb) {
+                const uint32_t r = philox4x32_10_x(uid, (uint32_t)(iter0 + t), 0u, PHILOX_TAG, seed, PHILOX_KEY1);
+                const int j = lo + (int)__umulhi(r, (uint32_t)n);
+                d.item = __ldg(&coo[j].item);
+                d.rating = __ldg(&coo[j].rating);
+                blk = item_block_of(d.item, sh_ptr, world);
+            }
+#pragma unroll
+            for (int b = 0; b < kMaxWorld; ++b) {
+                if (b < world) {
+                    const unsigned m = __ballot_sync(0xffffffffu, blk == b);
+                    if (blk == b) row[off[b] + __popc(m & ((1u << lane) - 1u))] = d;
+                    off[b] += __popc(m);
+                }
             }
         }
-        __syncthreads();
-        if (threadIdx.x < world) sh_base[threadIdx.x] = sh_cnt[threadIdx.x] ? atomicAdd(&cursor[threadIdx.x], sh_cnt[threadIdx.x]) : 0;
-        __syncthreads();
+    }
+}
+
+// Update kernel of one DSGD sub-epoch: a lane group owns one USER, keeps that user's P row and
+// bias in registers, applies the user's run of draws for the resident item block strictly in
+// order (exact sequential semantics on the user side, P traffic once per run instead of once per
+// update), and adds the item-side steps with 128-bit L2 atomics (other users update the same
+// item rows concurrently). Same arithmetic as sgd_update_slots.
+struct UserRunParams {
+    const DsgdDraw *draws;
+    const int *row_off;   // [n_active][world + 1]
+    const int *active_users;
+    int n_active, pitch, world, block;
+    float *P, *Q, *user_bias, *item_bias;
+    int kp;
+    float mu;
+    const float *lr;
+    float P_reg, Q_reg, ub_reg, ib_reg;
+    int is_train;
+};
+
+template <int L, int V>
+__global__ void __launch_bounds__(256)
+mf_sgd_user_runs(const UserRunParams p) {
+    constexpr int G = 32 / L;
+    const int lane = threadIdx.x & 31, g = lane / L, l = lane % L;
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_groups = ((gridDim.x * blockDim.x) >> 5) * G;
+    const int vecs = p.kp >> 2;
+    const float lr = __ldg(p.lr);
+    float4 *const Pv = reinterpret_cast<float4 *>(p.P);
+    float4 *const Qv = reinterpret_cast<float4 *>(p.Q);
+    for (int a0 = warp_global * G; a0 < p.n_active; a0 += n_groups) {
+        const int a = a0 + g;
+        int j = 0, end = 0, u = 0;
+        if (a < p.n_active) {
+            j = __ldg(p.row_off + (size_t)a * (p.world + 1) + p.block);
+            end = __ldg(p.row_off + (size_t)a * (p.world + 1) + p.block + 1);
+            u = __ldg(p.active_users + a);
+        }
+        if (!__any_sync(0xffffffffu, j < end)) continue;
+        const bool mine = j < end;
+        float4 pv[V];
+        const size_t po = (size_t)u * vecs + l;
 #pragma unroll
-        for (int e = 0; e < PER; ++e)
-            if (bk[e] >= 0) out[sh_base[bk[e]] + loc[e]] = r[e];
-        __syncthreads();
+        for (int v = 0; v < V; ++v)
+            pv[v] = (mine && v * L + l < vecs) ? __ldcg(Pv + po + v * L) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float ub = mine ? __ldcg(p.user_bias + u) : 0.f;
+        const DsgdDraw *row = p.draws + (size_t)a * p.pitch;
+        while (__any_sync(0xffffffffu, j < end)) {
+            const bool ok = j < end;
+            DsgdDraw d;
+            d.item = 0; d.rating = 0.f;
+            if (ok) d = row[j];
+            const size_t qo = (size_t)d.item * vecs + l;
+            float4 qv[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+                qv[v] = (ok && v * L + l < vecs) ? __ldcg(Qv + qo + v * L) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float ib = ok ? __ldcg(p.item_bias + d.item) : 0.f;
+            float acc = 0.f;
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                acc = __fmaf_rn(pv[v].x, qv[v].x, acc);
+                acc = __fmaf_rn(pv[v].y, qv[v].y, acc);
+                acc = __fmaf_rn(pv[v].z, qv[v].z, acc);
+                acc = __fmaf_rn(pv[v].w, qv[v].w, acc);
+            }
+            const float dot = group_sum<L>(acc);
+            const float pred = __fadd_rn(__fadd_rn(__fadd_rn(p.mu, ub), ib), dot);
+            const float err = __fsub_rn(d.rating, pred);
+            if (ok) {
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    const float4 x = pv[v], y = qv[v];
+                    float4 nq;
+                    nq.x = __fmul_rn(lr, __fsub_rn(__fmul_rn(err, x.x), __fmul_rn(p.Q_reg, y.x)));
+                    nq.y = __fmul_rn(lr, __fsub_rn(__fmul_rn(err, x.y), __fmul_rn(p.Q_reg, y.y)));
+                    nq.z = __fmul_rn(lr, __fsub_rn(__fmul_rn(err, x.z), __fmul_rn(p.Q_reg, y.z)));
+                    nq.w = __fmul_rn(lr, __fsub_rn(__fmul_rn(err, x.w), __fmul_rn(p.Q_reg, y.w)));
+                    pv[v].x = __fadd_rn(x.x, __fmul_rn(lr, __fsub_rn(__fmul_rn(err, y.x), __fmul_rn(p.P_reg, x.x))));
+                    pv[v].y = __fadd_rn(x.y, __fmul_rn(lr, __fsub_rn(__fmul_rn(err, y.y), __fmul_rn(p.P_reg, x.y))));
+                    pv[v].z = __fadd_rn(x.z, __fmul_rn(lr, __fsub_rn(__fmul_rn(err, y.z), __fmul_rn(p.P_reg, x.z))));
+                    pv[v].w = __fadd_rn(x.w, __fmul_rn(lr, __fsub_rn(__fmul_rn(err, y.w), __fmul_rn(p.P_reg, x.w))));
+                    if (p.is_train && v * L + l < vecs) red_add_v4(Qv + qo + v * L, nq);
+                }
+                if (p.is_train && l == 0)
+                    red_add_f32(p.item_bias + d.item, __fmul_rn(lr, __fsub_rn(err, __fmul_rn(p.ib_reg, ib))));
+                ub = __fadd_rn(ub, __fmul_rn(lr, __fsub_rn(err, __fmul_rn(p.ub_reg, ub))));
+            }
+            ++j;
+        }
+        if (mine) {
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+                if (v * L + l < vecs) __stcg(Pv + po + v * L, pv[v]);
+            if (l == 0) __stcg(p.user_bias + u, ub);
+        }
     }
 }
 

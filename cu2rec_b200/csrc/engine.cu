@@ -187,6 +187,7 @@ cu2b_status download_dense(cudaStream_t st, float *dst, const float *src, int ro
 typedef void (*SgdKernel)(const SgdParams);
 typedef void (*LossKernel)(const LossParams);
 typedef void (*BlockedKernel)(const BlockedParams);
+typedef void (*UserRunKernel)(const UserRunParams);
 
 cu2b_status layout_for(int kp, int *L, int *V) {
     const int vecs = kp / 4;
@@ -260,6 +261,23 @@ BlockedKernel pick_blocked(int L, int V) {
                 case 2: return mf_sgd_blocked_round<32, 2>;
                 case 3: return mf_sgd_blocked_round<32, 3>;
                 default: return mf_sgd_blocked_round<32, 4>;
+            }
+    }
+}
+
+UserRunKernel pick_user_runs(int L, int V) {
+    switch (L) {
+        case 1: return mf_sgd_user_runs<1, 1>;
+        case 2: return mf_sgd_user_runs<2, 1>;
+        case 4: return mf_sgd_user_runs<4, 1>;
+        case 8: return mf_sgd_user_runs<8, 1>;
+        case 16: return mf_sgd_user_runs<16, 1>;
+        default:
+            switch (V) {
+                case 1: return mf_sgd_user_runs<32, 1>;
+                case 2: return mf_sgd_user_runs<32, 2>;
+                case 3: return mf_sgd_user_runs<32, 3>;
+                default: return mf_sgd_user_runs<32, 4>;
             }
     }
 }
@@ -555,10 +573,10 @@ cu2b_status enqueue_sgd_iterations(cu2b_session *s, int iter_abs, int n_seg) {
 
 }  // namespace
 
-extern "C" cu2b_status cu2b_session_create(cu2b_session **out, int device, const cu2b_csr *train,
-                                           const cu2b_csr *test, const cu2b_config *cfg,
-                                           const float *P, const float *Q, const float *user_bias,
-                                           const float *item_bias, float global_bias) {
+static cu2b_status session_create_impl(cu2b_session **out, int device, const cu2b_csr *train,
+                                       const cu2b_csr *test, const cu2b_config *cfg, const float *P,
+                                       const float *Q, const float *user_bias, const float *item_bias,
+                                       float global_bias, bool alloc_stream) {
     if (!out || !cfg || !P || !Q || !user_bias || !item_bias)
         return cu2b_fail(CU2B_ERR_INVALID, "cu2b_session_create: null argument");
     *out = nullptr;
@@ -631,9 +649,11 @@ extern "C" cu2b_status cu2b_session_create(cu2b_session **out, int device, const
     s->chunks_per_seg = std::max(1, (s->n_active + s->chunk - 1) / s->chunk);
     const long long cap_ratings = 48LL << 20;  // <= 576 MB of triplets per batch
     s->max_batch_segs = (int)std::max<long long>(1, std::min<long long>(cap_ratings / std::max<long long>(1, s->seg_pitch), 4096));
-    CU2B_TRY(s->pool.alloc(&s->stream_buf, (size_t)s->max_batch_segs * s->seg_pitch + kChunkMax + 4));
-    CU2B_TRY(s->pool.alloc(&s->gate, (size_t)s->chunks_per_seg));
-    CUDA_TRY(cudaMemsetAsync(s->gate, 0, (size_t)s->chunks_per_seg * sizeof(int), s->stream));
+    if (alloc_stream) {
+        CU2B_TRY(s->pool.alloc(&s->stream_buf, (size_t)s->max_batch_segs * s->seg_pitch + kChunkMax + 4));
+        CU2B_TRY(s->pool.alloc(&s->gate, (size_t)s->chunks_per_seg));
+        CUDA_TRY(cudaMemsetAsync(s->gate, 0, (size_t)s->chunks_per_seg * sizeof(int), s->stream));
+    }
     s->counter_slots = 256;
     CU2B_TRY(s->pool.alloc(&s->counters, (size_t)s->counter_slots));
 
@@ -675,8 +695,17 @@ extern "C" cu2b_status cu2b_session_create(cu2b_session **out, int device, const
     return CU2B_OK;
 }
 
+extern "C" cu2b_status cu2b_session_create(cu2b_session **out, int device, const cu2b_csr *train,
+                                           const cu2b_csr *test, const cu2b_config *cfg,
+                                           const float *P, const float *Q, const float *user_bias,
+                                           const float *item_bias, float global_bias) {
+    return session_create_impl(out, device, train, test, cfg, P, Q, user_bias, item_bias, global_bias, true);
+}
+
 extern "C" cu2b_status cu2b_session_run(cu2b_session *s, int n_iterations) {
     if (!s || n_iterations < 0) return cu2b_fail(CU2B_ERR_INVALID, "cu2b_session_run: bad argument");
+    if (!s->stream_buf && s->cfg.mode == CU2B_MODE_HOGWILD && s->n_active > 0)
+        return cu2b_fail(CU2B_ERR_INVALID, "this session belongs to a DSGD context; use cu2b_dsgd_run");
     CUDA_TRY(cudaSetDevice(s->device));
     const int total = s->cfg.total_iterations, ce = s->cfg.check_error;
     auto is_check = [&](int i) {  // training.cu:118
