@@ -39,6 +39,10 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# torchrun pins OMP_NUM_THREADS=1; the host-side workload generator / CSV code is OpenMP code.
+# Give every rank its share of the host cores (must happen before libgomp initialises).
+if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // int(os.environ.get("LOCAL_WORLD_SIZE", os.environ["WORLD_SIZE"]))))
 
 WORKLOADS = {
     # name: (users, items, ratings, integer_ratings, default k)

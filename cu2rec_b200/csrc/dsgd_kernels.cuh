@@ -24,12 +24,12 @@ __device__ __forceinline__ void st_release_sys(int *p, int v) {
 
 // Spins (one thread) until *flag >= need. On timeout records an error and returns so that the
 // stream drains instead of hanging.
-__global__ void dsgd_wait_kernel(const int *flag, int need, int *error_flag) {
+__global__ void dsgd_wait_kernel(const int *flag, int need, int *error_flag, int site, long long timeout_cycles) {
     const long long t0 = clock64();
     while (ld_acquire_sys(flag) < need) {
         __nanosleep(200);
-        if (clock64() - t0 > kSpinTimeoutCycles) {
-            atomicExch(error_flag, 1);
+        if (clock64() - t0 > timeout_cycles) {
+            atomicCAS(error_flag, 0, site * 1000000 + need * 100 + (ld_acquire_sys(flag) % 100));
             return;
         }
     }
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(256)
 dsgd_loss_combine_kernel(DevState *st, const double *part_train, int nblk_train, const double *part_test,
                          int nblk_test, long long n_train_global, long long n_test_global, int iteration,
                          int apply_schedule, cu2b_metrics *log, DsgdLossPeers peers, int rank, int world,
-                         int check_no, int *error_flag) {
+                         int check_no, int *error_flag, long long timeout_cycles) {
     __shared__ double sh[256][2];
     __shared__ double tot[4];
     reduce_partials(part_train, nblk_train, &tot[0], sh);
@@ -272,7 +272,7 @@ dsgd_loss_combine_kernel(DevState *st, const double *part_train, int nblk_train,
         const long long t0 = clock64();
         while (ld_acquire_sys(peers.flags[rank] + threadIdx.x) < check_no) {
             __nanosleep(200);
-            if (clock64() - t0 > kSpinTimeoutCycles) { atomicExch(error_flag, 1); break; }
+            if (clock64() - t0 > timeout_cycles) { atomicCAS(error_flag, 0, 5000000 + check_no * 100 + threadIdx.x); break; }
         }
     }
     __syncthreads();

@@ -425,7 +425,7 @@ cu2b_status check_device_error(cu2b_session *s) {
     DevState st;
     CUDA_TRY(cudaMemcpy(&st, s->state, sizeof(st), cudaMemcpyDeviceToHost));
     if (st.error)
-        return cu2b_fail(CU2B_ERR_CUDA, "device-side wait timed out (code %d): %s", st.error,
+        return cu2b_fail(CU2B_ERR_CUDA, "device-side wait timed out (code %d = site*1e6 + need*100 + seen): %s", st.error,
                          st.error == 2 ? "per-user ordering gate" : "DSGD peer did not deliver");
     return CU2B_OK;
 }
