@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <climits>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -314,6 +315,40 @@ cu2b_status build_block_schedule(const cu2b_rating *coo, int64_t n, int rows, in
         for (int64_t t = 0; t < n; ++t) out->sched[(size_t)cursor[bucket(coo[t])]++] = coo[t];
     }
     return CU2B_OK;
+}
+
+// Share of the draws of its item block that the most frequently drawn item receives under
+// per-user sampling (one uniform draw per user per iteration). Host CSR only; 0 if unknown.
+double hot_item_share(const cu2b_csr *m, const int *item_block_ptr, int n_blocks) {
+    if (!m || m->on_device || m->nonzeros <= 0) return 0.0;
+    std::vector<double> w((size_t)m->cols, 0.0);
+    for (int u = 0; u < m->rows; ++u) {
+        const int lo = m->indptr[u], hi = m->indptr[u + 1];
+        if (hi > lo) {
+            const double pu = 1.0 / (hi - lo);
+            for (int j = lo; j < hi; ++j) w[m->indices[j]] += pu;
+        }
+    }
+    double hot = 0.0;
+    for (int b = 0; b < n_blocks; ++b) {
+        const int i0 = item_block_ptr ? item_block_ptr[b] : 0, i1 = item_block_ptr ? item_block_ptr[b + 1] : m->cols;
+        double tot = 0.0, mx = 0.0;
+        for (int i = i0; i < i1; ++i) { tot += w[i]; mx = std::max(mx, w[i]); }
+        if (tot > 0) hot = std::max(hot, mx / tot);
+    }
+    return hot;
+}
+
+// Asynchronous SGD is only stable while (updates of one parameter in flight) x lr stays well
+// below pi/2 (delayed-gradient bound); measured on B200: a DSGD sub-epoch with ~150 updates of
+// one item bias in flight at lr 0.01 diverges (profiles/r1_dsgd_round_sweep.jsonl). Bound the
+// number of concurrently processed ratings so that the hottest item sees <= budget / lr of them.
+int inflight_cap(double hot_share, float lr, double budget_default) {
+    double budget = budget_default;
+    if (const char *e = getenv("CU2B_INFLIGHT_LR")) budget = atof(e);
+    if (hot_share <= 0 || budget <= 0 || lr <= 0) return INT32_MAX;
+    const double cap = budget / ((double)lr * hot_share);
+    return cap > 1e9 ? INT32_MAX : (int)std::max(32.0, cap);
 }
 
 StreamView flat_view(const cu2b_rating *base, long long n, int chunk) {
@@ -640,6 +675,12 @@ static cu2b_status session_create_impl(cu2b_session **out, int device, const cu2
     s->sgd_grid_max = std::max(1, occ) * s->sm_count;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s->loss_kernel, kThreads, 0));
     s->loss_grid_max = std::max(1, occ) * s->sm_count;
+    {
+        // ratings in flight per CTA: 8 consumer warps x (32/L) groups x unroll (2 for L < 32)
+        const int per_cta = kConsumerWarps * (32 / s->L) * (s->L < 32 ? 2 : 1);
+        const int cap = inflight_cap(hot_item_share(train, nullptr, 1), cfg->learning_rate, 0.5);
+        s->sgd_grid_max = std::max(1, std::min(s->sgd_grid_max, cap / per_cta));
+    }
 
     if (const char *e = getenv("CU2B_TUNE_GATE")) s->no_gate = e[0] == '0';
     // update stream geometry: one segment per reference iteration
