@@ -448,16 +448,19 @@ def run_ours_dsgd(args, rank, world):
     dev_s = maxreduce(st["total_ms"]) / 1e3           # slowest rank, device time
     updates = sumreduce(st["updates"])
     sgd_ms_max = maxreduce(st["sgd_ms"])
+    sampler_ms_max, loss_ms_max = maxreduce(st["sampler_ms"]), maxreduce(st["loss_ms"])
     launches = sumreduce(st["kernel_launches"])
     value = updates / dev_s
     bytes_per_update = 16 * k + 12
     peak, peak_src = peaks()
     my_gbs = st["updates"] * bytes_per_update / (st["sgd_ms"] / 1e3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "mf_sgd_hogwild", "achieved": my_gbs, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "mf_sgd_user_runs", "achieved": my_gbs, "peak": peak, "unit": "GB/s",
                 "frac": my_gbs / peak, "traffic": None, "peak_source": peak_src, "scope": "rank 0, per GPU",
                 "algorithmic_bytes_per_update": bytes_per_update, "kernel_ms_per_step_max_rank": sgd_ms_max / args.steps,
-                "note": "per-rank P strip (%d MB) + Q fit in L2 at this width, so the kernel is L2-bound" % (
-                    inp.P.nbytes >> 20)}
+                "note": "DSGD sub-epoch kernel: a lane group keeps its user's P row in registers over the user's run, "
+                        "item rows are L2-resident (per-rank P strip %d MB); in-flight updates are capped for "
+                        "asynchronous-SGD stability (see DESIGN.md), so this is latency-, not bandwidth-bound" % (
+                            inp.P.nbytes >> 20)}
 
     # end to end: per rank H2D of its strips + model, T iterations, download, destroy
     pinp = cu.api.DsgdRankInputs(
@@ -499,6 +502,9 @@ def run_ours_dsgd(args, rank, world):
                     "what": "per rank: cu2b_dsgd_create(pinned host strips + model) + handle exchange + %d iterations "
                             "+ download + destroy; max over ranks" % T},
             "gpu_launches": int(launches), "clocks": clk,
+            "breakdown_ms_per_step_max_rank": {"sgd_subepochs": sgd_ms_max / args.steps, "sampler": sampler_ms_max / args.steps,
+                                               "loss_check_incl_gather": loss_ms_max / args.steps,
+                                               "handoff_waits_and_sends": (dev_s * 1e3 - sgd_ms_max - sampler_ms_max - loss_ms_max) / args.steps},
             "test_rmse": [round(r["test_rmse"], 5) for r in lg], "e2e_test_rmse": e2e_rmse,
             "loss_allreduce_check": {"nccl_train_rmse": nccl_rmse, "peer_memory_train_rmse": lg[-1]["train_rmse"]},
             "block_nnz_imbalance": float(part.block_nnz.max() / part.block_nnz.mean()),

@@ -166,11 +166,15 @@ mf_sgd_user_runs(const UserRunParams p) {
             pv[v] = (mine && v * L + l < vecs) ? __ldcg(Pv + po + v * L) : make_float4(0.f, 0.f, 0.f, 0.f);
         float ub = mine ? __ldcg(p.user_bias + u) : 0.f;
         const DsgdDraw *row = p.draws + (size_t)a * p.pitch;
+        DsgdDraw nxt;
+        nxt.item = 0; nxt.rating = 0.f;
+        if (mine) nxt = row[j];
         while (__any_sync(0xffffffffu, j < end)) {
             const bool ok = j < end;
-            DsgdDraw d;
-            d.item = 0; d.rating = 0.f;
-            if (ok) d = row[j];
+            const DsgdDraw d = nxt;
+            // the next draw is fetched one update ahead: it is not part of the item row's
+            // read -> atomic-add window, so it shortens the update without adding staleness
+            if (j + 1 < end) nxt = row[j + 1];
             const size_t qo = (size_t)d.item * vecs + l;
             float4 qv[V];
 #pragma unroll
