@@ -310,11 +310,13 @@ class Session:
         check(self.lib.cu2b_session_log(self.h, buf, cap, C.byref(n)))
         return _metrics_rows(buf, min(cap, n.value))
 
-    def download(self):
-        P = np.empty((self.rows, self.k), dtype=np.float32)
-        Q = np.empty((self.cols, self.k), dtype=np.float32)
-        ub = np.empty(self.rows, dtype=np.float32)
-        ib = np.empty(self.cols, dtype=np.float32)
+    def download(self, out=None):
+        """-> (P, Q, user_bias, item_bias). `out` = four preallocated float32 arrays (e.g. page-locked)."""
+        if out is None:
+            out = (np.empty((self.rows, self.k), dtype=np.float32), np.empty((self.cols, self.k), dtype=np.float32),
+                   np.empty(self.rows, dtype=np.float32), np.empty(self.cols, dtype=np.float32))
+        P, Q, ub, ib = out
+        assert P.size == self.rows * self.k and Q.size == self.cols * self.k and ub.size == self.rows and ib.size == self.cols
         check(self.lib.cu2b_session_download(self.h, _ptr(P), _ptr(Q), _ptr(ub), _ptr(ib)))
         return P, Q, ub, ib
 
@@ -461,12 +463,12 @@ class Dsgd:
         check(self.lib.cu2b_dsgd_local_sums(self.h, out))
         return list(out)
 
-    def download(self):
+    def download(self, out=None):
         """-> (P strip, Q in renumbered item order, user_bias strip, item_bias renumbered)."""
-        P = np.empty((self.rows, self.k), dtype=np.float32)
-        Q = np.empty((self.cols, self.k), dtype=np.float32)
-        ub = np.empty(self.rows, dtype=np.float32)
-        ib = np.empty(self.cols, dtype=np.float32)
+        if out is None:
+            out = (np.empty((self.rows, self.k), dtype=np.float32), np.empty((self.cols, self.k), dtype=np.float32),
+                   np.empty(self.rows, dtype=np.float32), np.empty(self.cols, dtype=np.float32))
+        P, Q, ub, ib = out
         check(self.lib.cu2b_session_download(self._session(), _ptr(P), _ptr(Q), _ptr(ub), _ptr(ib)))
         return P, Q, ub, ib
 

@@ -17,6 +17,7 @@
 #include <cfloat>
 #include <cmath>
 #include <climits>
+#include <ctime>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -46,6 +47,26 @@ using namespace cu2b;
     } while (0)
 
 namespace {
+
+// CU2B_TRACE=1: wall-clock phase timings of the host-side session life cycle on stderr.
+struct Trace {
+    bool on;
+    double t0, last;
+    const char *what;
+    static double now() {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    }
+    explicit Trace(const char *w) : on(getenv("CU2B_TRACE") != nullptr), t0(now()), last(t0), what(w) {}
+    void mark(const char *phase) {
+        if (!on) return;
+        cudaDeviceSynchronize();
+        const double t = now();
+        fprintf(stderr, "[cu2b trace] %s: %-28s %8.2f ms (total %8.2f)\n", what, phase, t - last, t - t0);
+        last = t;
+    }
+};
 
 // ---------------------------------------------------------------------------------------
 // small RAII pool: everything allocated through it is released when it goes out of scope
@@ -322,12 +343,19 @@ cu2b_status build_block_schedule(const cu2b_rating *coo, int64_t n, int rows, in
 double hot_item_share(const cu2b_csr *m, const int *item_block_ptr, int n_blocks) {
     if (!m || m->on_device || m->nonzeros <= 0) return 0.0;
     std::vector<double> w((size_t)m->cols, 0.0);
-    for (int u = 0; u < m->rows; ++u) {
-        const int lo = m->indptr[u], hi = m->indptr[u + 1];
-        if (hi > lo) {
-            const double pu = 1.0 / (hi - lo);
-            for (int j = lo; j < hi; ++j) w[m->indices[j]] += pu;
+#pragma omp parallel
+    {
+        std::vector<double> mine((size_t)m->cols, 0.0);
+#pragma omp for schedule(static) nowait
+        for (int u = 0; u < m->rows; ++u) {
+            const int lo = m->indptr[u], hi = m->indptr[u + 1];
+            if (hi > lo) {
+                const double pu = 1.0 / (hi - lo);
+                for (int j = lo; j < hi; ++j) mine[m->indices[j]] += pu;
+            }
         }
+#pragma omp critical
+        for (int i = 0; i < m->cols; ++i) w[i] += mine[i];
     }
     double hot = 0.0;
     for (int b = 0; b < n_blocks; ++b) {
@@ -645,9 +673,13 @@ static cu2b_status session_create_impl(cu2b_session **out, int device, const cu2
     s->sm_count = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
 
+    Trace tr("session_create");
+    tr.mark("setup");
     std::vector<int> indptr_host;
     CU2B_TRY(upload_matrix(s->pool, s->stream, train, &s->train, &indptr_host));
+    tr.mark("upload train matrix");
     CU2B_TRY(upload_matrix(s->pool, s->stream, test, &s->test, nullptr));
+    tr.mark("upload test matrix");
     // users with at least one training rating (sgd.cu:35 skips the others)
     std::vector<int> active;
     active.reserve(s->rows);
@@ -667,6 +699,7 @@ static cu2b_status session_create_impl(cu2b_session **out, int device, const cu2
     CUDA_TRY(cudaMemcpyAsync(s->ub, user_bias, (size_t)s->rows * sizeof(float), cudaMemcpyHostToDevice, s->stream));
     CUDA_TRY(cudaMemcpyAsync(s->ib, item_bias, (size_t)s->cols * sizeof(float), cudaMemcpyHostToDevice, s->stream));
 
+    tr.mark("active list + model upload");
     // kernels and their persistent grid sizes
     s->sgd_kernel = pick_sgd(s->L, s->V);
     s->loss_kernel = pick_loss(s->L, s->V);
@@ -682,6 +715,7 @@ static cu2b_status session_create_impl(cu2b_session **out, int device, const cu2
         s->sgd_grid_max = std::max(1, std::min(s->sgd_grid_max, cap / per_cta));
     }
 
+    tr.mark("occupancy + hot-item share");
     if (const char *e = getenv("CU2B_TUNE_GATE")) s->no_gate = e[0] == '0';
     // update stream geometry: one segment per reference iteration
     s->seg_pitch = ((long long)s->n_active + 3) & ~3LL;
@@ -732,6 +766,7 @@ static cu2b_status session_create_impl(cu2b_session **out, int device, const cu2
     st.log_cap = s->log_cap;
     CUDA_TRY(cudaMemcpyAsync(s->state, &st, sizeof(st), cudaMemcpyHostToDevice, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
+    tr.mark("stream/loss buffers + state");
     *out = guard.release();
     return CU2B_OK;
 }
@@ -816,11 +851,13 @@ extern "C" cu2b_status cu2b_session_download(cu2b_session *s, float *P, float *Q
                                              float *item_bias) {
     if (!s) return cu2b_fail(CU2B_ERR_INVALID, "cu2b_session_download: null session");
     CUDA_TRY(cudaSetDevice(s->device));
+    Trace tr("session_download");
     if (P) CU2B_TRY(download_dense(s->stream, P, s->P, s->rows, s->k, s->kp));
     if (Q) CU2B_TRY(download_dense(s->stream, Q, s->Q, s->cols, s->k, s->kp));
     if (user_bias) CUDA_TRY(cudaMemcpyAsync(user_bias, s->ub, (size_t)s->rows * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
     if (item_bias) CUDA_TRY(cudaMemcpyAsync(item_bias, s->ib, (size_t)s->cols * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
+    tr.mark("D2H");
     return CU2B_OK;
 }
 
@@ -845,7 +882,9 @@ extern "C" cu2b_status cu2b_session_stats(cu2b_session *s, cu2b_stats *out, int 
 extern "C" void cu2b_session_destroy(cu2b_session *s) {
     if (!s) return;
     cudaSetDevice(s->device);
+    Trace tr("session_destroy");
     delete s;
+    tr.mark("free");
 }
 
 extern "C" cu2b_status cu2b_train(const cu2b_csr *train, const cu2b_csr *test, cu2b_config *cfg,
