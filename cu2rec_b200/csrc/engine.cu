@@ -253,20 +253,34 @@ SgdKernel pick_sgd(int L, int V) {
         default: return pick_sgd_t<3>(L, V);
     }
 }
-LossKernel pick_loss(int L, int V) {
+// The loss kernel is issue-bound, not memory-bound (profiles/r1_loss_summary.txt: SM 70 %, L2
+// 23 %), so it uses a denser lane layout than the update kernel: up to four float4 per lane,
+// i.e. 4 ratings per warp at k = 128 (L = 8, V = 4) -- fewer shuffles and fewer instructions per
+// rating, and the 4 ratings of a pass usually share the user, so their P loads coalesce.
+void loss_layout_for(int kp, int *L, int *V) {
+    const int vecs = kp / 4, need = (vecs + 3) / 4;
+    int l = 1;
+    while (l < need) l <<= 1;
+    *L = l;
+    *V = (vecs + l - 1) / l;
+}
+
+LossKernel pick_loss(int kp) {
+    int L, V;
+    loss_layout_for(kp, &L, &V);
     switch (L) {
-        case 1: return mf_loss_fused<1, 1>;
-        case 2: return mf_loss_fused<2, 1>;
-        case 4: return mf_loss_fused<4, 1>;
-        case 8: return mf_loss_fused<8, 1>;
-        case 16: return mf_loss_fused<16, 1>;
-        default:
+        case 1:
             switch (V) {
-                case 1: return mf_loss_fused<32, 1>;
-                case 2: return mf_loss_fused<32, 2>;
-                case 3: return mf_loss_fused<32, 3>;
-                default: return mf_loss_fused<32, 4>;
+                case 1: return mf_loss_fused<1, 1>;
+                case 2: return mf_loss_fused<1, 2>;
+                case 3: return mf_loss_fused<1, 3>;
+                default: return mf_loss_fused<1, 4>;
             }
+        case 2: return V == 3 ? mf_loss_fused<2, 3> : mf_loss_fused<2, 4>;
+        case 4: return V == 3 ? mf_loss_fused<4, 3> : mf_loss_fused<4, 4>;
+        case 8: return V == 3 ? mf_loss_fused<8, 3> : mf_loss_fused<8, 4>;
+        case 16: return V == 3 ? mf_loss_fused<16, 3> : mf_loss_fused<16, 4>;
+        default: return V == 3 ? mf_loss_fused<32, 3> : mf_loss_fused<32, 4>;
     }
 }
 
@@ -702,7 +716,7 @@ static cu2b_status session_create_impl(cu2b_session **out, int device, const cu2
     tr.mark("active list + model upload");
     // kernels and their persistent grid sizes
     s->sgd_kernel = pick_sgd(s->L, s->V);
-    s->loss_kernel = pick_loss(s->L, s->V);
+    s->loss_kernel = pick_loss(s->kp);
     int occ = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s->sgd_kernel, kThreads, 0));
     s->sgd_grid_max = std::max(1, occ) * s->sm_count;
@@ -971,7 +985,7 @@ struct Scratch {
         CUDA_TRY(cudaMemcpyAsync(s.ub, ub, (size_t)rows * sizeof(float), cudaMemcpyHostToDevice, s.stream));
         CUDA_TRY(cudaMemcpyAsync(s.ib, ib, (size_t)cols * sizeof(float), cudaMemcpyHostToDevice, s.stream));
         s.sgd_kernel = pick_sgd(s.L, s.V);
-        s.loss_kernel = pick_loss(s.L, s.V);
+        s.loss_kernel = pick_loss(s.kp);
         int occ = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s.sgd_kernel, kThreads, 0));
         s.sgd_grid_max = std::max(1, occ) * s.sm_count;

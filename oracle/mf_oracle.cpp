@@ -17,9 +17,11 @@
 // Two arithmetic "flavours" of the single update / prediction are provided:
 //   ORC_FLAVOUR_REF    : the op order of matrix_factorization/mf_sequential.cu:114-141
 //                        (serial ascending-f dot product, unfused mul/add);
-//   ORC_FLAVOUR_KERNEL : the op order of our CUDA kernels (per-lane fmaf partial sums,
+//   ORC_FLAVOUR_KERNEL : the op order of our CUDA update kernels (per-lane fmaf partial sums,
 //                        xor-butterfly reduction over L lanes, same unfused update ops).
 //                        Used for the bit-exact check of the deterministic mode.
+//   ORC_FLAVOUR_LOSS_KERNEL : same, with the lane layout of the loss kernel (up to four float4
+//                        per lane so that several ratings share a warp).
 // Build with -ffp-contract=off so the compiler introduces no FMAs of its own.
 
 #include <cmath>
@@ -33,7 +35,7 @@
 
 extern "C" {
 
-enum { ORC_FLAVOUR_REF = 0, ORC_FLAVOUR_KERNEL = 1 };
+enum { ORC_FLAVOUR_REF = 0, ORC_FLAVOUR_KERNEL = 1, ORC_FLAVOUR_LOSS_KERNEL = 2 };
 
 typedef struct {
     int32_t user;
@@ -159,9 +161,17 @@ static void kernel_layout(int k, int *L, int *V) {
     *V = (vecs + l - 1) / l;
 }
 
-static float dot_kernel_flavour(const float *p, const float *q, int k) {
-    int L, V;
-    kernel_layout(k, &L, &V);
+// The loss kernel packs more ratings into a warp: up to 4 float4 per lane.
+static void loss_layout(int k, int *L, int *V) {
+    int vecs = ((k + 3) & ~3) / 4;
+    int need = (vecs + 3) / 4;  // lanes needed at 4 float4 per lane
+    int l = 1;
+    while (l < need) l <<= 1;
+    *L = l;
+    *V = (vecs + l - 1) / l;
+}
+
+static float dot_layout(const float *p, const float *q, int k, int L, int V) {
     float acc[32];
     for (int l = 0; l < L; ++l) {
         float a = 0.0f;
@@ -184,6 +194,12 @@ static float dot_kernel_flavour(const float *p, const float *q, int k) {
     return acc[0];
 }
 
+static float dot_kernel_flavour(const float *p, const float *q, int k) {
+    int L, V;
+    kernel_layout(k, &L, &V);
+    return dot_layout(p, q, k, L, V);
+}
+
 float orc_predict(const float *p, const float *q, int k, float ub, float ib, float mu,
                   int flavour) {
     if (flavour == ORC_FLAVOUR_REF) {
@@ -192,6 +208,11 @@ float orc_predict(const float *p, const float *q, int k, float ub, float ib, flo
         return pred;
     }
     float base = (mu + ub) + ib;
+    if (flavour == ORC_FLAVOUR_LOSS_KERNEL) {
+        int L, V;
+        loss_layout(k, &L, &V);
+        return base + dot_layout(p, q, k, L, V);
+    }
     return base + dot_kernel_flavour(p, q, k);
 }
 

@@ -13,7 +13,7 @@ LIB = os.path.join(ODIR, "liboracle.so")
 REF_DIR = os.path.join(ODIR, "_ref")
 
 TRIPLET = np.dtype([("user", np.int32), ("item", np.int32), ("rating", np.float32)])
-FLAVOUR_REF, FLAVOUR_KERNEL = 0, 1
+FLAVOUR_REF, FLAVOUR_KERNEL, FLAVOUR_LOSS_KERNEL = 0, 1, 2
 
 
 class Hyper(C.Structure):

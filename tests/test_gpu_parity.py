@@ -74,7 +74,7 @@ def test_residuals_and_metrics_vs_oracle(k):
     P, Q, ub, ib = _model(rng, U, I, k)
     mu = 3.3
     err = cu.calculate_loss_gpu(P, Q, k, m, ub, ib, mu)
-    want_k = O.residuals(m.indptr, m.indices, m.data, P, Q, ub, ib, mu, k, O.FLAVOUR_KERNEL)
+    want_k = O.residuals(m.indptr, m.indices, m.data, P, Q, ub, ib, mu, k, O.FLAVOUR_LOSS_KERNEL)
     assert err.view(np.uint32).tolist() == want_k.view(np.uint32).tolist()  # same op order => same bits
     want_r = O.residuals(m.indptr, m.indices, m.data, P, Q, ub, ib, mu, k, O.FLAVOUR_REF)
     np.testing.assert_allclose(err, want_r, rtol=0, atol=2e-5)  # reference op order: fp32 rounding only
