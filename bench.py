@@ -175,6 +175,16 @@ class CpuReference:
         self.binary = O.ref_binary("mf_cpu")
         self.kind = "reference" if self.binary else "port"
         self.tmp = tempfile.mkdtemp(prefix="cu2b_ref_")
+        # mf_sequential.cu:111 draws from the INCLUSIVE range [low, high]: for the last user the
+        # reference reads one element past its rating arrays with probability 1/(degree+1) per
+        # iteration and can segfault on what it finds there. End the sample on the heaviest user
+        # near the requested cut to make that rare, and retry on a crash (run_once).
+        tr_all, _, U_all, _ = make_workload(workload)
+        if self.sample_users < U_all:
+            lo = max(1, int(self.sample_users * 0.9))
+            deg = np.bincount(tr_all["user"][: int(np.searchsorted(tr_all["user"], self.sample_users))],
+                              minlength=self.sample_users)
+            self.sample_users = lo + int(np.argmax(deg[lo:self.sample_users])) + 1
         self.tr, self.te, self.U, self.I = make_workload(workload, users_prefix=self.sample_users)
         if self.binary:
             write_csv(os.path.join(self.tmp, "train.csv"), self.tr)
@@ -194,8 +204,15 @@ class CpuReference:
         if self.binary:
             cfg = os.path.join(self.tmp, "c.cfg")
             open(cfg, "w").write("0 %d %d 0.01 42 0.02 0.02 0.02 0.02" % (self.iters, self.k))
-            out = subprocess.run([self.binary, "-c", cfg, os.path.join(self.tmp, "train.csv"), os.path.join(self.tmp, "test.csv")],
-                                 capture_output=True, text=True, check=True).stdout
+            for attempt in range(6):
+                p = subprocess.run([self.binary, "-c", cfg, os.path.join(self.tmp, "train.csv"), os.path.join(self.tmp, "test.csv")],
+                                   capture_output=True, text=True)
+                if p.returncode == 0:
+                    break
+                log("[bench] reference mf_cpu died with rc=%d (its out-of-range sample, mf_sequential.cu:111); retrying" % p.returncode)
+            else:
+                raise RuntimeError("reference mf_cpu crashed 6 times in a row")
+            out = p.stdout
             secs = float(re.search(r"Time taken for \d+ of iterations is ([0-9.eE+-]+)", out).group(1))
             rmse = float([l for l in out.splitlines() if l.startswith("TEST:")][-1].split()[-1])
             return updates, secs, rmse

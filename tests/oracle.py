@@ -48,6 +48,17 @@ def ref_binary(name):
     return p if os.path.exists(p) else None
 
 
+def run_mf_cpu(cfg, train_csv, test_csv, attempts=8):
+    """Runs the unmodified reference mf_cpu and returns its stdout. mf_sequential.cu:111 samples from
+    the inclusive range [low, high], so the last user occasionally reads one element past the
+    rating arrays and the process can die on what it finds there: retry."""
+    for _ in range(attempts):
+        p = subprocess.run([ref_binary("mf_cpu"), "-c", str(cfg), str(train_csv), str(test_csv)], capture_output=True, text=True)
+        if p.returncode == 0:
+            return p.stdout
+    raise RuntimeError("reference mf_cpu crashed %d times in a row (rc=%d)" % (attempts, p.returncode))
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 

@@ -475,3 +475,77 @@ def test_full_size_properties_ml20m_shape():
     assert rm[-1] < rm[0] and np.isfinite(rm).all()
     assert out["stats"]["updates"] == 300 * U
     assert np.all(np.isfinite(out["P"])) and np.all(np.isfinite(out["Q"]))
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json configs as parity cases
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.skipif(O.ref_binary("mf_cpu") is None, reason="oracle/_ref not built")
+def test_config1_ml100k_shape_k32_vs_compiled_mf_cpu(tmp_path):
+    """configs[0]: MovieLens-100K-shape synthetic, k=32, the reference's mf_sequential CPU path vs
+    our GPU path at equal iterations: final TEST RMSE within 0.5 % (mean of two mf_cpu runs; it
+    seeds from random_device)."""
+    U, I = 943, 1682
+    tr, te = cu.synth_ratings(U, I, 100000, integer_ratings=False)
+    def write(path, r):
+        with open(path, "w") as f:
+            f.write("userId,itemId,rating\n")
+            f.write("".join("%d,%d,%.1f\n" % (u + 1, i + 1, x) for u, i, x in r))
+    write(tmp_path / "train.csv", tr)
+    write(tmp_path / "test.csv", te)
+    iters, k = 500, 32
+    (tmp_path / "c.cfg").write_text("0 %d %d 0.01 42 0.02 0.02 0.02 0.02" % (iters, k))
+    finals = []
+    for _ in range(2):
+        out = O.run_mf_cpu(tmp_path / "c.cfg", tmp_path / "train.csv", tmp_path / "test.csv")
+        finals.append(float([l for l in out.splitlines() if l.startswith("TEST:")][-1].split()[-1]))
+    ref = float(np.mean(finals))
+    r2, rows, cols, gb = cu.readCSV(tmp_path / "train.csv")
+    t2, trows, tcols, _ = cu.readCSV(tmp_path / "test.csv")
+    rows, cols = max(rows, trows), max(cols, tcols)
+    cfg = cu.Config()
+    cfg.read_config(tmp_path / "c.cfg")
+    out = cu.train(cu.createSparseMatrix(r2, rows, cols), cu.createSparseMatrix(t2, rows, cols), cfg, gb)
+    got = out["log"][-1]["test_rmse"]
+    assert abs(got - ref) / ref < 0.005, (got, finals)
+
+
+def test_config4_deterministic_mode_k256_vs_sequential_ordering():
+    """configs[3] at a size the CPU replay finishes in seconds: k=256, 64 x 64 blocks, 1.5 M
+    ratings of the Netflix-shape generator. Bit-exact against the sequential replay in the
+    schedule's order (KERNEL flavour), 5e-5 against the mf_sequential op order."""
+    U, I, k, B = 40000, 6000, 256, 64
+    tr, _ = cu.synth_ratings(U, I, 1500000, integer_ratings=True, seed=77)
+    rng = np.random.RandomState(8)
+    P, Q, ub, ib = _model(rng, U, I, k)
+    cfg = cu.Config(n_factors=k)
+    got = cu.sgd_blocked(tr, P, Q, ub, ib, 3.6, cfg, B, n_passes=1)
+    order = O.block_schedule_order(tr, U, I, B)
+    want = O.sgd_apply_stream(tr[order], P.ravel(), Q.ravel(), ub, ib, 3.6, O.hyper_from_cfg(cfg), O.FLAVOUR_KERNEL)
+    for g, w in zip(got, want):
+        assert np.array_equal(g.ravel().view(np.uint32), w.view(np.uint32))
+    ref = O.sgd_apply_stream(tr[order], P.ravel(), Q.ravel(), ub, ib, 3.6, O.hyper_from_cfg(cfg), O.FLAVOUR_REF)
+    for g, w in zip(got, ref):
+        np.testing.assert_allclose(g.ravel(), w, rtol=0, atol=5e-5)
+
+
+def test_config4_deterministic_mode_full_netflix_shape_is_reproducible():
+    """configs[3] at full size (480 189 x 17 770 x ~100 M, k=256): size-independent properties --
+    two independent runs of one deterministic pass give identical bits, the pass lowers the
+    training loss, and the schedule is a permutation of the ratings."""
+    U, I, k = 480189, 17770, 256
+    tr, te = cu.synth_ratings(U, I, 100480507, integer_ratings=True)
+    mtr, mte = cu.createSparseMatrix(tr, U, I), cu.createSparseMatrix(te, U, I)
+    mu = np.float32(tr["rating"].astype(np.float64).sum() / len(tr))
+    iters = int(np.ceil(len(tr) / U))  # exactly one pass worth of updates
+    runs = []
+    for _ in range(2):
+        cfg = cu.Config(total_iterations=iters, n_factors=k, check_error=iters, mode=cu.MODE_DETERMINISTIC, n_blocks=512)
+        out = cu.train(mtr, mte, cfg, mu)
+        runs.append(out)
+        assert out["stats"]["updates"] == len(tr)
+    a, b = runs
+    assert np.array_equal(a["P"].view(np.uint32), b["P"].view(np.uint32))
+    assert np.array_equal(a["Q"].view(np.uint32), b["Q"].view(np.uint32))
+    assert [r["train_rmse"] for r in a["log"]] == [r["train_rmse"] for r in b["log"]]
+    assert np.isfinite(a["log"][-1]["train_rmse"]) and a["log"][-1]["train_rmse"] < a["log"][0]["train_rmse"]

@@ -219,8 +219,7 @@ def test_trainer_matches_compiled_mf_cpu_rmse(tmp_path):
     (tmp_path / "c.cfg").write_text("0 %d %d 0.01 42 0.02 0.02 0.02 0.02" % (iters, k))
     finals = []
     for _ in range(2):
-        out = subprocess.run([O.ref_binary("mf_cpu"), "-c", str(tmp_path / "c.cfg"), str(tmp_path / "train.csv"),
-                              str(tmp_path / "test.csv")], capture_output=True, text=True, check=True).stdout
+        out = O.run_mf_cpu(tmp_path / "c.cfg", tmp_path / "train.csv", tmp_path / "test.csv")
         finals.append(float([l for l in out.splitlines() if l.startswith("TEST:")][-1].split()[-1]))
     ref_rmse = float(np.mean(finals))
     mu = np.float32(tr["rating"].astype(np.float64).sum() / len(tr))
