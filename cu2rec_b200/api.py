@@ -484,6 +484,20 @@ class Dsgd:
             pass
 
 
+def predict_topk(P, Q, user_bias, item_bias, global_bias, topk, exclude=None):
+    """Top-k unrated items for every user -> (items [U, topk] int32, scores [U, topk] float32, timing dict)."""
+    P, Q, ub, ib = _f32(P), _f32(Q), _f32(user_bias), _f32(item_bias)
+    rows, cols = ub.shape[0], ib.shape[0]
+    k = P.size // rows
+    items = np.empty((rows, topk), dtype=np.int32)
+    scores = np.empty((rows, topk), dtype=np.float32)
+    ms = (C.c_double * 2)()
+    ex = exclude.c() if exclude is not None else None
+    check(_lib.load().cu2b_predict_topk(_ptr(P), rows, _ptr(Q), cols, _ptr(ub), _ptr(ib), float(global_bias), k,
+                                        C.byref(ex) if ex is not None else None, topk, _ptr(items), _ptr(scores), ms))
+    return items, scores, dict(candidates_ms=ms[0], rescore_ms=ms[1])
+
+
 def device_info(device=0):
     lib = _lib.load()
     name = C.create_string_buffer(256)

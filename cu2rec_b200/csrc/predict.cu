@@ -1,0 +1,460 @@
+// Batched predict + top-k (BASELINE config 5): score every user against the
+// whole catalogue and keep each user's best unrated items. Replaces the per-user CPU loops of
+// the reference (predict_ratings predict.cu:17-29, get_recommendations predict.cu:49-63).
+//
+// Scoring all 480 189 x 17 770 pairs at k = 128 is a genuine dense GEMM (2.2 TFLOP), so this is
+// the one place the 5th-generation tensor cores are used:
+//   pass 1  predict_candidates_kernel (tcgen05 / TMEM / TMA, one CTA per SM, persistent):
+//           D[128 users x 128 items] = P_tile . Q_tile^T in TF32 (kind::tf32 reads the fp32 rows
+//           as they are), fp32 accumulators in TMEM, double buffered. The epilogue warps read the
+//           accumulators with tcgen05.ld, add the item bias, drop items the user has already
+//           rated (one 128-bit word of a per-user bitmap per tile) and keep a sorted list of the
+//           KC best candidates per user in registers. Nothing of the 8.5 G score matrix is
+//           ever written.
+//   pass 2  predict_rescore_kernel: exact fp32 scores of the KC candidates in the reference's
+//           op order (serial dot, predict.cu:22-26), final ordering (score desc, item asc), top-k.
+// The candidate list is longer than k (KC = 16 or 32), so TF32 rounding can only matter if a true
+// top-k item is not even among the KC best TF32 scores.
+//
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer,
+// warps 2-5 epilogue (TMEM lane quadrant = warp % 4).
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "cu2b_internal.h"
+
+#define CUDA_TRY(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return cu2b_fail(CU2B_ERR_CUDA, "Cuda Error: %s (%s:%d)", cudaGetErrorString(e__), \
+                             __FILE__, __LINE__);                                             \
+    } while (0)
+
+namespace {
+
+constexpr int BM = 128;        // users per tile (MMA M, = TMEM lanes)
+constexpr int BN = 128;        // items per tile (MMA N, = TMEM columns per accumulator)
+constexpr int SLAB_K = 32;     // floats per 128-byte swizzle row
+constexpr int SLAB_BYTES = BM * SLAB_K * 4;  // 16 KB: 128 rows x 128 B
+constexpr int kThreadsPredict = 192;
+
+__device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint64_t *b, int n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(b)), "r"(n)); }
+__device__ __forceinline__ void bar_arrive(uint64_t *b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(b)) : "memory"); }
+__device__ __forceinline__ void bar_expect(uint64_t *b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t *b, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\tbra WAIT_LOOP;\n\tDONE:\n\t}" ::"r"(s32(b)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+            "r"(s32(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(s32(bar))
+        : "memory");
+}
+// K-major, 128-byte swizzle shared-memory matrix descriptor (sm_100 UMMA): start address and
+// stride between 8-row groups (1024 B) in 16-byte units, version 1, layout type SWIZZLE_128B.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);        // start address      bits [0,14)
+    d |= (uint64_t)1 << 16;                            // leading byte off.  bits [16,30) (unused for SW128 K-major)
+    d |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;       // stride byte offset bits [32,46)
+    d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+    return d;
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 128
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct PredictSmemCtl {
+    uint64_t a_full, a_empty;
+    uint64_t b_full[2], b_empty[2];
+    uint64_t acc_full[2], acc_empty[2];
+    uint32_t tmem_base;
+    uint32_t pad;
+    float ib[2][BN];
+};
+
+struct PredictParams {
+    int users, items, kslabs;
+    int n_user_tiles, n_item_tiles;
+    const float *item_bias;
+    const uint32_t *bitmap;  // [users][mask_pitch] words, bit i set => item i already rated; nullptr => none
+    int mask_pitch;          // words per user (multiple of 4)
+    int32_t *cand_items;     // [users][KC]
+    float *cand_scores;      // [users][KC] (TF32 scores incl. item bias; diagnostics)
+};
+
+template <int KC>
+__global__ void __launch_bounds__(kThreadsPredict, 1)
+predict_candidates_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_q,
+                          const PredictParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // SW128 needs 1024-byte alignment
+    uint8_t *smem_a = base;                                        // kslabs slabs
+    uint8_t *smem_b = base + (size_t)p.kslabs * SLAB_BYTES;        // 2 stages x kslabs slabs
+    PredictSmemCtl *ctl = (PredictSmemCtl *)(smem_b + (size_t)2 * p.kslabs * SLAB_BYTES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t slab_tx = (uint32_t)p.kslabs * SLAB_BYTES;
+
+    if (threadIdx.x == 0) {
+        bar_init(&ctl->a_full, 1);
+        bar_init(&ctl->a_empty, 1);
+        for (int s = 0; s < 2; ++s) {
+            bar_init(&ctl->b_full[s], 1);
+            bar_init(&ctl->b_empty[s], 1);
+            bar_init(&ctl->acc_full[s], 1);
+            bar_init(&ctl->acc_empty[s], 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // TMEM: 2 accumulators x 128 columns
+        const uint32_t ncols = 256;
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&ctl->tmem_base)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = ctl->tmem_base;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int it = 0, n = 0;
+            for (int ut = blockIdx.x; ut < p.n_user_tiles; ut += gridDim.x, ++n) {
+                if (n > 0) bar_wait(&ctl->a_empty, (n - 1) & 1);
+                bar_expect(&ctl->a_full, slab_tx);
+                for (int sl = 0; sl < p.kslabs; ++sl)
+                    tma_load_2d(smem_a + (size_t)sl * SLAB_BYTES, &map_p, sl * SLAB_K, ut * BM, &ctl->a_full);
+                for (int j = 0; j < p.n_item_tiles; ++j, ++it) {
+                    const int s = it & 1;
+                    if (it >= 2) bar_wait(&ctl->b_empty[s], ((it >> 1) - 1) & 1);
+                    bar_expect(&ctl->b_full[s], slab_tx);
+                    for (int sl = 0; sl < p.kslabs; ++sl)
+                        tma_load_2d(smem_b + ((size_t)s * p.kslabs + sl) * SLAB_BYTES, &map_q, sl * SLAB_K, j * BN,
+                                    &ctl->b_full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(BM, BN);
+            int it = 0, n = 0;
+            for (int ut = blockIdx.x; ut < p.n_user_tiles; ut += gridDim.x, ++n) {
+                bar_wait(&ctl->a_full, n & 1);
+                for (int j = 0; j < p.n_item_tiles; ++j, ++it) {
+                    const int s = it & 1;
+                    bar_wait(&ctl->b_full[s], (it >> 1) & 1);
+                    if (it >= 2) bar_wait(&ctl->acc_empty[s], ((it >> 1) - 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t d_tmem = tmem_base + (uint32_t)s * BN;
+                    for (int sl = 0; sl < p.kslabs; ++sl) {
+                        const uint32_t a0 = s32(smem_a + (size_t)sl * SLAB_BYTES);
+                        const uint32_t b0 = s32(smem_b + ((size_t)s * p.kslabs + sl) * SLAB_BYTES);
+#pragma unroll
+                        for (int ks = 0; ks < SLAB_K / 8; ++ks)  // K = 8 tf32 (32 bytes) per instruction
+                            umma_tf32(d_tmem, umma_desc_sw128(a0 + ks * 32), umma_desc_sw128(b0 + ks * 32), idesc,
+                                      (uint32_t)((sl | ks) != 0));
+                    }
+                    umma_commit(&ctl->b_empty[s]);   // smem stage may be refilled once these MMAs retire
+                    umma_commit(&ctl->acc_full[s]);  // accumulator ready for the epilogue
+                }
+                umma_commit(&ctl->a_empty);
+            }
+        }
+    } else {
+        // ===== epilogue: 4 warps, one TMEM lane (= one user) per thread =====
+        const int quad = warp & 3;
+        const int et = (warp - 2) * 32 + lane;  // 0..127, only used to stage the item-bias tile
+        int it = 0;
+        for (int ut = blockIdx.x; ut < p.n_user_tiles; ut += gridDim.x) {
+            const int u = ut * BM + quad * 32 + lane;
+            float cs[KC];
+            int ci[KC];
+#pragma unroll
+            for (int i = 0; i < KC; ++i) { cs[i] = -INFINITY; ci[i] = -1; }
+            uint4 mask = make_uint4(0u, 0u, 0u, 0u);
+            const uint4 *mrow = (p.bitmap && u < p.users) ? reinterpret_cast<const uint4 *>(p.bitmap + (size_t)u * p.mask_pitch) : nullptr;
+            if (mrow) mask = __ldg(mrow);
+            for (int j = 0; j < p.n_item_tiles; ++j, ++it) {
+                const int s = it & 1;
+                const int n0 = j * BN;
+                ctl->ib[s][et] = (n0 + et < p.items) ? __ldg(p.item_bias + n0 + et) : 0.f;
+                const uint4 mask_next = (mrow && j + 1 < p.n_item_tiles) ? __ldg(mrow + j + 1) : make_uint4(0u, 0u, 0u, 0u);
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                bar_wait(&ctl->acc_full[s], (it >> 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t mw[4] = {mask.x, mask.y, mask.z, mask.w};
+#pragma unroll
+                for (int ch = 0; ch < BN / 32; ++ch) {
+                    float v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * BN + ch * 32), v);
+                    const uint32_t mword = mw[ch];
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const int item = n0 + ch * 32 + c;
+                        const float sc = v[c] + ctl->ib[s][ch * 32 + c];
+                        const bool ok = item < p.items && !((mword >> c) & 1u);
+                        if (ok && sc > cs[KC - 1]) {
+                            // sorted insert (descending); ties keep the earlier (smaller) item first
+                            cs[KC - 1] = sc;
+                            ci[KC - 1] = item;
+#pragma unroll
+                            for (int i = KC - 1; i > 0; --i) {
+                                if (cs[i] > cs[i - 1]) {
+                                    const float ts = cs[i]; cs[i] = cs[i - 1]; cs[i - 1] = ts;
+                                    const int ti = ci[i]; ci[i] = ci[i - 1]; ci[i - 1] = ti;
+                                }
+                            }
+                        }
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) bar_arrive(&ctl->acc_empty[s]);
+                mask = mask_next;
+            }
+            if (u < p.users) {
+#pragma unroll
+                for (int i = 0; i < KC; ++i) {
+                    p.cand_items[(size_t)u * KC + i] = ci[i];
+                    p.cand_scores[(size_t)u * KC + i] = cs[i];
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t ncols = 256;
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    }
+}
+
+// One bit per (user, item) already rated.
+__global__ void __launch_bounds__(256)
+rated_bitmap_kernel(const int *__restrict__ indptr, const int *__restrict__ indices, int users, long long nnz,
+                    uint32_t *bitmap, int mask_pitch) {
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < nnz; j += (long long)gridDim.x * blockDim.x) {
+        int lo = 0, hi = users;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(indptr + mid) <= j) lo = mid; else hi = mid;
+        }
+        const int item = __ldg(indices + j);
+        atomicOr(bitmap + (size_t)lo * mask_pitch + (item >> 5), 1u << (item & 31));
+    }
+}
+
+// Exact fp32 score of every candidate in the reference's op order (predict.cu:22-26), then the
+// final order: score descending, item ascending on ties. One warp per user, lane = candidate.
+template <int KC>
+__global__ void __launch_bounds__(256)
+predict_rescore_kernel(const float *__restrict__ P, const float *__restrict__ Q, const float *__restrict__ user_bias,
+                       const float *__restrict__ item_bias, float mu, int k, int users,
+                       const int32_t *__restrict__ cand_items, int topk, int32_t *out_items, float *out_scores) {
+    const int lane = threadIdx.x & 31;
+    const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (u >= users) return;
+    int item = lane < KC ? cand_items[(size_t)u * KC + lane] : -1;
+    float score = -INFINITY;
+    if (item >= 0) {
+        const float *pu = P + (size_t)u * k, *qi = Q + (size_t)item * k;
+        float pred = __fadd_rn(__fadd_rn(mu, __ldg(user_bias + u)), __ldg(item_bias + item));
+        for (int f = 0; f < k; ++f) pred = __fadd_rn(pred, __fmul_rn(__ldg(qi + f), __ldg(pu + f)));
+        score = pred;
+    }
+    int rank = 0;
+#pragma unroll
+    for (int o = 0; o < KC; ++o) {
+        const float so = __shfl_sync(0xffffffffu, score, o);
+        const int io = __shfl_sync(0xffffffffu, item, o);
+        if (io >= 0 && (so > score || (so == score && io < item))) ++rank;
+    }
+    if (item >= 0 && rank < topk) {
+        out_items[(size_t)u * topk + rank] = item;
+        out_scores[(size_t)u * topk + rank] = score;
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+cu2b_status make_row_major_map(EncodeTiledFn encode, CUtensorMap *map, const float *base, int rows, int k) {
+    const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)k * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)SLAB_K, (cuuint32_t)BM};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return cu2b_fail(CU2B_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return CU2B_OK;
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cu2b_status alloc(size_t bytes) {
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(bytes, 16));
+        if (e != cudaSuccess) return cu2b_fail(CU2B_ERR_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+        return CU2B_OK;
+    }
+    template <typename T> T *as() { return (T *)p; }
+};
+
+template <int KC>
+cu2b_status run_predict(const CUtensorMap &mp, const CUtensorMap &mq, const PredictParams &pp, int sm_count,
+                        const float *P, const float *Q, const float *ub, const float *ib, float mu, int k, int topk,
+                        int32_t *out_items, float *out_scores, float *ms_candidates, float *ms_rescore) {
+    const size_t smem = (size_t)3 * pp.kslabs * SLAB_BYTES + sizeof(PredictSmemCtl) + 1024;
+    CUDA_TRY(cudaFuncSetAttribute(predict_candidates_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEvent_t e0, e1, e2;
+    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+    const int grid = std::max(1, std::min(pp.n_user_tiles, sm_count));
+    cudaEventRecord(e0);
+    predict_candidates_kernel<KC><<<grid, kThreadsPredict, smem>>>(mp, mq, pp);
+    cudaEventRecord(e1);
+    const int warps_per_cta = 8;
+    predict_rescore_kernel<KC><<<(pp.users + warps_per_cta - 1) / warps_per_cta, 256>>>(
+        P, Q, ub, ib, mu, k, pp.users, pp.cand_items, topk, out_items, out_scores);
+    cudaEventRecord(e2);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess) {
+        cudaEventElapsedTime(ms_candidates, e0, e1);
+        cudaEventElapsedTime(ms_rescore, e1, e2);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    if (e != cudaSuccess) return cu2b_fail(CU2B_ERR_CUDA, "predict kernels: %s", cudaGetErrorString(e));
+    return CU2B_OK;
+}
+
+}  // namespace
+
+extern "C" cu2b_status cu2b_predict_topk(const float *P, int rows, const float *Q, int cols, const float *user_bias,
+                                         const float *item_bias, float global_bias, int n_factors,
+                                         const cu2b_csr *exclude, int topk, int32_t *out_items, float *out_scores,
+                                         double *ms_out) {
+    if (!P || !Q || !user_bias || !item_bias || !out_items || !out_scores || rows < 1 || cols < 1 || topk < 1)
+        return cu2b_fail(CU2B_ERR_INVALID, "cu2b_predict_topk: bad argument");
+    if (n_factors < 32 || n_factors > 128 || n_factors % 32)
+        return cu2b_fail(CU2B_ERR_UNSUPPORTED, "cu2b_predict_topk: n_factors must be 32, 64, 96 or 128 in this build (got %d)", n_factors);
+    if (topk > 24) return cu2b_fail(CU2B_ERR_UNSUPPORTED, "cu2b_predict_topk: topk <= 24 in this build (got %d)", topk);
+    if (exclude && (exclude->on_device || exclude->rows > rows || exclude->cols > cols))
+        return cu2b_fail(CU2B_ERR_INVALID, "cu2b_predict_topk: exclude matrix must be a host CSR within the model dimensions");
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) return cu2b_fail(CU2B_ERR_CUDA, "cu2b_predict_topk needs an sm_100 device (tcgen05)");
+    EncodeTiledFn encode = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void **)&encode, cudaEnableDefault, &qres));
+    if (!encode || qres != cudaDriverEntryPointSuccess) return cu2b_fail(CU2B_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+
+    const int k = n_factors;
+    const int kc = topk <= 10 ? 16 : 32;
+    DevBuf dP, dQ, dub, dib, dcand_i, dcand_s, dout_i, dout_s, dmask, dptr, dind;
+    cu2b_status rc;
+    if ((rc = dP.alloc((size_t)rows * k * 4)) || (rc = dQ.alloc((size_t)cols * k * 4)) || (rc = dub.alloc((size_t)rows * 4)) ||
+        (rc = dib.alloc((size_t)cols * 4)) || (rc = dcand_i.alloc((size_t)rows * kc * 4)) ||
+        (rc = dcand_s.alloc((size_t)rows * kc * 4)) || (rc = dout_i.alloc((size_t)rows * topk * 4)) ||
+        (rc = dout_s.alloc((size_t)rows * topk * 4)))
+        return rc;
+    CUDA_TRY(cudaMemcpy(dP.p, P, (size_t)rows * k * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(dQ.p, Q, (size_t)cols * k * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(dub.p, user_bias, (size_t)rows * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(dib.p, item_bias, (size_t)cols * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemset(dout_i.p, 0xFF, (size_t)rows * topk * 4));  // item -1 = "no such candidate"
+    {
+        std::vector<float> nanv((size_t)rows * topk, NAN);
+        CUDA_TRY(cudaMemcpy(dout_s.p, nanv.data(), nanv.size() * 4, cudaMemcpyHostToDevice));
+    }
+    PredictParams pp;
+    pp.users = rows;
+    pp.items = cols;
+    pp.kslabs = k / SLAB_K;
+    pp.n_user_tiles = (rows + BM - 1) / BM;
+    pp.n_item_tiles = (cols + BN - 1) / BN;
+    pp.item_bias = dib.as<float>();
+    pp.bitmap = nullptr;
+    pp.mask_pitch = pp.n_item_tiles * 4;
+    pp.cand_items = dcand_i.as<int32_t>();
+    pp.cand_scores = dcand_s.as<float>();
+    if (exclude && exclude->nonzeros > 0) {
+        if ((rc = dmask.alloc((size_t)rows * pp.mask_pitch * 4)) || (rc = dptr.alloc(((size_t)exclude->rows + 1) * 4)) ||
+            (rc = dind.alloc((size_t)exclude->nonzeros * 4)))
+            return rc;
+        CUDA_TRY(cudaMemset(dmask.p, 0, (size_t)rows * pp.mask_pitch * 4));
+        CUDA_TRY(cudaMemcpy(dptr.p, exclude->indptr, ((size_t)exclude->rows + 1) * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(dind.p, exclude->indices, (size_t)exclude->nonzeros * 4, cudaMemcpyHostToDevice));
+        const int grid = (int)std::min<long long>(((long long)exclude->nonzeros + 255) / 256, (long long)prop.multiProcessorCount * 16);
+        rated_bitmap_kernel<<<grid, 256>>>(dptr.as<int>(), dind.as<int>(), exclude->rows, exclude->nonzeros,
+                                          dmask.as<uint32_t>(), pp.mask_pitch);
+        CUDA_TRY(cudaGetLastError());
+        pp.bitmap = dmask.as<uint32_t>();
+    }
+    CUtensorMap mp, mq;
+    if ((rc = make_row_major_map(encode, &mp, dP.as<float>(), rows, k)) || (rc = make_row_major_map(encode, &mq, dQ.as<float>(), cols, k)))
+        return rc;
+    float ms_c = 0.f, ms_r = 0.f;
+    if (kc == 16)
+        rc = run_predict<16>(mp, mq, pp, prop.multiProcessorCount, dP.as<float>(), dQ.as<float>(), dub.as<float>(), dib.as<float>(),
+                             global_bias, k, topk, dout_i.as<int32_t>(), dout_s.as<float>(), &ms_c, &ms_r);
+    else
+        rc = run_predict<32>(mp, mq, pp, prop.multiProcessorCount, dP.as<float>(), dQ.as<float>(), dub.as<float>(), dib.as<float>(),
+                             global_bias, k, topk, dout_i.as<int32_t>(), dout_s.as<float>(), &ms_c, &ms_r);
+    if (rc != CU2B_OK) return rc;
+    CUDA_TRY(cudaMemcpy(out_items, dout_i.p, (size_t)rows * topk * 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(out_scores, dout_s.p, (size_t)rows * topk * 4, cudaMemcpyDeviceToHost));
+    if (ms_out) { ms_out[0] = ms_c; ms_out[1] = ms_r; }
+    return CU2B_OK;
+}

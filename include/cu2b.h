@@ -268,6 +268,20 @@ cu2b_session *cu2b_dsgd_session(cu2b_dsgd *d);
 cu2b_status cu2b_dsgd_local_sums(cu2b_dsgd *d, double out[4]);
 void cu2b_dsgd_destroy(cu2b_dsgd *d);
 
+/* ------------------------------------------------------------------------------------
+ * Batched predict + top-k (predict.cu:17-29 predict_ratings, :49-63 get_recommendations, for ALL
+ * users at once): for every user the topk items with the highest predicted rating
+ * mu + b_u + b_i + p_u.q_i among the items NOT present in `exclude` (may be NULL). Candidate
+ * generation runs on the tensor cores (tcgen05, TF32); the returned scores are exact fp32 in the
+ * reference's summation order and the order is (score descending, item ascending). Slots that
+ * cannot be filled hold item -1 / score NaN. n_factors in {32,64,96,128}, topk <= 24 in this
+ * build. ms_out (optional) receives {candidate kernel ms, rescore kernel ms}.
+ * ---------------------------------------------------------------------------------- */
+cu2b_status cu2b_predict_topk(const float *P, int rows, const float *Q, int cols, const float *user_bias,
+                              const float *item_bias, float global_bias, int n_factors,
+                              const cu2b_csr *exclude, int topk, int32_t *out_items, float *out_scores,
+                              double *ms_out);
+
 /* Device introspection used by bench / CLI ("Free memory: %ld", mf.cu:35-37). */
 cu2b_status cu2b_device_info(int device, char *name, int name_cap, int *sm_count,
                              int *cc_major, int *cc_minor, int64_t *free_bytes,

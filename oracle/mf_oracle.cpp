@@ -24,6 +24,7 @@
 //                        per lane so that several ratings share a warp).
 // Build with -ffp-contract=off so the compiler introduces no FMAs of its own.
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -462,6 +463,35 @@ void orc_block_schedule_order(const orc_triplet *coo, long n, int rows, int cols
     long w = 0;
     for (size_t b = 0; b < buckets.size(); ++b)
         for (long t : buckets[b]) order[w++] = t;
+}
+
+// ---------------------------------------------------------------------------------------
+// Batched predict. predict.cu:17-29 (score = mu + b_u + b_i + sum_f Q_i[f]*P_u[f], serial) and
+// predict.cu:49-63 (drop rated items, sort high to low) for every user; ties by ascending item.
+// ---------------------------------------------------------------------------------------
+void orc_predict_topk(int rows, int cols, int k, const float *P, const float *Q, const float *user_bias,
+                      const float *item_bias, float mu, const int *ex_indptr, const int *ex_indices, int ex_rows,
+                      int topk, int32_t *out_items, float *out_scores) {
+    std::vector<char> rated((size_t)cols);
+    std::vector<std::pair<float, int>> sc;
+    for (int u = 0; u < rows; ++u) {
+        std::fill(rated.begin(), rated.end(), 0);
+        if (ex_indptr && u < ex_rows)
+            for (int j = ex_indptr[u]; j < ex_indptr[u + 1]; ++j) rated[ex_indices[j]] = 1;
+        sc.clear();
+        for (int i = 0; i < cols; ++i) {
+            if (rated[i]) continue;
+            sc.push_back({orc_predict(P + (size_t)u * k, Q + (size_t)i * k, k, user_bias[u], item_bias[i], mu, ORC_FLAVOUR_REF), i});
+        }
+        const int take = (int)std::min<size_t>((size_t)topk, sc.size());
+        std::partial_sort(sc.begin(), sc.begin() + take, sc.end(), [](const std::pair<float, int> &a, const std::pair<float, int> &b) {
+            return a.first > b.first || (a.first == b.first && a.second < b.second);
+        });
+        for (int r = 0; r < topk; ++r) {
+            out_items[(size_t)u * topk + r] = r < take ? sc[r].second : -1;
+            out_scores[(size_t)u * topk + r] = r < take ? sc[r].first : NAN;
+        }
+    }
 }
 
 }  // extern "C"

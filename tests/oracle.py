@@ -171,3 +171,19 @@ def block_schedule_order(coo, rows, cols, B):
     order = np.empty(coo.shape[0], dtype=np.int64)
     lib().orc_block_schedule_order(_p(coo), C.c_long(coo.shape[0]), rows, cols, B, _p(order))
     return order
+
+
+def predict_topk(P, Q, ub, ib, mu, topk, exclude=None):
+    """exclude = (indptr, indices) or None -> (items [U, topk], scores [U, topk])."""
+    P, Q, ub, ib = (np.ascontiguousarray(x, np.float32) for x in (P, Q, ub, ib))
+    rows, cols = ub.shape[0], ib.shape[0]
+    k = P.size // rows
+    items = np.empty((rows, topk), dtype=np.int32)
+    scores = np.empty((rows, topk), dtype=np.float32)
+    if exclude is None:
+        lib().orc_predict_topk(rows, cols, k, _p(P), _p(Q), _p(ub), _p(ib), C.c_float(mu), None, None, 0, topk, _p(items), _p(scores))
+    else:
+        ip, ii = np.ascontiguousarray(exclude[0], np.int32), np.ascontiguousarray(exclude[1], np.int32)
+        lib().orc_predict_topk(rows, cols, k, _p(P), _p(Q), _p(ub), _p(ib), C.c_float(mu), _p(ip), _p(ii), ip.shape[0] - 1, topk,
+                               _p(items), _p(scores))
+    return items, scores
