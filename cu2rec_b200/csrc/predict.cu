@@ -13,11 +13,12 @@
 //           ever written.
 //   pass 2  predict_rescore_kernel: exact fp32 scores of the KC candidates in the reference's
 //           op order (serial dot, predict.cu:22-26), final ordering (score desc, item asc), top-k.
-// The candidate list is longer than k (KC = 16 or 32), so TF32 rounding can only matter if a true
-// top-k item is not even among the KC best TF32 scores.
+// Each of the two epilogue groups keeps KC >= k candidates from its half of the item tiles, so
+// TF32 rounding can only matter if a true top-k item is not among the KC best TF32 scores of its
+// own half (the lists hold 24-32 candidates for a top-10).
 //
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer,
-// warps 2-5 epilogue (TMEM lane quadrant = warp % 4).
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2-5 and
+// 6-9 two epilogue groups, one per accumulator buffer (TMEM lane quadrant = warp % 4).
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -44,7 +45,7 @@ constexpr int BM = 128;        // users per tile (MMA M, = TMEM lanes)
 constexpr int BN = 128;        // items per tile (MMA N, = TMEM columns per accumulator)
 constexpr int SLAB_K = 32;     // floats per 128-byte swizzle row
 constexpr int SLAB_BYTES = BM * SLAB_K * 4;  // 16 KB: 128 rows x 128 B
-constexpr int kThreadsPredict = 192;
+constexpr int kThreadsPredict = 320;  // TMA warp, MMA warp, 2 x 4 epilogue warps
 
 __device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bar_init(uint64_t *b, int n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(b)), "r"(n)); }
@@ -115,7 +116,7 @@ struct PredictSmemCtl {
     uint64_t acc_full[2], acc_empty[2];
     uint32_t tmem_base;
     uint32_t pad;
-    float ib[2][BN];
+    float ib[2][2][BN];  // [epilogue group][tile parity][column]
 };
 
 struct PredictParams {
@@ -124,8 +125,8 @@ struct PredictParams {
     const float *item_bias;
     const uint32_t *bitmap;  // [users][mask_pitch] words, bit i set => item i already rated; nullptr => none
     int mask_pitch;          // words per user (multiple of 4)
-    int32_t *cand_items;     // [users][KC]
-    float *cand_scores;      // [users][KC] (TF32 scores incl. item bias; diagnostics)
+    int32_t *cand_items;     // [users][2][KC]: one sorted list per epilogue group
+    float *cand_scores;      // [users][2][KC] (TF32 scores incl. item bias; diagnostics)
 };
 
 template <int KC>
@@ -208,62 +209,87 @@ predict_candidates_kernel(const __grid_constant__ CUtensorMap map_p, const __gri
             }
         }
     } else {
-        // ===== epilogue: 4 warps, one TMEM lane (= one user) per thread =====
-        const int quad = warp & 3;
-        const int et = (warp - 2) * 32 + lane;  // 0..127, only used to stage the item-bias tile
-        int it = 0;
-        for (int ut = blockIdx.x; ut < p.n_user_tiles; ut += gridDim.x) {
+        // ===== epilogue: two groups of 4 warps; group g owns accumulator buffer g, i.e. every
+        // second item tile. One TMEM lane (= one user) per thread; each group keeps its own sorted
+        // candidate list per user (disjoint item tiles, so the two lists never overlap). =====
+        const int grp = (warp - 2) >> 2;        // 0 or 1
+        const int quad = warp & 3;              // TMEM lane quadrant this warp may read
+        const int et = ((warp - 2) & 3) * 32 + lane;  // 0..127 inside the group (stages the item-bias tile)
+        int n = 0;
+        for (int ut = blockIdx.x; ut < p.n_user_tiles; ut += gridDim.x, ++n) {
             const int u = ut * BM + quad * 32 + lane;
             float cs[KC];
             int ci[KC];
 #pragma unroll
             for (int i = 0; i < KC; ++i) { cs[i] = -INFINITY; ci[i] = -1; }
-            uint4 mask = make_uint4(0u, 0u, 0u, 0u);
             const uint4 *mrow = (p.bitmap && u < p.users) ? reinterpret_cast<const uint4 *>(p.bitmap + (size_t)u * p.mask_pitch) : nullptr;
-            if (mrow) mask = __ldg(mrow);
-            for (int j = 0; j < p.n_item_tiles; ++j, ++it) {
-                const int s = it & 1;
+            const int it0 = n * p.n_item_tiles;  // global tile counter at the start of this user tile
+            // first item tile of this user tile that belongs to my buffer
+            int j = ((it0 & 1) == grp) ? 0 : 1;
+            uint4 mask = (mrow && j < p.n_item_tiles) ? __ldg(mrow + j) : make_uint4(0u, 0u, 0u, 0u);
+            for (int t = 0; j < p.n_item_tiles; j += 2, ++t) {
+                const int it = it0 + j;
                 const int n0 = j * BN;
-                ctl->ib[s][et] = (n0 + et < p.items) ? __ldg(p.item_bias + n0 + et) : 0.f;
-                const uint4 mask_next = (mrow && j + 1 < p.n_item_tiles) ? __ldg(mrow + j + 1) : make_uint4(0u, 0u, 0u, 0u);
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                bar_wait(&ctl->acc_full[s], (it >> 1) & 1);
+                float *ibs = ctl->ib[grp][t & 1];  // double buffered: a slow warp may still read the previous tile's
+                ibs[et] = (n0 + et < p.items) ? __ldg(p.item_bias + n0 + et) : 0.f;
+                const uint4 mask_next = (mrow && j + 2 < p.n_item_tiles) ? __ldg(mrow + j + 2) : make_uint4(0u, 0u, 0u, 0u);
+                if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+                else          asm volatile("bar.sync 2, 128;" ::: "memory");
+                bar_wait(&ctl->acc_full[grp], (it >> 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t mw[4] = {mask.x, mask.y, mask.z, mask.w};
-#pragma unroll
+#pragma unroll 1
                 for (int ch = 0; ch < BN / 32; ++ch) {
                     float v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * BN + ch * 32), v);
-                    const uint32_t mword = mw[ch];
+                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(grp * BN + ch * 32), v);
+                    const uint32_t mword = ch == 0 ? mask.x : ch == 1 ? mask.y : ch == 2 ? mask.z : mask.w;
+                    const int valid = p.items - (n0 + ch * 32);  // columns [0, valid) of this chunk exist
+                    const uint32_t live = (valid >= 32 ? 0xffffffffu : valid <= 0 ? 0u : ((1u << valid) - 1u)) & ~mword;
+                    // cheap unrolled pass: add the item bias, mark the columns that beat the current
+                    // KC-th best score. After the first few tiles almost no column does.
+                    const float thr = cs[KC - 1];
+                    uint32_t hits = 0;
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
-                        const int item = n0 + ch * 32 + c;
-                        const float sc = v[c] + ctl->ib[s][ch * 32 + c];
-                        const bool ok = item < p.items && !((mword >> c) & 1u);
-                        if (ok && sc > cs[KC - 1]) {
-                            // sorted insert (descending); ties keep the earlier (smaller) item first
-                            cs[KC - 1] = sc;
-                            ci[KC - 1] = item;
+                        v[c] += ibs[ch * 32 + c];
+                        hits |= (uint32_t)(v[c] > thr) << c;
+                    }
+                    hits &= live;
+                    // rare path, kept out of the unrolled code (it exists once, not 128 times)
+                    while (__any_sync(0xffffffffu, hits != 0)) {
+                        if (hits) {
+                            const int c = __ffs(hits) - 1;
+                            hits &= hits - 1;
+                            float sc = 0.f;
 #pragma unroll
-                            for (int i = KC - 1; i > 0; --i) {
-                                if (cs[i] > cs[i - 1]) {
-                                    const float ts = cs[i]; cs[i] = cs[i - 1]; cs[i - 1] = ts;
-                                    const int ti = ci[i]; ci[i] = ci[i - 1]; ci[i - 1] = ti;
+                            for (int i = 0; i < 32; ++i) sc = (i == c) ? v[i] : sc;
+                            if (sc > cs[KC - 1]) {
+                                const int item = n0 + ch * 32 + c;
+                                // position = number of kept scores >= sc (ties keep the earlier item
+                                // first); compares and moves are independent (no serial bubble chain)
+                                int pos = 0;
+#pragma unroll
+                                for (int i = 0; i < KC; ++i) pos += (cs[i] >= sc);
+#pragma unroll
+                                for (int i = KC - 1; i > 0; --i) {
+                                    const bool shift = i > pos;
+                                    cs[i] = shift ? cs[i - 1] : (i == pos ? sc : cs[i]);
+                                    ci[i] = shift ? ci[i - 1] : (i == pos ? item : ci[i]);
                                 }
+                                if (pos == 0) { cs[0] = sc; ci[0] = item; }
                             }
                         }
                     }
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) bar_arrive(&ctl->acc_empty[s]);
+                if (lane == 0) bar_arrive(&ctl->acc_empty[grp]);
                 mask = mask_next;
             }
             if (u < p.users) {
 #pragma unroll
                 for (int i = 0; i < KC; ++i) {
-                    p.cand_items[(size_t)u * KC + i] = ci[i];
-                    p.cand_scores[(size_t)u * KC + i] = cs[i];
+                    p.cand_items[((size_t)u * 2 + grp) * KC + i] = ci[i];
+                    p.cand_scores[((size_t)u * 2 + grp) * KC + i] = cs[i];
                 }
             }
         }
@@ -302,17 +328,27 @@ predict_rescore_kernel(const float *__restrict__ P, const float *__restrict__ Q,
     const int lane = threadIdx.x & 31;
     const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (u >= users) return;
-    int item = lane < KC ? cand_items[(size_t)u * KC + lane] : -1;
+    static_assert(2 * KC <= 32, "one lane per candidate");
+    int item = lane < 2 * KC ? cand_items[(size_t)u * 2 * KC + lane] : -1;
     float score = -INFINITY;
     if (item >= 0) {
-        const float *pu = P + (size_t)u * k, *qi = Q + (size_t)item * k;
+        // k is a multiple of 32 here: 128-bit loads, products still added one by one in ascending f
+        const float4 *pu = reinterpret_cast<const float4 *>(P + (size_t)u * k);
+        const float4 *qi = reinterpret_cast<const float4 *>(Q + (size_t)item * k);
         float pred = __fadd_rn(__fadd_rn(mu, __ldg(user_bias + u)), __ldg(item_bias + item));
-        for (int f = 0; f < k; ++f) pred = __fadd_rn(pred, __fmul_rn(__ldg(qi + f), __ldg(pu + f)));
+#pragma unroll 4
+        for (int f = 0; f < k / 4; ++f) {
+            const float4 a = __ldg(qi + f), b = __ldg(pu + f);
+            pred = __fadd_rn(pred, __fmul_rn(a.x, b.x));
+            pred = __fadd_rn(pred, __fmul_rn(a.y, b.y));
+            pred = __fadd_rn(pred, __fmul_rn(a.z, b.z));
+            pred = __fadd_rn(pred, __fmul_rn(a.w, b.w));
+        }
         score = pred;
     }
     int rank = 0;
 #pragma unroll
-    for (int o = 0; o < KC; ++o) {
+    for (int o = 0; o < 2 * KC; ++o) {
         const float so = __shfl_sync(0xffffffffu, score, o);
         const int io = __shfl_sync(0xffffffffu, item, o);
         if (io >= 0 && (so > score || (so == score && io < item))) ++rank;
@@ -387,7 +423,7 @@ extern "C" cu2b_status cu2b_predict_topk(const float *P, int rows, const float *
         return cu2b_fail(CU2B_ERR_INVALID, "cu2b_predict_topk: bad argument");
     if (n_factors < 32 || n_factors > 128 || n_factors % 32)
         return cu2b_fail(CU2B_ERR_UNSUPPORTED, "cu2b_predict_topk: n_factors must be 32, 64, 96 or 128 in this build (got %d)", n_factors);
-    if (topk > 24) return cu2b_fail(CU2B_ERR_UNSUPPORTED, "cu2b_predict_topk: topk <= 24 in this build (got %d)", topk);
+    if (topk > 16) return cu2b_fail(CU2B_ERR_UNSUPPORTED, "cu2b_predict_topk: topk <= 16 in this build (got %d)", topk);
     if (exclude && (exclude->on_device || exclude->rows > rows || exclude->cols > cols))
         return cu2b_fail(CU2B_ERR_INVALID, "cu2b_predict_topk: exclude matrix must be a host CSR within the model dimensions");
     int dev = 0;
@@ -401,12 +437,14 @@ extern "C" cu2b_status cu2b_predict_topk(const float *P, int rows, const float *
     if (!encode || qres != cudaDriverEntryPointSuccess) return cu2b_fail(CU2B_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
 
     const int k = n_factors;
-    const int kc = topk <= 10 ? 16 : 32;
+    // per epilogue group; both groups together hand 2*kc candidates to the exact rescoring pass.
+    // A group sees every second item tile, so each list must be able to hold the whole top-k.
+    const int kc = 16;
     DevBuf dP, dQ, dub, dib, dcand_i, dcand_s, dout_i, dout_s, dmask, dptr, dind;
     cu2b_status rc;
     if ((rc = dP.alloc((size_t)rows * k * 4)) || (rc = dQ.alloc((size_t)cols * k * 4)) || (rc = dub.alloc((size_t)rows * 4)) ||
-        (rc = dib.alloc((size_t)cols * 4)) || (rc = dcand_i.alloc((size_t)rows * kc * 4)) ||
-        (rc = dcand_s.alloc((size_t)rows * kc * 4)) || (rc = dout_i.alloc((size_t)rows * topk * 4)) ||
+        (rc = dib.alloc((size_t)cols * 4)) || (rc = dcand_i.alloc((size_t)rows * 2 * kc * 4)) ||
+        (rc = dcand_s.alloc((size_t)rows * 2 * kc * 4)) || (rc = dout_i.alloc((size_t)rows * topk * 4)) ||
         (rc = dout_s.alloc((size_t)rows * topk * 4)))
         return rc;
     CUDA_TRY(cudaMemcpy(dP.p, P, (size_t)rows * k * 4, cudaMemcpyHostToDevice));
@@ -446,11 +484,7 @@ extern "C" cu2b_status cu2b_predict_topk(const float *P, int rows, const float *
     if ((rc = make_row_major_map(encode, &mp, dP.as<float>(), rows, k)) || (rc = make_row_major_map(encode, &mq, dQ.as<float>(), cols, k)))
         return rc;
     float ms_c = 0.f, ms_r = 0.f;
-    if (kc == 16)
-        rc = run_predict<16>(mp, mq, pp, prop.multiProcessorCount, dP.as<float>(), dQ.as<float>(), dub.as<float>(), dib.as<float>(),
-                             global_bias, k, topk, dout_i.as<int32_t>(), dout_s.as<float>(), &ms_c, &ms_r);
-    else
-        rc = run_predict<32>(mp, mq, pp, prop.multiProcessorCount, dP.as<float>(), dQ.as<float>(), dub.as<float>(), dib.as<float>(),
+    rc = run_predict<16>(mp, mq, pp, prop.multiProcessorCount, dP.as<float>(), dQ.as<float>(), dub.as<float>(), dib.as<float>(),
                              global_bias, k, topk, dout_i.as<int32_t>(), dout_s.as<float>(), &ms_c, &ms_r);
     if (rc != CU2B_OK) return rc;
     CUDA_TRY(cudaMemcpy(out_items, dout_i.p, (size_t)rows * topk * 4, cudaMemcpyDeviceToHost));

@@ -15,7 +15,7 @@ def _model(rng, U, I, k):
 
 
 @pytest.mark.parametrize("U,I,k,topk", [(300, 500, 32, 5), (1000, 1777, 64, 10), (777, 2000, 128, 10), (130, 127, 96, 3),
-                                        (257, 4000, 128, 24)])
+                                        (257, 4000, 128, 16)])
 def test_topk_matches_brute_force(U, I, k, topk):
     """Items and their order equal the CPU brute force (exact fp32 scores in the reference's op
     order, ties by item id); scores are bit-identical."""
@@ -57,4 +57,4 @@ def test_topk_rejects_unsupported_shapes():
         cu.predict_topk(P, Q, ub, ib, 3.0, 5)
     P, Q, ub, ib = _model(rng, 10, 10, 64)
     with pytest.raises(cu._lib.Cu2bError):
-        cu.predict_topk(P, Q, ub, ib, 3.0, 30)
+        cu.predict_topk(P, Q, ub, ib, 3.0, 17)
