@@ -260,7 +260,8 @@ def run_reference_arm(args):
 def config_dict(args, k):
     U, I, R, _, _ = WORKLOADS[args.workload]
     return {"workload": "%s-shape synthetic low-rank+noise (%d users x %d items x ~%d ratings, 90/10 split), k=%d, "
-                        "hogwild, per_user sampler (one sampled rating per user per iteration)" % (args.workload, U, I, R, k),
+                        "hogwild, per_user sampler (one sampled rating per user per iteration), iteration-tiled "
+                        "schedule (16 iterations per user tile)" % (args.workload, U, I, R, k),
             "n_factors": k, "iters_per_step": args.iters_per_step, "updates_per_step": args.iters_per_step * U,
             "step": "T reference iterations + one train/test loss check (training.cu:118)",
             "l2": "inputs larger than L2 (P %d MB + rating/update streams >> 126 MB)" % (U * k * 4 >> 20),
@@ -280,12 +281,12 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def traffic_from_profiles(k):
+def traffic_from_profiles(kernel, k):
     """DRAM bytes per update of the SGD kernel from the committed ncu --set full capture."""
     p = os.path.join(ROOT, "profiles", "sgd_traffic.json")
     if os.path.exists(p):
         try:
-            return float(json.load(open(p))[str(k)]["bytes_per_update"])
+            return float(json.load(open(p))[kernel][str(k)]["bytes_per_update"])
         except Exception:
             return None
     return None
@@ -334,8 +335,9 @@ def run_ours(args):
     sgd_gbs = updates * bytes_per_update / (st["sgd_ms"] / 1e3) / 1e9
     peak, peak_src = peaks()
     launches = max(1, int(st["sgd_launches"]))
-    bpu = traffic_from_profiles(k)
-    roofline = {"bound": "hbm", "kernel": "mf_sgd_hogwild", "achieved": sgd_gbs, "peak": peak, "unit": "GB/s",
+    kernel_name = "mf_sgd_user_tiles" if cfg.round_iters > 1 else "mf_sgd_hogwild"
+    bpu = traffic_from_profiles(kernel_name, k)
+    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": sgd_gbs, "peak": peak, "unit": "GB/s",
                 "frac": sgd_gbs / peak, "peak_source": peak_src,
                 # per launch, like `achieved`: ncu dram__bytes_read+write per update x updates per launch
                 "traffic": None if bpu is None else bpu * updates / launches,
@@ -346,6 +348,23 @@ def run_ours(args):
                 "kernel_updates_per_s": updates / (st["sgd_ms"] / 1e3),
                 "note": "Q (9 MB at k=128) stays in L2, so about half of the algorithmic bytes never reach "
                         "HBM; frac > 1 of the copy peak is possible, traffic is the physical DRAM volume"}
+
+    # ---- the reference's iteration-synchronous order (round_iters = 1), for comparison ----------
+    variants = {}
+    if not args.no_variants:
+        cfg1 = cu.Config(total_iterations=(2 + args.warmup) * T, n_factors=k, check_error=T, round_iters=1)
+        with cu.Session(mtr, mte, cfg1, P0, Q0, ub0, ib0, mu) as s1:
+            for _ in range(args.warmup):
+                s1.run(T)
+            s1.stats(reset=True)
+            s1.run(T)
+            s1.run(T)
+            st1, lg1 = s1.stats(), s1.log()
+        variants["iteration_synchronous_round1"] = {
+            "kernel": "mf_sgd_hogwild (TMA triplet stream, warp per rating, per-user ordering gate)",
+            "value": st1["updates"] / (st1["total_ms"] / 1e3), "kernel_updates_per_s": st1["updates"] / (st1["sgd_ms"] / 1e3),
+            "algorithmic_gbs": st1["updates"] * bytes_per_update / (st1["sgd_ms"] / 1e3) / 1e9,
+            "test_rmse": [round(r["test_rmse"], 5) for r in lg1]}
 
     # ---- end to end through the C ABI with pinned host buffers --------------------------------
     hp = {n: pin(getattr(mtr, n)) for n in ("indptr", "indices", "data")}
@@ -393,7 +412,7 @@ def run_ours(args):
         "breakdown_ms_per_step": {"sgd": st["sgd_ms"] / args.steps, "sampler": st["sampler_ms"] / args.steps,
                                   "loss_check": st["loss_ms"] / args.steps},
         "test_rmse": [round(r["test_rmse"], 5) for r in lg], "e2e_test_rmse": e2e_rmse,
-        "epochs_per_step": T * U / float(mtr.nonzeros),
+        "epochs_per_step": T * U / float(mtr.nonzeros), "variants": variants,
     }
     print(json.dumps(line), flush=True)
     return 0
@@ -553,6 +572,7 @@ def main():
     ap.add_argument("--iters-per-step", type=int, default=500)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-variants", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         log("[bench] note: fewer than 3 warm-up steps requested")

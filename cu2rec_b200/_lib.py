@@ -20,7 +20,7 @@ class Config(C.Structure):  # cu2b_config
         ("P_reg", C.c_float), ("Q_reg", C.c_float), ("user_bias_reg", C.c_float), ("item_bias_reg", C.c_float),
         ("is_train", C.c_int), ("n_threads", C.c_int), ("check_error", C.c_int),
         ("patience", C.c_float), ("learning_rate_decay", C.c_float),
-        ("mode", C.c_int), ("sampler", C.c_int), ("n_blocks", C.c_int), ("n_gpus", C.c_int),
+        ("mode", C.c_int), ("sampler", C.c_int), ("n_blocks", C.c_int), ("n_gpus", C.c_int), ("round_iters", C.c_int),
     ]
 
 

@@ -29,6 +29,7 @@
 #include "dsgd_kernels.cuh"
 #include "loss_kernels.cuh"
 #include "sgd_kernels.cuh"
+#include "tiled_kernels.cuh"
 
 using namespace cu2b;
 
@@ -210,6 +211,7 @@ typedef void (*SgdKernel)(const SgdParams);
 typedef void (*LossKernel)(const LossParams);
 typedef void (*BlockedKernel)(const BlockedParams);
 typedef void (*UserRunKernel)(const UserRunParams);
+typedef void (*UserTileKernel)(const UserTileParams);
 
 cu2b_status layout_for(int kp, int *L, int *V) {
     const int vecs = kp / 4;
@@ -314,6 +316,23 @@ UserRunKernel pick_user_runs(int L, int V) {
                 case 2: return mf_sgd_user_runs<32, 2>;
                 case 3: return mf_sgd_user_runs<32, 3>;
                 default: return mf_sgd_user_runs<32, 4>;
+            }
+    }
+}
+
+UserTileKernel pick_user_tiles(int L, int V) {
+    switch (L) {
+        case 1: return mf_sgd_user_tiles<1, 1>;
+        case 2: return mf_sgd_user_tiles<2, 1>;
+        case 4: return mf_sgd_user_tiles<4, 1>;
+        case 8: return mf_sgd_user_tiles<8, 1>;
+        case 16: return mf_sgd_user_tiles<16, 1>;
+        default:
+            switch (V) {
+                case 1: return mf_sgd_user_tiles<32, 1>;
+                case 2: return mf_sgd_user_tiles<32, 2>;
+                case 3: return mf_sgd_user_tiles<32, 3>;
+                default: return mf_sgd_user_tiles<32, 4>;
             }
     }
 }
@@ -484,6 +503,13 @@ struct cu2b_session {
     int *bucket_ptr = nullptr;
     int B = 0;
     long long blocked_budget = 0;
+    bool dsgd_child = false;  // created by cu2b_dsgd_create: no single-GPU update stream
+    double hot_share = 0.0;   // hottest item's share of the draws (asynchronous-SGD stability bound)
+    // iteration-tiled schedule (cfg.round_iters > 1)
+    DsgdDraw *draws = nullptr;
+    int *draw_row_off = nullptr, *one_block_ptr = nullptr;
+    int draw_pitch = 0, round_iters = 1, tiles_grid = 0;
+    UserTileKernel tiles_kernel = nullptr;
     // experiment switches (environment): CU2B_TUNE_GATE=0 drops the per-user ordering gate,
     // CU2B_TUNE_CHUNK overrides the chunk size
     bool no_gate = false;
@@ -611,8 +637,60 @@ cu2b_status enqueue_blocked_iterations(cu2b_session *s, int n_seg) {
     return CU2B_OK;
 }
 
+// Iteration-tiled schedule: rounds of up to round_iters iterations, users processed in tiles.
+cu2b_status enqueue_tiled_iterations(cu2b_session *s, int iter_abs, int n_seg) {
+    constexpr int kTU_warps = kConsumerWarps;
+    const int TU = kTU_warps * (32 / s->L);
+    while (n_seg > 0) {
+        const int nb = std::min(n_seg, s->round_iters);
+        {
+            const int id = s->timing.begin(Timing::SAMPLER, s->stream);
+            const int grid = std::max(1, std::min((s->n_active + 7) / 8, s->sm_count * 8));
+            dsgd_sample_runs_kernel<<<grid, 256, 0, s->stream>>>(s->train.indptr, s->train.coo, s->active, s->user_ids,
+                                                                s->n_active, (uint32_t)s->cfg.seed, iter_abs, nb,
+                                                                s->draw_pitch, s->one_block_ptr, 1, s->draws,
+                                                                s->draw_row_off);
+            CUDA_TRY(cudaGetLastError());
+            s->stats.kernel_launches++;
+            s->timing.end(id, s->stream);
+        }
+        {
+            const int id = s->timing.begin(Timing::SGD, s->stream);
+            UserTileParams tp;
+            tp.draws = s->draws;
+            tp.active_users = s->active;
+            tp.n_active = s->n_active;
+            tp.pitch = s->draw_pitch;
+            tp.nb = nb;
+            tp.n_tiles = (s->n_active + TU - 1) / TU;
+            if (s->counter_next == 0)
+                CUDA_TRY(cudaMemsetAsync(s->counters, 0, sizeof(unsigned long long) * s->counter_slots, s->stream));
+            tp.tile_counter = s->counters + s->counter_next;
+            s->counter_next = (s->counter_next + 1) % s->counter_slots;
+            tp.P = s->P; tp.Q = s->Q; tp.user_bias = s->ub; tp.item_bias = s->ib;
+            tp.kp = s->kp;
+            tp.mu = s->mu;
+            tp.lr = &s->state->lr;
+            tp.P_reg = s->cfg.P_reg; tp.Q_reg = s->cfg.Q_reg;
+            tp.ub_reg = s->cfg.user_bias_reg; tp.ib_reg = s->cfg.item_bias_reg;
+            tp.is_train = s->cfg.is_train;
+            const int grid = std::max(1, std::min(tp.n_tiles, s->tiles_grid));
+            s->tiles_kernel<<<grid, kThreads, 0, s->stream>>>(tp);
+            CUDA_TRY(cudaGetLastError());
+            s->stats.kernel_launches++;
+            s->stats.sgd_launches++;
+            s->timing.end(id, s->stream);
+        }
+        s->stats.updates += (long long)nb * s->n_active;
+        iter_abs += nb;
+        n_seg -= nb;
+    }
+    return CU2B_OK;
+}
+
 // n_seg reference iterations starting at absolute iteration `iter_abs`
 cu2b_status enqueue_sgd_iterations(cu2b_session *s, int iter_abs, int n_seg) {
+    if (s->round_iters > 1) return enqueue_tiled_iterations(s, iter_abs, n_seg);
     while (n_seg > 0) {
         const int nb = std::min(n_seg, s->max_batch_segs);
         // 1. sampler: one draw per active user per iteration (sgd.cu:27-37)
@@ -725,7 +803,8 @@ static cu2b_status session_create_impl(cu2b_session **out, int device, const cu2
     {
         // ratings in flight per CTA: 8 consumer warps x (32/L) groups x unroll (2 for L < 32)
         const int per_cta = kConsumerWarps * (32 / s->L) * (s->L < 32 ? 2 : 1);
-        const int cap = inflight_cap(hot_item_share(train, nullptr, 1), cfg->learning_rate, 0.5);
+        s->hot_share = hot_item_share(train, nullptr, 1);
+        const int cap = inflight_cap(s->hot_share, cfg->learning_rate, 0.5);
         s->sgd_grid_max = std::max(1, std::min(s->sgd_grid_max, cap / per_cta));
     }
 
@@ -738,7 +817,32 @@ static cu2b_status session_create_impl(cu2b_session **out, int device, const cu2
     s->chunks_per_seg = std::max(1, (s->n_active + s->chunk - 1) / s->chunk);
     const long long cap_ratings = 48LL << 20;  // <= 576 MB of triplets per batch
     s->max_batch_segs = (int)std::max<long long>(1, std::min<long long>(cap_ratings / std::max<long long>(1, s->seg_pitch), 4096));
-    if (alloc_stream) {
+    s->round_iters = 1;
+    s->dsgd_child = !alloc_stream;
+    if (alloc_stream && cfg->mode == CU2B_MODE_HOGWILD && cfg->round_iters > 1) {
+        const int TU = kConsumerWarps * (32 / s->L);
+        int r = std::min(cfg->round_iters, kTileDrawsMax / TU);
+        if (const char *e = getenv("CU2B_ROUND")) r = std::min(std::max(1, atoi(e)), kTileDrawsMax / TU);
+        s->round_iters = std::max(1, r);
+    }
+    if (s->round_iters > 1) {
+        const int TU = kConsumerWarps * (32 / s->L);
+        s->draw_pitch = std::min((s->round_iters + 3) & ~3, kTileDrawsMax / TU);
+        s->round_iters = std::min(s->round_iters, s->draw_pitch);
+        CU2B_TRY(s->pool.alloc(&s->draws, (size_t)std::max(1, s->n_active) * s->draw_pitch + kTileDrawsMax));
+        CU2B_TRY(s->pool.alloc(&s->draw_row_off, (size_t)std::max(1, s->n_active) * 2));
+        CU2B_TRY(s->pool.alloc(&s->one_block_ptr, (size_t)2));
+        const int ptr2[2] = {0, s->cols};
+        CUDA_TRY(cudaMemcpyAsync(s->one_block_ptr, ptr2, sizeof(ptr2), cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        s->tiles_kernel = pick_user_tiles(s->L, s->V);
+        int occ_t = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, s->tiles_kernel, kThreads, 0));
+        const int per_cta = kConsumerWarps * (32 / s->L);
+        const int cap = inflight_cap(s->hot_share, cfg->learning_rate, 0.5);
+        s->tiles_grid = std::max(1, std::min(std::max(1, occ_t) * s->sm_count, cap / per_cta));
+    }
+    if (alloc_stream && s->round_iters == 1) {
         CU2B_TRY(s->pool.alloc(&s->stream_buf, (size_t)s->max_batch_segs * s->seg_pitch + kChunkMax + 4));
         CU2B_TRY(s->pool.alloc(&s->gate, (size_t)s->chunks_per_seg));
         CUDA_TRY(cudaMemsetAsync(s->gate, 0, (size_t)s->chunks_per_seg * sizeof(int), s->stream));
@@ -794,8 +898,7 @@ extern "C" cu2b_status cu2b_session_create(cu2b_session **out, int device, const
 
 extern "C" cu2b_status cu2b_session_run(cu2b_session *s, int n_iterations) {
     if (!s || n_iterations < 0) return cu2b_fail(CU2B_ERR_INVALID, "cu2b_session_run: bad argument");
-    if (!s->stream_buf && s->cfg.mode == CU2B_MODE_HOGWILD && s->n_active > 0)
-        return cu2b_fail(CU2B_ERR_INVALID, "this session belongs to a DSGD context; use cu2b_dsgd_run");
+    if (s->dsgd_child) return cu2b_fail(CU2B_ERR_INVALID, "this session belongs to a DSGD context; use cu2b_dsgd_run");
     CUDA_TRY(cudaSetDevice(s->device));
     const int total = s->cfg.total_iterations, ce = s->cfg.check_error;
     auto is_check = [&](int i) {  // training.cu:118

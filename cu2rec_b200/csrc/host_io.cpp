@@ -58,6 +58,7 @@ extern "C" void cu2b_config_default(cu2b_config *c) {
     c->sampler = CU2B_SAMPLER_PER_USER;
     c->n_blocks = 0;
     c->n_gpus = 1;
+    c->round_iters = 16;
 }
 
 namespace {
@@ -121,6 +122,7 @@ extern "C" cu2b_status cu2b_config_read(const char *path, cu2b_config *c) {
     r.get(&c->sampler);
     r.get(&c->n_blocks);
     r.get(&c->n_gpus);
+    r.get(&c->round_iters);
     fclose(f);
     return CU2B_OK;
 }

@@ -71,12 +71,15 @@ typedef struct cu2b_config {
                      pass over the rating list */
     int n_blocks; /* deterministic mode: B of the BxB block grid, 0 = automatic */
     int n_gpus;   /* DSGD width, 0/1 = single GPU */
+    int round_iters; /* Hogwild schedule on one GPU: this many consecutive iterations of a user are
+                        applied back to back with the user's row kept in registers (default 16;
+                        1 = the reference's iteration-synchronous order) */
 } cu2b_config;
 
 void cu2b_config_default(cu2b_config *cfg);
 /* config.cu:7-13: nine whitespace separated positional tokens; a short file keeps defaults.
  * Optional tokens 10.. (n_threads patience learning_rate_decay check_error mode sampler
- * n_blocks n_gpus) are an add-only extension (config.h TODO / create_config.py:16-17). */
+ * n_blocks n_gpus round_iters) are an add-only extension (config.h TODO / create_config.py:16-17). */
 cu2b_status cu2b_config_read(const char *path, cu2b_config *cfg);
 /* config.cu:15-22: writes the nine reference tokens on one line. */
 cu2b_status cu2b_config_write(const char *path, const cu2b_config *cfg);

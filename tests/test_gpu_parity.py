@@ -322,15 +322,17 @@ def _small_problem(U=1500, I=400, n=60000, seed=11):
     return tr, te, cu.createSparseMatrix(tr, U, I), cu.createSparseMatrix(te, U, I), np.float32(tr["rating"].astype(np.float64).mean())
 
 
-@pytest.mark.parametrize("k", [8, 32, 50])
-def test_training_rmse_parity_vs_oracle_trainer(k):
+@pytest.mark.parametrize("k,round_iters", [(8, 1), (32, 1), (50, 1), (8, 16), (32, 16), (50, 16), (128, 16), (32, 64)])
+def test_training_rmse_parity_vs_oracle_trainer(k, round_iters):
     """Hogwild GPU training vs the sequential CPU restatement (pinned to the compiled mf_cpu in
     tests/test_oracle_pins.py) at equal iterations, same sampler stream, same init: final and
     TEST RMSE within 0.5 %, every intermediate check within 1.5 %."""
     tr, te, mtr, mte, mu = _small_problem()
     U, I = mtr.rows, mtr.cols
     iters, ce = 300, 100
-    cfg = cu.Config(total_iterations=iters, n_factors=k, check_error=ce)
+    # round_iters = 1: the reference's iteration-synchronous order (mf_sgd_hogwild + ordering gate);
+    # > 1: the iteration-tiled schedule (mf_sgd_user_tiles), same draws, different interleaving
+    cfg = cu.Config(total_iterations=iters, n_factors=k, check_error=ce, round_iters=round_iters)
     out = cu.train(mtr, mte, cfg, mu)
     init = lambda n: O.init_normal(n, k)
     *_, olog = O.train((mtr.indptr, mtr.indices, mtr.data), (mte.indptr, mte.indices, mte.data), init(U * k), init(I * k),
@@ -369,12 +371,13 @@ def test_training_schedule_on_device_follows_reference_rule():
     assert cfg.learning_rate == out["log"][-1]["learning_rate"] and cfg.cur_iterations == 200
 
 
-def test_session_resume_equals_single_run():
+@pytest.mark.parametrize("round_iters", [1, 16])
+def test_session_resume_equals_single_run(round_iters):
     tr, te, mtr, mte, mu = _small_problem(U=500, I=150, n=15000)
     U, I, k = mtr.rows, mtr.cols, 16
     init = lambda n: cu.initialize_normal_array(n, k)
     P, Q, ub, ib = init(U * k), init(I * k), init(U), init(I)
-    cfg = cu.Config(total_iterations=40, n_factors=k, check_error=10)
+    cfg = cu.Config(total_iterations=40, n_factors=k, check_error=10, round_iters=round_iters)
     with cu.Session(mtr, mte, cfg, P, Q, ub, ib, mu) as s:
         s.run(40)
         log_a, ev_a = s.log(), s.eval()
@@ -468,13 +471,18 @@ def test_full_size_properties_ml20m_shape():
     assert abs((mae_a * na + mae_b * nb) / (na + nb) - mae) / mae < 1e-6
     assert abs(np.sqrt((rmse_a ** 2 * na + rmse_b ** 2 * nb) / (na + nb)) - rmse) / rmse < 1e-6
     assert (mae, rmse) == cu.loss(P, Q, k, mtr, ub, ib, mu)
-    # (3) training: loss goes down, model stays finite, update count is iterations x users
-    cfg = cu.Config(total_iterations=300, n_factors=k, check_error=100)
-    out = cu.train(mtr, mte, cfg, mu)
-    rm = [r["test_rmse"] for r in out["log"]]
-    assert rm[-1] < rm[0] and np.isfinite(rm).all()
-    assert out["stats"]["updates"] == 300 * U
-    assert np.all(np.isfinite(out["P"])) and np.all(np.isfinite(out["Q"]))
+    # (3) training: loss goes down, model stays finite, update count is iterations x users; the
+    #     tiled schedule lands within 0.5 % of the iteration-synchronous one at equal iterations
+    finals = {}
+    for r_it in (1, 16):
+        cfg = cu.Config(total_iterations=300, n_factors=k, check_error=100, round_iters=r_it)
+        out = cu.train(mtr, mte, cfg, mu)
+        rm = [r["test_rmse"] for r in out["log"]]
+        assert rm[-1] < rm[0] and np.isfinite(rm).all()
+        assert out["stats"]["updates"] == 300 * U
+        assert np.all(np.isfinite(out["P"])) and np.all(np.isfinite(out["Q"]))
+        finals[r_it] = rm[-1]
+    assert abs(finals[16] - finals[1]) / finals[1] < 0.005
 
 
 # ---------------------------------------------------------------------------------------------

@@ -148,10 +148,11 @@ def test_config_goldens_and_round_trip(tmp_path, golden_dir, fixtures_dir, ref_t
     c4 = cu.Config()
     c4.read_config(tmp_path / "short.cfg")
     assert (c4.total_iterations, c4.n_factors, c4.learning_rate) == (77, 12, np.float32(0.01))
-    (tmp_path / "ext.cfg").write_text("0 10 8 0.05 7 0.1 0.2 0.3 0.4 64 3 0.5 25 1 1 16 2")
+    (tmp_path / "ext.cfg").write_text("0 10 8 0.05 7 0.1 0.2 0.3 0.4 64 3 0.5 25 1 1 16 2 4")
     c5 = cu.Config()
     c5.read_config(tmp_path / "ext.cfg")
     assert (c5.n_threads, c5.patience, c5.check_error, c5.mode, c5.sampler, c5.n_blocks, c5.n_gpus) == (64, 3.0, 25, 1, 1, 16, 2)
+    assert c5.round_iters == 4 and cu.Config().round_iters == 16
     with pytest.raises(cu._lib.Cu2bError):
         cu.Config().read_config(tmp_path / "missing.cfg")
 
