@@ -507,7 +507,6 @@ struct cu2b_session {
     double hot_share = 0.0;   // hottest item's share of the draws (asynchronous-SGD stability bound)
     // iteration-tiled schedule (cfg.round_iters > 1)
     DsgdDraw *draws = nullptr;
-    int *draw_row_off = nullptr, *one_block_ptr = nullptr;
     int draw_pitch = 0, round_iters = 1, tiles_grid = 0;
     UserTileKernel tiles_kernel = nullptr;
     // experiment switches (environment): CU2B_TUNE_GATE=0 drops the per-user ordering gate,
@@ -645,11 +644,11 @@ cu2b_status enqueue_tiled_iterations(cu2b_session *s, int iter_abs, int n_seg) {
         const int nb = std::min(n_seg, s->round_iters);
         {
             const int id = s->timing.begin(Timing::SAMPLER, s->stream);
-            const int grid = std::max(1, std::min((s->n_active + 7) / 8, s->sm_count * 8));
-            dsgd_sample_runs_kernel<<<grid, 256, 0, s->stream>>>(s->train.indptr, s->train.coo, s->active, s->user_ids,
-                                                                s->n_active, (uint32_t)s->cfg.seed, iter_abs, nb,
-                                                                s->draw_pitch, s->one_block_ptr, 1, s->draws,
-                                                                s->draw_row_off);
+            const long long draws = (long long)nb * s->n_active;
+            const int grid = (int)std::max<long long>(1, std::min<long long>((draws + 255) / 256, (long long)s->sm_count * 16));
+            sample_user_major_kernel<<<grid, 256, 0, s->stream>>>(s->train.indptr, s->train.coo, s->active, s->user_ids,
+                                                                 s->n_active, (uint32_t)s->cfg.seed, iter_abs, nb,
+                                                                 s->draw_pitch, s->draws);
             CUDA_TRY(cudaGetLastError());
             s->stats.kernel_launches++;
             s->timing.end(id, s->stream);
@@ -830,11 +829,6 @@ static cu2b_status session_create_impl(cu2b_session **out, int device, const cu2
         s->draw_pitch = std::min((s->round_iters + 3) & ~3, kTileDrawsMax / TU);
         s->round_iters = std::min(s->round_iters, s->draw_pitch);
         CU2B_TRY(s->pool.alloc(&s->draws, (size_t)std::max(1, s->n_active) * s->draw_pitch + kTileDrawsMax));
-        CU2B_TRY(s->pool.alloc(&s->draw_row_off, (size_t)std::max(1, s->n_active) * 2));
-        CU2B_TRY(s->pool.alloc(&s->one_block_ptr, (size_t)2));
-        const int ptr2[2] = {0, s->cols};
-        CUDA_TRY(cudaMemcpyAsync(s->one_block_ptr, ptr2, sizeof(ptr2), cudaMemcpyHostToDevice, s->stream));
-        CUDA_TRY(cudaStreamSynchronize(s->stream));
         s->tiles_kernel = pick_user_tiles(s->L, s->V);
         int occ_t = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, s->tiles_kernel, kThreads, 0));

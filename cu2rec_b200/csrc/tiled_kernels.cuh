@@ -41,6 +41,27 @@ struct UserTileParams {
     int is_train;
 };
 
+// Sampler of one round for the tiled schedule: thread i draws rating (user a = i / nb, iteration
+// t = i % nb) -- same Philox counter as sample_per_user_kernel -- and stores it user-major.
+__global__ void __launch_bounds__(256)
+sample_user_major_kernel(const int *__restrict__ indptr, const cu2b_rating *__restrict__ coo,
+                         const int *__restrict__ active_users, const int *__restrict__ user_ids, int n_active,
+                         uint32_t seed, int iter0, int nb, int pitch, DsgdDraw *__restrict__ draws) {
+    const long long n = (long long)n_active * nb;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int a = (int)(i / nb), t = (int)(i - (long long)a * nb);
+        const int u = __ldg(&active_users[a]);
+        const uint32_t uid = user_ids ? (uint32_t)__ldg(&user_ids[u]) : (uint32_t)u;
+        const int lo = __ldg(&indptr[u]), hi = __ldg(&indptr[u + 1]);
+        const uint32_t r = philox4x32_10_x(uid, (uint32_t)(iter0 + t), 0u, PHILOX_TAG, seed, PHILOX_KEY1);
+        const int j = lo + (int)__umulhi(r, (uint32_t)(hi - lo));
+        DsgdDraw d;
+        d.item = __ldg(&coo[j].item);
+        d.rating = __ldg(&coo[j].rating);
+        draws[(size_t)a * pitch + t] = d;
+    }
+}
+
 template <int L, int V>
 __global__ void __launch_bounds__(kThreads)
 mf_sgd_user_tiles(const UserTileParams p) {
