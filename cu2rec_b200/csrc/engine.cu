@@ -74,20 +74,41 @@ struct Trace {
 // ---------------------------------------------------------------------------------------
 struct DevPool {
     std::vector<void *> ptrs;
+    // Stream-ordered allocation from the device's default memory pool (kept warm: release
+    // threshold = never), so that a train() call does not pay cudaMalloc/cudaFree of several GB
+    // every time. DSGD contexts export their buffers through CUDA IPC and therefore use plain
+    // cudaMalloc (async == false).
+    bool async = false;
+    cudaStream_t stream = nullptr;
     ~DevPool() { release(); }
+    void use_async(cudaStream_t st) {
+        int dev = 0, supported = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return;
+        cudaDeviceGetAttribute(&supported, cudaDevAttrMemoryPoolsSupported, dev);
+        if (!supported) return;
+        cudaMemPool_t mp;
+        if (cudaDeviceGetDefaultMemPool(&mp, dev) != cudaSuccess) return;
+        unsigned long long never = ~0ULL;
+        cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &never);
+        async = true;
+        stream = st;
+    }
     void release() {
-        for (void *p : ptrs) cudaFree(p);
+        for (void *p : ptrs) {
+            if (async) cudaFreeAsync(p, stream); else cudaFree(p);
+        }
         ptrs.clear();
     }
     template <typename T>
     cu2b_status alloc(T **out, size_t count) {
         void *p = nullptr;
         size_t bytes = std::max<size_t>(16, count * sizeof(T));
-        cudaError_t e = cudaMalloc(&p, bytes);
+        cudaError_t e = async ? cudaMallocAsync(&p, bytes, stream) : cudaMalloc(&p, bytes);
         if (e != cudaSuccess) {
             *out = nullptr;
+            cudaGetLastError();
             return cu2b_fail(e == cudaErrorMemoryAllocation ? CU2B_ERR_NOMEM : CU2B_ERR_CUDA,
-                             "cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
+                             "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
         }
         ptrs.push_back(p);
         *out = (T *)p;
@@ -95,7 +116,10 @@ struct DevPool {
     }
     void free_one(void *p) {
         auto it = std::find(ptrs.begin(), ptrs.end(), p);
-        if (it != ptrs.end()) { cudaFree(p); ptrs.erase(it); }
+        if (it != ptrs.end()) {
+            if (async) cudaFreeAsync(p, stream); else cudaFree(p);
+            ptrs.erase(it);
+        }
     }
 };
 
@@ -182,7 +206,7 @@ cu2b_status upload_matrix(DevPool &pool, cudaStream_t st, const cu2b_csr *m, Dev
     expand_coo_kernel<<<grid, 256, 0, st>>>(out->indptr, m->rows, indices, data, (long long)nnz, out->coo);
     CUDA_TRY(cudaGetLastError());
     if (tmp_i) {
-        CUDA_TRY(cudaStreamSynchronize(st));
+        if (!pool.async) CUDA_TRY(cudaStreamSynchronize(st));  // stream-ordered frees need no sync
         pool.free_one(tmp_i);
         pool.free_one(tmp_d);
     }
@@ -517,7 +541,11 @@ struct cu2b_session {
     Timing timing;
     cu2b_stats stats;
     ~cu2b_session() {
-        if (stream) cudaStreamDestroy(stream);
+        pool.release();  // stream-ordered frees are enqueued before the stream goes away
+        if (stream) {
+            cudaStreamSynchronize(stream);
+            cudaStreamDestroy(stream);
+        }
     }
 };
 
@@ -763,6 +791,7 @@ static cu2b_status session_create_impl(cu2b_session **out, int device, const cu2
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     s->sm_count = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    if (alloc_stream && !getenv("CU2B_NO_MEMPOOL")) s->pool.use_async(s->stream);
 
     Trace tr("session_create");
     tr.mark("setup");
