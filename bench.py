@@ -261,7 +261,7 @@ def config_dict(args, k):
     U, I, R, _, _ = WORKLOADS[args.workload]
     return {"workload": "%s-shape synthetic low-rank+noise (%d users x %d items x ~%d ratings, 90/10 split), k=%d, "
                         "hogwild, per_user sampler (one sampled rating per user per iteration), iteration-tiled "
-                        "schedule (16 iterations per user tile)" % (args.workload, U, I, R, k),
+                        "schedule (32 iterations per user tile)" % (args.workload, U, I, R, k),
             "n_factors": k, "iters_per_step": args.iters_per_step, "updates_per_step": args.iters_per_step * U,
             "step": "T reference iterations + one train/test loss check (training.cu:118)",
             "l2": "inputs larger than L2 (P %d MB + rating/update streams >> 126 MB)" % (U * k * 4 >> 20),

@@ -530,8 +530,13 @@ struct cu2b_session {
     bool dsgd_child = false;  // created by cu2b_dsgd_create: no single-GPU update stream
     double hot_share = 0.0;   // hottest item's share of the draws (asynchronous-SGD stability bound)
     // iteration-tiled schedule (cfg.round_iters > 1)
-    DsgdDraw *draws = nullptr;
+    DsgdDraw *draws = nullptr;       // two buffers of n_active * draw_pitch draws
+    size_t draws_stride = 0;
     int draw_pitch = 0, round_iters = 1, tiles_grid = 0;
+    cudaStream_t sampler_stream = nullptr;  // the sampler of round r+1 overlaps the update kernel of round r
+    cudaEvent_t ev_sampled[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+    bool consumed_pending[2] = {false, false};
+    long long rounds_enqueued = 0;
     UserTileKernel tiles_kernel = nullptr;
     // experiment switches (environment): CU2B_TUNE_GATE=0 drops the per-user ordering gate,
     // CU2B_TUNE_CHUNK overrides the chunk size
@@ -541,10 +546,16 @@ struct cu2b_session {
     Timing timing;
     cu2b_stats stats;
     ~cu2b_session() {
+        if (sampler_stream) cudaStreamSynchronize(sampler_stream);
         pool.release();  // stream-ordered frees are enqueued before the stream goes away
         if (stream) {
             cudaStreamSynchronize(stream);
             cudaStreamDestroy(stream);
+        }
+        if (sampler_stream) cudaStreamDestroy(sampler_stream);
+        for (int b = 0; b < 2; ++b) {
+            if (ev_sampled[b]) cudaEventDestroy(ev_sampled[b]);
+            if (ev_consumed[b]) cudaEventDestroy(ev_consumed[b]);
         }
     }
 };
@@ -665,52 +676,72 @@ cu2b_status enqueue_blocked_iterations(cu2b_session *s, int n_seg) {
 }
 
 // Iteration-tiled schedule: rounds of up to round_iters iterations, users processed in tiles.
+// The draws of round r+1 are sampled on a second stream while the update kernel of round r runs
+// (two draw buffers, two events per buffer); everything stays stream/event ordered on the device.
 cu2b_status enqueue_tiled_iterations(cu2b_session *s, int iter_abs, int n_seg) {
-    constexpr int kTU_warps = kConsumerWarps;
-    const int TU = kTU_warps * (32 / s->L);
-    while (n_seg > 0) {
-        const int nb = std::min(n_seg, s->round_iters);
-        {
-            const int id = s->timing.begin(Timing::SAMPLER, s->stream);
-            const long long draws = (long long)nb * s->n_active;
-            const int grid = (int)std::max<long long>(1, std::min<long long>((draws + 255) / 256, (long long)s->sm_count * 16));
-            sample_user_major_kernel<<<grid, 256, 0, s->stream>>>(s->train.indptr, s->train.coo, s->active, s->user_ids,
-                                                                 s->n_active, (uint32_t)s->cfg.seed, iter_abs, nb,
-                                                                 s->draw_pitch, s->draws);
-            CUDA_TRY(cudaGetLastError());
-            s->stats.kernel_launches++;
-            s->timing.end(id, s->stream);
-        }
-        {
-            const int id = s->timing.begin(Timing::SGD, s->stream);
-            UserTileParams tp;
-            tp.draws = s->draws;
-            tp.active_users = s->active;
-            tp.n_active = s->n_active;
-            tp.pitch = s->draw_pitch;
-            tp.nb = nb;
-            tp.n_tiles = (s->n_active + TU - 1) / TU;
-            if (s->counter_next == 0)
-                CUDA_TRY(cudaMemsetAsync(s->counters, 0, sizeof(unsigned long long) * s->counter_slots, s->stream));
-            tp.tile_counter = s->counters + s->counter_next;
-            s->counter_next = (s->counter_next + 1) % s->counter_slots;
-            tp.P = s->P; tp.Q = s->Q; tp.user_bias = s->ub; tp.item_bias = s->ib;
-            tp.kp = s->kp;
-            tp.mu = s->mu;
-            tp.lr = &s->state->lr;
-            tp.P_reg = s->cfg.P_reg; tp.Q_reg = s->cfg.Q_reg;
-            tp.ub_reg = s->cfg.user_bias_reg; tp.ib_reg = s->cfg.item_bias_reg;
-            tp.is_train = s->cfg.is_train;
-            const int grid = std::max(1, std::min(tp.n_tiles, s->tiles_grid));
-            s->tiles_kernel<<<grid, kThreads, 0, s->stream>>>(tp);
-            CUDA_TRY(cudaGetLastError());
-            s->stats.kernel_launches++;
-            s->stats.sgd_launches++;
-            s->timing.end(id, s->stream);
-        }
+    const int TU = kConsumerWarps * (32 / s->L);
+    // carve the segment into rounds
+    std::vector<std::pair<int, int>> rounds;  // (first absolute iteration, count)
+    for (int done = 0; done < n_seg;) {
+        const int nb = std::min(n_seg - done, s->round_iters);
+        rounds.push_back({iter_abs + done, nb});
+        done += nb;
+    }
+    auto launch_sampler = [&](int abs_it, int nb, int buf) -> cu2b_status {
+        if (s->consumed_pending[buf]) CUDA_TRY(cudaStreamWaitEvent(s->sampler_stream, s->ev_consumed[buf], 0));
+        const long long draws = (long long)nb * s->n_active;
+        const int grid = (int)std::max<long long>(1, std::min<long long>((draws + 255) / 256, (long long)s->sm_count * 16));
+        const int tid = s->timing.begin(Timing::SAMPLER, s->sampler_stream);
+        sample_user_major_kernel<<<grid, 256, 0, s->sampler_stream>>>(s->train.indptr, s->train.coo, s->active, s->user_ids,
+                                                                     s->n_active, (uint32_t)s->cfg.seed, abs_it, nb,
+                                                                     s->draw_pitch, s->draws + (size_t)buf * s->draws_stride);
+        CUDA_TRY(cudaGetLastError());
+        s->timing.end(tid, s->sampler_stream);
+        CUDA_TRY(cudaEventRecord(s->ev_sampled[buf], s->sampler_stream));
+        s->stats.kernel_launches++;
+        return CU2B_OK;
+    };
+    // the sampler stream must not run ahead of earlier work on the main stream (model upload,
+    // previous segment): fork it from the main stream once per segment
+    cudaEvent_t fork = s->timing.get();
+    CUDA_TRY(cudaEventRecord(fork, s->stream));
+    CUDA_TRY(cudaStreamWaitEvent(s->sampler_stream, fork, 0));
+    s->timing.pool.push_back(fork);
+    if (!rounds.empty()) CU2B_TRY(launch_sampler(rounds[0].first, rounds[0].second, (int)(s->rounds_enqueued & 1)));
+    for (size_t r = 0; r < rounds.size(); ++r) {
+        const int buf = (int)(s->rounds_enqueued & 1);
+        const int nb = rounds[r].second;
+        if (r + 1 < rounds.size()) CU2B_TRY(launch_sampler(rounds[r + 1].first, rounds[r + 1].second, buf ^ 1));
+        CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_sampled[buf], 0));
+        const int id = s->timing.begin(Timing::SGD, s->stream);
+        UserTileParams tp;
+        tp.draws = s->draws + (size_t)buf * s->draws_stride;
+        tp.active_users = s->active;
+        tp.n_active = s->n_active;
+        tp.pitch = s->draw_pitch;
+        tp.nb = nb;
+        tp.n_tiles = (s->n_active + TU - 1) / TU;
+        if (s->counter_next == 0)
+            CUDA_TRY(cudaMemsetAsync(s->counters, 0, sizeof(unsigned long long) * s->counter_slots, s->stream));
+        tp.tile_counter = s->counters + s->counter_next;
+        s->counter_next = (s->counter_next + 1) % s->counter_slots;
+        tp.P = s->P; tp.Q = s->Q; tp.user_bias = s->ub; tp.item_bias = s->ib;
+        tp.kp = s->kp;
+        tp.mu = s->mu;
+        tp.lr = &s->state->lr;
+        tp.P_reg = s->cfg.P_reg; tp.Q_reg = s->cfg.Q_reg;
+        tp.ub_reg = s->cfg.user_bias_reg; tp.ib_reg = s->cfg.item_bias_reg;
+        tp.is_train = s->cfg.is_train;
+        const int grid = std::max(1, std::min(tp.n_tiles, s->tiles_grid));
+        s->tiles_kernel<<<grid, kThreads, 0, s->stream>>>(tp);
+        CUDA_TRY(cudaGetLastError());
+        s->stats.kernel_launches++;
+        s->stats.sgd_launches++;
+        s->timing.end(id, s->stream);
+        CUDA_TRY(cudaEventRecord(s->ev_consumed[buf], s->stream));
+        s->consumed_pending[buf] = true;
+        s->rounds_enqueued++;
         s->stats.updates += (long long)nb * s->n_active;
-        iter_abs += nb;
-        n_seg -= nb;
     }
     return CU2B_OK;
 }
@@ -857,7 +888,13 @@ static cu2b_status session_create_impl(cu2b_session **out, int device, const cu2
         const int TU = kConsumerWarps * (32 / s->L);
         s->draw_pitch = std::min((s->round_iters + 3) & ~3, kTileDrawsMax / TU);
         s->round_iters = std::min(s->round_iters, s->draw_pitch);
-        CU2B_TRY(s->pool.alloc(&s->draws, (size_t)std::max(1, s->n_active) * s->draw_pitch + kTileDrawsMax));
+        s->draws_stride = ((size_t)std::max(1, s->n_active) * s->draw_pitch + kTileDrawsMax + 1) & ~(size_t)1;
+        CU2B_TRY(s->pool.alloc(&s->draws, 2 * s->draws_stride));
+        CUDA_TRY(cudaStreamCreateWithFlags(&s->sampler_stream, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            CUDA_TRY(cudaEventCreateWithFlags(&s->ev_sampled[b], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&s->ev_consumed[b], cudaEventDisableTiming));
+        }
         s->tiles_kernel = pick_user_tiles(s->L, s->V);
         int occ_t = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, s->tiles_kernel, kThreads, 0));

@@ -58,7 +58,7 @@ extern "C" void cu2b_config_default(cu2b_config *c) {
     c->sampler = CU2B_SAMPLER_PER_USER;
     c->n_blocks = 0;
     c->n_gpus = 1;
-    c->round_iters = 16;
+    c->round_iters = 32;
 }
 
 namespace {

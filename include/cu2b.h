@@ -72,7 +72,7 @@ typedef struct cu2b_config {
     int n_blocks; /* deterministic mode: B of the BxB block grid, 0 = automatic */
     int n_gpus;   /* DSGD width, 0/1 = single GPU */
     int round_iters; /* Hogwild schedule on one GPU: this many consecutive iterations of a user are
-                        applied back to back with the user's row kept in registers (default 16;
+                        applied back to back with the user's row kept in registers (default 32;
                         1 = the reference's iteration-synchronous order) */
 } cu2b_config;
 

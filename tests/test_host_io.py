@@ -152,7 +152,7 @@ def test_config_goldens_and_round_trip(tmp_path, golden_dir, fixtures_dir, ref_t
     c5 = cu.Config()
     c5.read_config(tmp_path / "ext.cfg")
     assert (c5.n_threads, c5.patience, c5.check_error, c5.mode, c5.sampler, c5.n_blocks, c5.n_gpus) == (64, 3.0, 25, 1, 1, 16, 2)
-    assert c5.round_iters == 4 and cu.Config().round_iters == 16
+    assert c5.round_iters == 4 and cu.Config().round_iters == 32
     with pytest.raises(cu._lib.Cu2bError):
         cu.Config().read_config(tmp_path / "missing.cfg")
 
