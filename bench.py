@@ -260,8 +260,8 @@ def run_reference_arm(args):
 def config_dict(args, k):
     U, I, R, _, _ = WORKLOADS[args.workload]
     return {"workload": "%s-shape synthetic low-rank+noise (%d users x %d items x ~%d ratings, 90/10 split), k=%d, "
-                        "hogwild, per_user sampler (one sampled rating per user per iteration), iteration-tiled "
-                        "schedule (32 iterations per user tile)" % (args.workload, U, I, R, k),
+                        "hogwild, per_user sampler (one sampled rating per user per iteration) fused into the "
+                        "update kernel, iteration-tiled schedule (32 iterations per user round)" % (args.workload, U, I, R, k),
             "n_factors": k, "iters_per_step": args.iters_per_step, "updates_per_step": args.iters_per_step * U,
             "step": "T reference iterations + one train/test loss check (training.cu:118)",
             "l2": "inputs larger than L2 (P %d MB + rating/update streams >> 126 MB)" % (U * k * 4 >> 20),
@@ -335,7 +335,8 @@ def run_ours(args):
     sgd_gbs = updates * bytes_per_update / (st["sgd_ms"] / 1e3) / 1e9
     peak, peak_src = peaks()
     launches = max(1, int(st["sgd_launches"]))
-    kernel_name = "mf_sgd_user_tiles" if cfg.round_iters > 1 else "mf_sgd_hogwild"
+    kernel_name = ("mf_sgd_hogwild" if cfg.round_iters <= 1 else
+                   "mf_sgd_user_tiles" if os.environ.get("CU2B_TILE_PIPE") == "tma" else "mf_sgd_user_rounds")
     bpu = traffic_from_profiles(kernel_name, k)
     roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": sgd_gbs, "peak": peak, "unit": "GB/s",
                 "frac": sgd_gbs / peak, "peak_source": peak_src,

@@ -147,6 +147,7 @@ mf_sgd_user_runs(const UserRunParams p) {
     const int n_groups = ((gridDim.x * blockDim.x) >> 5) * G;
     const int vecs = p.kp >> 2;
     const float lr = __ldg(p.lr);
+    const StepCoef sc = step_coef(lr, p.P_reg, p.Q_reg, p.ub_reg, p.ib_reg);
     float4 *const Pv = reinterpret_cast<float4 *>(p.P);
     float4 *const Qv = reinterpret_cast<float4 *>(p.Q);
     for (int a0 = warp_global * G; a0 < p.n_active; a0 += n_groups) {
@@ -175,42 +176,7 @@ mf_sgd_user_runs(const UserRunParams p) {
             // the next draw is fetched one update ahead: it is not part of the item row's
             // read -> atomic-add window, so it shortens the update without adding staleness
             if (j + 1 < end) nxt = row[j + 1];
-            const size_t qo = (size_t)d.item * vecs + l;
-            float4 qv[V];
-#pragma unroll
-            for (int v = 0; v < V; ++v)
-                qv[v] = (ok && v * L + l < vecs) ? __ldcg(Qv + qo + v * L) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float ib = ok ? __ldcg(p.item_bias + d.item) : 0.f;
-            float acc = 0.f;
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-                acc = __fmaf_rn(pv[v].x, qv[v].x, acc);
-                acc = __fmaf_rn(pv[v].y, qv[v].y, acc);
-                acc = __fmaf_rn(pv[v].z, qv[v].z, acc);
-                acc = __fmaf_rn(pv[v].w, qv[v].w, acc);
-            }
-            const float dot = group_sum<L>(acc);
-            const float pred = __fadd_rn(__fadd_rn(__fadd_rn(p.mu, ub), ib), dot);
-            const float err = __fsub_rn(d.rating, pred);
-            if (ok) {
-#pragma unroll
-                for (int v = 0; v < V; ++v) {
-                    const float4 x = pv[v], y = qv[v];
-                    float4 nq;
-                    nq.x = __fmul_rn(lr, __fsub_rn(__fmul_rn(err, x.x), __fmul_rn(p.Q_reg, y.x)));
-                    nq.y = __fmul_rn(lr, __fsub_rn(__fmul_rn(err, x.y), __fmul_rn(p.Q_reg, y.y)));
-                    nq.z = __fmul_rn(lr, __fsub_rn(__fmul_rn(err, x.z), __fmul_rn(p.Q_reg, y.z)));
-                    nq.w = __fmul_rn(lr, __fsub_rn(__fmul_rn(err, x.w), __fmul_rn(p.Q_reg, y.w)));
-                    pv[v].x = __fadd_rn(x.x, __fmul_rn(lr, __fsub_rn(__fmul_rn(err, y.x), __fmul_rn(p.P_reg, x.x))));
-                    pv[v].y = __fadd_rn(x.y, __fmul_rn(lr, __fsub_rn(__fmul_rn(err, y.y), __fmul_rn(p.P_reg, x.y))));
-                    pv[v].z = __fadd_rn(x.z, __fmul_rn(lr, __fsub_rn(__fmul_rn(err, y.z), __fmul_rn(p.P_reg, x.z))));
-                    pv[v].w = __fadd_rn(x.w, __fmul_rn(lr, __fsub_rn(__fmul_rn(err, y.w), __fmul_rn(p.P_reg, x.w))));
-                    if (p.is_train && v * L + l < vecs) red_add_v4(Qv + qo + v * L, nq);
-                }
-                if (p.is_train && l == 0)
-                    red_add_f32(p.item_bias + d.item, __fmul_rn(lr, __fsub_rn(err, __fmul_rn(p.ib_reg, ib))));
-                ub = __fadd_rn(ub, __fmul_rn(lr, __fsub_rn(err, __fmul_rn(p.ub_reg, ub))));
-            }
+            user_side_update<L, V>(pv, ub, d.item, d.rating, ok, l, vecs, Qv, p.item_bias, p.mu, lr, sc, p.is_train);
             ++j;
         }
         if (mine) {

@@ -167,62 +167,112 @@ cu2b_status validate_csr(const cu2b_csr *m, const char *what) {
     return CU2B_OK;
 }
 
-// Uploads (or adopts) a CSR matrix and expands it to COO triplets on the device.
-cu2b_status upload_matrix(DevPool &pool, cudaStream_t st, const cu2b_csr *m, DevMatrix *out,
-                          std::vector<int> *indptr_host) {
+// Orders `waiter` after everything enqueued on `signaller` so far (one reusable event).
+cu2b_status stream_after(cudaStream_t waiter, cudaStream_t signaller, cudaEvent_t ev) {
+    CUDA_TRY(cudaEventRecord(ev, signaller));
+    CUDA_TRY(cudaStreamWaitEvent(waiter, ev, 0));
+    return CU2B_OK;
+}
+
+// A CSR matrix on its way to the device: allocate, copy (H2D, or adopt device arrays), expand to
+// COO triplets. The three phases are separate so that session creation can allocate everything
+// first, stream all copies through one copy stream and run the expansions on the compute stream
+// while the DMA engine is already moving the next buffer.
+struct MatrixUpload {
+    const cu2b_csr *m = nullptr;
+    DevMatrix *out = nullptr;
+    int *tmp_i = nullptr;
+    float *tmp_d = nullptr;
+};
+
+cu2b_status matrix_alloc(DevPool &pool, const cu2b_csr *m, DevMatrix *out, MatrixUpload *up) {
     CU2B_TRY(validate_csr(m, "upload_matrix"));
     out->rows = m->rows;
     out->cols = m->cols;
     out->nnz = m->nonzeros;
     const size_t nnz = (size_t)m->nonzeros;
+    up->m = m;
+    up->out = out;
     CU2B_TRY(pool.alloc(&out->indptr, (size_t)m->rows + 1));
     CU2B_TRY(pool.alloc(&out->coo, nnz + kChunkMax + 4));
-    const cudaMemcpyKind kind = m->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    CUDA_TRY(cudaMemcpyAsync(out->indptr, m->indptr, ((size_t)m->rows + 1) * sizeof(int), kind, st));
-    if (indptr_host) {
-        indptr_host->resize((size_t)m->rows + 1);
-        if (m->on_device) {
-            CUDA_TRY(cudaMemcpyAsync(indptr_host->data(), m->indptr, ((size_t)m->rows + 1) * sizeof(int),
-                                     cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaStreamSynchronize(st));
-        } else {
-            memcpy(indptr_host->data(), m->indptr, ((size_t)m->rows + 1) * sizeof(int));
-        }
-    }
-    if (nnz == 0) return CU2B_OK;
-    const int *indices = m->indices;
-    const float *data = m->data;
-    int *tmp_i = nullptr;
-    float *tmp_d = nullptr;
-    if (!m->on_device) {
-        CU2B_TRY(pool.alloc(&tmp_i, nnz));
-        CU2B_TRY(pool.alloc(&tmp_d, nnz));
-        CUDA_TRY(cudaMemcpyAsync(tmp_i, m->indices, nnz * sizeof(int), cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(tmp_d, m->data, nnz * sizeof(float), cudaMemcpyHostToDevice, st));
-        indices = tmp_i;
-        data = tmp_d;
-    }
-    const int grid = (int)std::min<size_t>((nnz + 255) / 256, 148 * 16);
-    expand_coo_kernel<<<grid, 256, 0, st>>>(out->indptr, m->rows, indices, data, (long long)nnz, out->coo);
-    CUDA_TRY(cudaGetLastError());
-    if (tmp_i) {
-        if (!pool.async) CUDA_TRY(cudaStreamSynchronize(st));  // stream-ordered frees need no sync
-        pool.free_one(tmp_i);
-        pool.free_one(tmp_d);
+    if (!m->on_device && nnz > 0) {
+        CU2B_TRY(pool.alloc(&up->tmp_i, nnz));
+        CU2B_TRY(pool.alloc(&up->tmp_d, nnz));
     }
     return CU2B_OK;
+}
+
+cu2b_status matrix_copy(cudaStream_t cst, const MatrixUpload &up) {
+    const cu2b_csr *m = up.m;
+    const size_t nnz = (size_t)m->nonzeros;
+    const cudaMemcpyKind kind = m->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    CUDA_TRY(cudaMemcpyAsync(up.out->indptr, m->indptr, ((size_t)m->rows + 1) * sizeof(int), kind, cst));
+    if (up.tmp_i) {
+        CUDA_TRY(cudaMemcpyAsync(up.tmp_i, m->indices, nnz * sizeof(int), cudaMemcpyHostToDevice, cst));
+        CUDA_TRY(cudaMemcpyAsync(up.tmp_d, m->data, nnz * sizeof(float), cudaMemcpyHostToDevice, cst));
+    }
+    return CU2B_OK;
+}
+
+cu2b_status matrix_expand(DevPool &pool, cudaStream_t st, MatrixUpload &up) {
+    const cu2b_csr *m = up.m;
+    const size_t nnz = (size_t)m->nonzeros;
+    if (nnz == 0) return CU2B_OK;
+    const int *indices = up.tmp_i ? up.tmp_i : m->indices;
+    const float *data = up.tmp_d ? up.tmp_d : m->data;
+    const int grid = (int)std::min<size_t>((nnz + 255) / 256, 148 * 16);
+    expand_coo_kernel<<<grid, 256, 0, st>>>(up.out->indptr, m->rows, indices, data, (long long)nnz, up.out->coo);
+    CUDA_TRY(cudaGetLastError());
+    if (up.tmp_i) {
+        if (!pool.async) CUDA_TRY(cudaStreamSynchronize(st));  // stream-ordered frees need no sync
+        pool.free_one(up.tmp_i);
+        pool.free_one(up.tmp_d);
+        up.tmp_i = nullptr;
+        up.tmp_d = nullptr;
+    }
+    return CU2B_OK;
+}
+
+cu2b_status host_indptr(const cu2b_csr *m, cudaStream_t st, std::vector<int> *indptr_host) {
+    indptr_host->resize((size_t)m->rows + 1);
+    if (m->on_device) {
+        CUDA_TRY(cudaMemcpyAsync(indptr_host->data(), m->indptr, ((size_t)m->rows + 1) * sizeof(int),
+                                 cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    } else {
+        memcpy(indptr_host->data(), m->indptr, ((size_t)m->rows + 1) * sizeof(int));
+    }
+    return CU2B_OK;
+}
+
+// Single-stream form (kernel-level entry points).
+cu2b_status upload_matrix(DevPool &pool, cudaStream_t st, const cu2b_csr *m, DevMatrix *out,
+                          std::vector<int> *indptr_host) {
+    MatrixUpload up;
+    CU2B_TRY(matrix_alloc(pool, m, out, &up));
+    CU2B_TRY(matrix_copy(st, up));
+    if (indptr_host) CU2B_TRY(host_indptr(m, st, indptr_host));
+    return matrix_expand(pool, st, up);
 }
 
 // dense [rows x k] host matrix <-> [rows x kp] device matrix
 cu2b_status upload_dense(cudaStream_t st, float *dst, const float *src, int rows, int k, int kp) {
     if (rows == 0) return CU2B_OK;
-    if (kp != k) CUDA_TRY(cudaMemsetAsync(dst, 0, (size_t)rows * kp * sizeof(float), st));
+    if (kp == k) {  // no padding: one contiguous copy
+        CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)rows * k * sizeof(float), cudaMemcpyHostToDevice, st));
+        return CU2B_OK;
+    }
+    CUDA_TRY(cudaMemsetAsync(dst, 0, (size_t)rows * kp * sizeof(float), st));
     CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)kp * sizeof(float), src, (size_t)k * sizeof(float),
                                (size_t)k * sizeof(float), (size_t)rows, cudaMemcpyHostToDevice, st));
     return CU2B_OK;
 }
 cu2b_status download_dense(cudaStream_t st, float *dst, const float *src, int rows, int k, int kp) {
     if (rows == 0) return CU2B_OK;
+    if (kp == k) {
+        CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)rows * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+        return CU2B_OK;
+    }
     CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)k * sizeof(float), src, (size_t)kp * sizeof(float),
                                (size_t)k * sizeof(float), (size_t)rows, cudaMemcpyDeviceToHost, st));
     return CU2B_OK;
@@ -236,6 +286,7 @@ typedef void (*LossKernel)(const LossParams);
 typedef void (*BlockedKernel)(const BlockedParams);
 typedef void (*UserRunKernel)(const UserRunParams);
 typedef void (*UserTileKernel)(const UserTileParams);
+typedef void (*UserRoundKernel)(const UserRoundParams);
 
 cu2b_status layout_for(int kp, int *L, int *V) {
     const int vecs = kp / 4;
@@ -361,6 +412,29 @@ UserTileKernel pick_user_tiles(int L, int V) {
     }
 }
 
+// pf = 1: one item row of look-ahead per lane group (see mf_sgd_user_rounds).
+template <int PF, int MINB>
+UserRoundKernel pick_user_rounds_t(int L, int V) {
+    switch (L) {
+        case 1: return mf_sgd_user_rounds<1, 1, PF, MINB>;
+        case 2: return mf_sgd_user_rounds<2, 1, PF, MINB>;
+        case 4: return mf_sgd_user_rounds<4, 1, PF, MINB>;
+        case 8: return mf_sgd_user_rounds<8, 1, PF, MINB>;
+        case 16: return mf_sgd_user_rounds<16, 1, PF, MINB>;
+        default:
+            switch (V) {
+                case 1: return mf_sgd_user_rounds<32, 1, PF, MINB>;
+                case 2: return mf_sgd_user_rounds<32, 2, PF, MINB>;
+                case 3: return mf_sgd_user_rounds<32, 3, PF, MINB>;
+                default: return mf_sgd_user_rounds<32, 4, PF, MINB>;
+            }
+    }
+}
+UserRoundKernel pick_user_rounds(int L, int V, int pf, int minb) {
+    if (pf) return minb >= 8 ? pick_user_rounds_t<1, 8>(L, V) : minb >= 6 ? pick_user_rounds_t<1, 6>(L, V) : minb == 5 ? pick_user_rounds_t<1, 5>(L, V) : pick_user_rounds_t<1, 4>(L, V);
+    return minb >= 8 ? pick_user_rounds_t<0, 8>(L, V) : minb >= 6 ? pick_user_rounds_t<0, 6>(L, V) : minb == 5 ? pick_user_rounds_t<0, 5>(L, V) : pick_user_rounds_t<0, 4>(L, V);
+}
+
 // Host side of the deterministic mode: stable counting sort of the ratings by
 // (round, user block) where round = (item block - user block) mod B.
 struct BlockSchedule {
@@ -399,12 +473,15 @@ cu2b_status build_block_schedule(const cu2b_rating *coo, int64_t n, int rows, in
 // per-user sampling (one uniform draw per user per iteration). Host CSR only; 0 if unknown.
 double hot_item_share(const cu2b_csr *m, const int *item_block_ptr, int n_blocks) {
     if (!m || m->on_device || m->nonzeros <= 0) return 0.0;
+    // An estimate is enough (it feeds a bound with a 2x safety margin): every `stride`-th user,
+    // at most ~64 K users, so that session creation does not pay a pass over all ratings.
+    const int stride = std::max(1, m->rows / 65536);
     std::vector<double> w((size_t)m->cols, 0.0);
 #pragma omp parallel
     {
         std::vector<double> mine((size_t)m->cols, 0.0);
 #pragma omp for schedule(static) nowait
-        for (int u = 0; u < m->rows; ++u) {
+        for (int u = 0; u < m->rows; u += stride) {
             const int lo = m->indptr[u], hi = m->indptr[u + 1];
             if (hi > lo) {
                 const double pu = 1.0 / (hi - lo);
@@ -538,6 +615,11 @@ struct cu2b_session {
     bool consumed_pending[2] = {false, false};
     long long rounds_enqueued = 0;
     UserTileKernel tiles_kernel = nullptr;
+    // default: the sampler is fused into the update kernel (mf_sgd_user_rounds); CU2B_TILE_PIPE=tma
+    // selects the separate sampler + TMA-fed tile kernel (mf_sgd_user_tiles) for A/B runs
+    bool fused_sampler = false;
+    UserRoundKernel rounds_kernel = nullptr;
+    int rounds_grid = 0;
     // experiment switches (environment): CU2B_TUNE_GATE=0 drops the per-user ordering gate,
     // CU2B_TUNE_CHUNK overrides the chunk size
     bool no_gate = false;
@@ -678,7 +760,43 @@ cu2b_status enqueue_blocked_iterations(cu2b_session *s, int n_seg) {
 // Iteration-tiled schedule: rounds of up to round_iters iterations, users processed in tiles.
 // The draws of round r+1 are sampled on a second stream while the update kernel of round r runs
 // (two draw buffers, two events per buffer); everything stays stream/event ordered on the device.
+cu2b_status enqueue_fused_rounds(cu2b_session *s, int iter_abs, int n_seg) {
+    UserRoundParams rp;
+    rp.indptr = s->train.indptr;
+    rp.coo = s->train.coo;
+    rp.active_users = s->active;
+    rp.user_ids = s->user_ids;
+    rp.n_active = s->n_active;
+    rp.seed = (uint32_t)s->cfg.seed;
+    rp.P = s->P; rp.Q = s->Q; rp.user_bias = s->ub; rp.item_bias = s->ib;
+    rp.kp = s->kp;
+    rp.mu = s->mu;
+    rp.lr = &s->state->lr;
+    rp.P_reg = s->cfg.P_reg; rp.Q_reg = s->cfg.Q_reg;
+    rp.ub_reg = s->cfg.user_bias_reg; rp.ib_reg = s->cfg.item_bias_reg;
+    rp.is_train = s->cfg.is_train;
+    for (int done = 0; done < n_seg;) {
+        const int nb = std::min(n_seg - done, s->round_iters);
+        rp.iter0 = iter_abs + done;
+        rp.nb = nb;
+        if (s->counter_next == 0)
+            CUDA_TRY(cudaMemsetAsync(s->counters, 0, sizeof(unsigned long long) * s->counter_slots, s->stream));
+        rp.tile_counter = s->counters + s->counter_next;
+        s->counter_next = (s->counter_next + 1) % s->counter_slots;
+        const int id = s->timing.begin(Timing::SGD, s->stream);
+        s->rounds_kernel<<<s->rounds_grid, kRoundWarps * 32, 0, s->stream>>>(rp);
+        CUDA_TRY(cudaGetLastError());
+        s->timing.end(id, s->stream);
+        s->stats.kernel_launches++;
+        s->stats.sgd_launches++;
+        s->stats.updates += (long long)nb * s->n_active;
+        done += nb;
+    }
+    return CU2B_OK;
+}
+
 cu2b_status enqueue_tiled_iterations(cu2b_session *s, int iter_abs, int n_seg) {
+    if (s->fused_sampler) return enqueue_fused_rounds(s, iter_abs, n_seg);
     const int TU = kConsumerWarps * (32 / s->L);
     // carve the segment into rounds
     std::vector<std::pair<int, int>> rounds;  // (first absolute iteration, count)
@@ -826,31 +944,51 @@ static cu2b_status session_create_impl(cu2b_session **out, int device, const cu2
 
     Trace tr("session_create");
     tr.mark("setup");
+    // All host->device copies go through one copy stream; the compute stream only waits for the
+    // buffer it is about to touch (the COO expansion of the training matrix overlaps the upload
+    // of the model and of the test matrix).
+    struct CopyLane {
+        cudaStream_t st = nullptr;
+        cudaEvent_t ev = nullptr;
+        ~CopyLane() {
+            if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+            if (ev) cudaEventDestroy(ev);
+        }
+    } lane;
+    CUDA_TRY(cudaStreamCreateWithFlags(&lane.st, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&lane.ev, cudaEventDisableTiming));
     std::vector<int> indptr_host;
-    CU2B_TRY(upload_matrix(s->pool, s->stream, train, &s->train, &indptr_host));
-    tr.mark("upload train matrix");
-    CU2B_TRY(upload_matrix(s->pool, s->stream, test, &s->test, nullptr));
-    tr.mark("upload test matrix");
+    CU2B_TRY(host_indptr(train, s->stream, &indptr_host));
     // users with at least one training rating (sgd.cu:35 skips the others)
     std::vector<int> active;
     active.reserve(s->rows);
     for (int u = 0; u < s->rows; ++u)
         if (indptr_host[u + 1] > indptr_host[u]) active.push_back(u);
     s->n_active = (int)active.size();
+    // 1. every allocation, in stream order on the compute stream
+    MatrixUpload up_train, up_test;
+    CU2B_TRY(matrix_alloc(s->pool, train, &s->train, &up_train));
+    CU2B_TRY(matrix_alloc(s->pool, test, &s->test, &up_test));
     CU2B_TRY(s->pool.alloc(&s->active, active.size()));
-    if (!active.empty())
-        CUDA_TRY(cudaMemcpyAsync(s->active, active.data(), active.size() * sizeof(int), cudaMemcpyHostToDevice, s->stream));
-
     CU2B_TRY(s->pool.alloc(&s->P, (size_t)s->rows * s->kp));
     CU2B_TRY(s->pool.alloc(&s->Q, (size_t)s->cols * s->kp));
     CU2B_TRY(s->pool.alloc(&s->ub, (size_t)s->rows));
     CU2B_TRY(s->pool.alloc(&s->ib, (size_t)s->cols));
-    CU2B_TRY(upload_dense(s->stream, s->P, P, s->rows, s->k, s->kp));
-    CU2B_TRY(upload_dense(s->stream, s->Q, Q, s->cols, s->k, s->kp));
-    CUDA_TRY(cudaMemcpyAsync(s->ub, user_bias, (size_t)s->rows * sizeof(float), cudaMemcpyHostToDevice, s->stream));
-    CUDA_TRY(cudaMemcpyAsync(s->ib, item_bias, (size_t)s->cols * sizeof(float), cudaMemcpyHostToDevice, s->stream));
-
-    tr.mark("active list + model upload");
+    CU2B_TRY(stream_after(lane.st, s->stream, lane.ev));
+    // 2. copies back to back on the copy stream; each expansion waits only for its own matrix
+    if (!active.empty())  // pageable source: staged synchronously, so it goes first
+        CUDA_TRY(cudaMemcpyAsync(s->active, active.data(), active.size() * sizeof(int), cudaMemcpyHostToDevice, lane.st));
+    CU2B_TRY(matrix_copy(lane.st, up_train));
+    CU2B_TRY(stream_after(s->stream, lane.st, lane.ev));
+    CU2B_TRY(matrix_expand(s->pool, s->stream, up_train));
+    CU2B_TRY(upload_dense(lane.st, s->P, P, s->rows, s->k, s->kp));
+    CU2B_TRY(upload_dense(lane.st, s->Q, Q, s->cols, s->k, s->kp));
+    CUDA_TRY(cudaMemcpyAsync(s->ub, user_bias, (size_t)s->rows * sizeof(float), cudaMemcpyHostToDevice, lane.st));
+    CUDA_TRY(cudaMemcpyAsync(s->ib, item_bias, (size_t)s->cols * sizeof(float), cudaMemcpyHostToDevice, lane.st));
+    CU2B_TRY(matrix_copy(lane.st, up_test));
+    CU2B_TRY(stream_after(s->stream, lane.st, lane.ev));
+    CU2B_TRY(matrix_expand(s->pool, s->stream, up_test));
+    tr.mark("uploads + COO expansion");
     // kernels and their persistent grid sizes
     s->sgd_kernel = pick_sgd(s->L, s->V);
     s->loss_kernel = pick_loss(s->kp);
@@ -879,12 +1017,32 @@ static cu2b_status session_create_impl(cu2b_session **out, int device, const cu2
     s->round_iters = 1;
     s->dsgd_child = !alloc_stream;
     if (alloc_stream && cfg->mode == CU2B_MODE_HOGWILD && cfg->round_iters > 1) {
-        const int TU = kConsumerWarps * (32 / s->L);
-        int r = std::min(cfg->round_iters, kTileDrawsMax / TU);
-        if (const char *e = getenv("CU2B_ROUND")) r = std::min(std::max(1, atoi(e)), kTileDrawsMax / TU);
+        const char *pipe = getenv("CU2B_TILE_PIPE");
+        s->fused_sampler = !(pipe && strcmp(pipe, "tma") == 0);
+        const int per_user_max = s->fused_sampler ? kRoundDrawsPerWarp / (32 / s->L)
+                                                  : kTileDrawsMax / (kConsumerWarps * (32 / s->L));
+        int r = std::min(cfg->round_iters, per_user_max);
+        if (const char *e = getenv("CU2B_ROUND")) r = std::min(std::max(1, atoi(e)), per_user_max);
         s->round_iters = std::max(1, r);
     }
-    if (s->round_iters > 1) {
+    if (s->round_iters > 1 && s->fused_sampler) {
+        // Measured on B200 (profiles/r1_rounds_sweep.jsonl): 4, 5, 6 or 8 resident CTAs per SM and the
+        // item-row look-ahead all land within 2 % of each other -- the kernel is bound by the L2
+        // atomic units of the slices that hold the popular item rows, not by latency. Default: 5 CTAs
+        // (46 registers, no spills), no look-ahead. CU2B_TUNE_PF / CU2B_TUNE_MINB switch for A/B runs.
+        int pf = 0, minb = 5;
+        if (const char *e = getenv("CU2B_TUNE_PF")) pf = atoi(e) != 0;
+        if (const char *e = getenv("CU2B_TUNE_MINB")) minb = atoi(e);
+        if (s->V > 1) minb = 4;  // k > 128: several float4 per lane, keep the registers
+        s->rounds_kernel = pick_user_rounds(s->L, s->V, pf, minb);
+        int occ_t = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, s->rounds_kernel, kRoundWarps * 32, 0));
+        if (const char *e = getenv("CU2B_TUNE_OCC")) occ_t = std::max(1, std::min(occ_t, atoi(e)));
+        const int per_cta = kRoundWarps * (32 / s->L);
+        const int cap = inflight_cap(s->hot_share, cfg->learning_rate, 0.5);
+        s->rounds_grid = std::max(1, std::min(std::min(std::max(1, occ_t) * s->sm_count, cap / per_cta),
+                                              (s->n_active + per_cta - 1) / per_cta));
+    } else if (s->round_iters > 1) {
         const int TU = kConsumerWarps * (32 / s->L);
         s->draw_pitch = std::min((s->round_iters + 3) & ~3, kTileDrawsMax / TU);
         s->round_iters = std::min(s->round_iters, s->draw_pitch);

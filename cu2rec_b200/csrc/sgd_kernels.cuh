@@ -7,8 +7,10 @@
 // whole warp touches one contiguous 512-byte row. Smaller k packs 32/L ratings into a warp.
 // The dot product is reduced with an xor butterfly over the L lanes (every lane ends with the
 // same value), the rating error is formed once, and both rows are written back in place.
-// Update arithmetic is the unfused op sequence of mf_sequential.cu:129-141 so that a
-// sequential replay on the CPU reproduces it bit for bit (oracle flavour KERNEL).
+// Update arithmetic (sgd_step below): mf_sequential.cu:129-141 with the learning rate folded into
+// the error and the regularisers, one multiply + one fma per step; a sequential replay on the
+// CPU reproduces it bit for bit (oracle flavour KERNEL), the reference's own op order agrees to
+// fp32 rounding (stated tolerance in the tests).
 #ifndef CU2B_SGD_KERNELS_CUH_
 #define CU2B_SGD_KERNELS_CUH_
 
@@ -82,6 +84,27 @@ sample_per_user_kernel(const int *__restrict__ indptr, const cu2b_rating *__rest
     }
 }
 
+// One SGD step of a row element, learning rate folded in:
+//   lr * (err * other - reg * self)  ==  fma(a, other, -(c * self)),  a = lr * err, c = lr * reg
+// (mf_sequential.cu:134-137 / sgd.cu:55-61). The row then takes self + step with ONE rounding,
+// either as an FADD in registers or as the L2 atomic add, so both write paths agree bit for bit.
+struct StepCoef {
+    float cP, cQ, cU, cI;
+};
+__device__ __forceinline__ StepCoef step_coef(float lr, float P_reg, float Q_reg, float ub_reg, float ib_reg) {
+    StepCoef c;
+    c.cP = __fmul_rn(lr, P_reg);
+    c.cQ = __fmul_rn(lr, Q_reg);
+    c.cU = __fmul_rn(lr, ub_reg);
+    c.cI = __fmul_rn(lr, ib_reg);
+    return c;
+}
+__device__ __forceinline__ float sgd_step(float a, float other, float c, float self) {
+    return __fmaf_rn(a, other, -__fmul_rn(c, self));
+}
+// bias: lr * (err - reg * b) == fma(-c, b, a)   (mf_sequential.cu:140-141)
+__device__ __forceinline__ float bias_step(float a, float c, float self) { return __fmaf_rn(-c, self, a); }
+
 template <int L>
 __device__ __forceinline__ float group_sum(float a) {
 #pragma unroll
@@ -99,6 +122,74 @@ __device__ __forceinline__ void red_add_v4(float4 *addr, float4 v) {
 __device__ __forceinline__ void red_add_f32(float *addr, float v) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }
+// One update with the user side held in registers (the user-major kernels: mf_sgd_user_rounds,
+// mf_sgd_user_tiles, mf_sgd_user_runs): the lane group's P slice `pv` and the user bias `ub` are
+// updated in place, the item row and item bias take their steps as L2 atomic adds. `ok` false =>
+// the group idles through the warp-wide shuffles.
+// Item-side operands of one update: the lane's slice of the Q row and the item bias.
+template <int V>
+struct ItemSide {
+    float4 q[V];
+    float ib;
+};
+template <int L, int V>
+__device__ __forceinline__ void item_side_load(ItemSide<V> &it, int item, bool ok, int l, int vecs, const float4 *Qv,
+                                               const float *item_bias) {
+    const size_t qo = (size_t)item * vecs + l;
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+        it.q[v] = (ok && v * L + l < vecs) ? __ldcg(Qv + qo + v * L) : make_float4(0.f, 0.f, 0.f, 0.f);
+    it.ib = ok ? __ldcg(item_bias + item) : 0.f;
+}
+// The arithmetic of one update given its operands; P slice and user bias are updated in place,
+// the item row and item bias take their steps as L2 atomic adds.
+template <int L, int V>
+__device__ __forceinline__ void user_side_apply(float4 (&pv)[V], float &ub, const ItemSide<V> &it, int item, float rating,
+                                                bool ok, int l, int vecs, float4 *Qv, float *item_bias, float mu,
+                                                float lr, const StepCoef &sc, int is_train) {
+    const size_t qo = (size_t)item * vecs + l;
+    float acc = 0.f;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        acc = __fmaf_rn(pv[v].x, it.q[v].x, acc);
+        acc = __fmaf_rn(pv[v].y, it.q[v].y, acc);
+        acc = __fmaf_rn(pv[v].z, it.q[v].z, acc);
+        acc = __fmaf_rn(pv[v].w, it.q[v].w, acc);
+    }
+    const float dot = group_sum<L>(acc);
+    const float pred = __fadd_rn(__fadd_rn(__fadd_rn(mu, ub), it.ib), dot);
+    const float err = __fsub_rn(rating, pred);
+    const float ea = __fmul_rn(lr, err);
+    if (ok) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const float4 x = pv[v], y = it.q[v];
+            float4 nq;
+            nq.x = sgd_step(ea, x.x, sc.cQ, y.x);
+            nq.y = sgd_step(ea, x.y, sc.cQ, y.y);
+            nq.z = sgd_step(ea, x.z, sc.cQ, y.z);
+            nq.w = sgd_step(ea, x.w, sc.cQ, y.w);
+            pv[v].x = __fadd_rn(x.x, sgd_step(ea, y.x, sc.cP, x.x));
+            pv[v].y = __fadd_rn(x.y, sgd_step(ea, y.y, sc.cP, x.y));
+            pv[v].z = __fadd_rn(x.z, sgd_step(ea, y.z, sc.cP, x.z));
+            pv[v].w = __fadd_rn(x.w, sgd_step(ea, y.w, sc.cP, x.w));
+            if (is_train && v * L + l < vecs) red_add_v4(Qv + qo + v * L, nq);
+        }
+        if (is_train && l == 0) red_add_f32(item_bias + item, bias_step(ea, sc.cI, it.ib));
+        ub = __fadd_rn(ub, bias_step(ea, sc.cU, ub));
+    }
+}
+// One update with the user side held in registers (the user-major kernels: mf_sgd_user_rounds,
+// mf_sgd_user_tiles, mf_sgd_user_runs). `ok` false => the group idles through the warp-wide shuffles.
+template <int L, int V>
+__device__ __forceinline__ void user_side_update(float4 (&pv)[V], float &ub, int item, float rating, bool ok, int l,
+                                                 int vecs, float4 *Qv, float *item_bias, float mu, float lr,
+                                                 const StepCoef &sc, int is_train) {
+    ItemSide<V> it;
+    item_side_load<L, V>(it, item, ok, l, vecs, Qv, item_bias);
+    user_side_apply<L, V>(pv, ub, it, item, rating, ok, l, vecs, Qv, item_bias, mu, lr, sc, is_train);
+}
+
 // Model rows are read-write data shared by every SM: they are read with ld.global.cg and, on
 // the non-atomic path, written with st.global.cg (L2 only; SASS LDG/STG .STRONG.GPU) so that no
 // stale copy can sit in the non-coherent L1. Measured on B200 (profiles/r1_sweep2.jsonl): weak
@@ -116,6 +207,7 @@ __device__ __forceinline__ void sgd_update_slots(const SgdParams &p, const cu2b_
     float ub[UNR], ib[UNR];
     float4 *const Pv = reinterpret_cast<float4 *>(p.P);
     float4 *const Qv = reinterpret_cast<float4 *>(p.Q);
+    const StepCoef sc = step_coef(lr, p.P_reg, p.Q_reg, p.ub_reg, p.ib_reg);
 #pragma unroll
     for (int x = 0; x < UNR; ++x) {
         const size_t po = (size_t)rt[x].user * vecs + l, qo = (size_t)rt[x].item * vecs + l;
@@ -145,19 +237,20 @@ __device__ __forceinline__ void sgd_update_slots(const SgdParams &p, const cu2b_
         const float dot = group_sum<L>(acc);
         const float pred = __fadd_rn(__fadd_rn(__fadd_rn(p.mu, ub[x]), ib[x]), dot);
         const float err = __fsub_rn(rt[x].rating, pred);
+        const float ea = __fmul_rn(lr, err);
         const size_t po = (size_t)rt[x].user * vecs + l, qo = (size_t)rt[x].item * vecs + l;
 #pragma unroll
         for (int v = 0; v < V; ++v) {
             const float4 a = pv[x][v], b = qv[x][v];
             float4 na, nb;
-            na.x = __fmul_rn(lr, __fsub_rn(__fmul_rn(err, b.x), __fmul_rn(p.P_reg, a.x)));
-            na.y = __fmul_rn(lr, __fsub_rn(__fmul_rn(err, b.y), __fmul_rn(p.P_reg, a.y)));
-            na.z = __fmul_rn(lr, __fsub_rn(__fmul_rn(err, b.z), __fmul_rn(p.P_reg, a.z)));
-            na.w = __fmul_rn(lr, __fsub_rn(__fmul_rn(err, b.w), __fmul_rn(p.P_reg, a.w)));
-            nb.x = __fmul_rn(lr, __fsub_rn(__fmul_rn(err, a.x), __fmul_rn(p.Q_reg, b.x)));
-            nb.y = __fmul_rn(lr, __fsub_rn(__fmul_rn(err, a.y), __fmul_rn(p.Q_reg, b.y)));
-            nb.z = __fmul_rn(lr, __fsub_rn(__fmul_rn(err, a.z), __fmul_rn(p.Q_reg, b.z)));
-            nb.w = __fmul_rn(lr, __fsub_rn(__fmul_rn(err, a.w), __fmul_rn(p.Q_reg, b.w)));
+            na.x = sgd_step(ea, b.x, sc.cP, a.x);
+            na.y = sgd_step(ea, b.y, sc.cP, a.y);
+            na.z = sgd_step(ea, b.z, sc.cP, a.z);
+            na.w = sgd_step(ea, b.w, sc.cP, a.w);
+            nb.x = sgd_step(ea, a.x, sc.cQ, b.x);
+            nb.y = sgd_step(ea, a.y, sc.cQ, b.y);
+            nb.z = sgd_step(ea, a.z, sc.cQ, b.z);
+            nb.w = sgd_step(ea, a.w, sc.cQ, b.w);
             if (ok[x] && v * L + l < vecs) {
                 if (ATOMP) {
                     red_add_v4(Pv + po + v * L, na);
@@ -178,11 +271,11 @@ __device__ __forceinline__ void sgd_update_slots(const SgdParams &p, const cu2b_
             }
         }
         if (ok[x] && l == 0) {
-            const float ustep = __fmul_rn(lr, __fsub_rn(err, __fmul_rn(p.ub_reg, ub[x])));
+            const float ustep = bias_step(ea, sc.cU, ub[x]);
             if (ATOMP) red_add_f32(p.user_bias + rt[x].user, ustep);
             else __stcg(p.user_bias + rt[x].user, __fadd_rn(ub[x], ustep));
             if (p.is_train) {
-                const float step = __fmul_rn(lr, __fsub_rn(err, __fmul_rn(p.ib_reg, ib[x])));
+                const float step = bias_step(ea, sc.cI, ib[x]);
                 if (ATOMQ) red_add_f32(p.item_bias + rt[x].item, step);
                 else __stcg(p.item_bias + rt[x].item, __fadd_rn(ib[x], step));
             }

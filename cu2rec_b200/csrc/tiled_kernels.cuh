@@ -100,6 +100,7 @@ mf_sgd_user_tiles(const UserTileParams p) {
     const int g = lane / L, l = lane % L;
     const int vecs = p.kp >> 2;
     const float lr = __ldg(p.lr);
+    const StepCoef sc = step_coef(lr, p.P_reg, p.Q_reg, p.ub_reg, p.ib_reg);
     float4 *const Pv = reinterpret_cast<float4 *>(p.P);
     float4 *const Qv = reinterpret_cast<float4 *>(p.Q);
     for (int it = 0;; ++it) {
@@ -122,42 +123,7 @@ mf_sgd_user_tiles(const UserTileParams p) {
             DsgdDraw d;
             d.item = 0; d.rating = 0.f;
             if (mine) d = row[j];
-            const size_t qo = (size_t)d.item * vecs + l;
-            float4 qv[V];
-#pragma unroll
-            for (int v = 0; v < V; ++v)
-                qv[v] = (mine && v * L + l < vecs) ? __ldcg(Qv + qo + v * L) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float ib = mine ? __ldcg(p.item_bias + d.item) : 0.f;
-            float acc = 0.f;
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-                acc = __fmaf_rn(pv[v].x, qv[v].x, acc);
-                acc = __fmaf_rn(pv[v].y, qv[v].y, acc);
-                acc = __fmaf_rn(pv[v].z, qv[v].z, acc);
-                acc = __fmaf_rn(pv[v].w, qv[v].w, acc);
-            }
-            const float dot = group_sum<L>(acc);
-            const float pred = __fadd_rn(__fadd_rn(__fadd_rn(p.mu, ub), ib), dot);
-            const float err = __fsub_rn(d.rating, pred);
-            if (mine) {
-#pragma unroll
-                for (int v = 0; v < V; ++v) {
-                    const float4 x = pv[v], y = qv[v];
-                    float4 nq;
-                    nq.x = __fmul_rn(lr, __fsub_rn(__fmul_rn(err, x.x), __fmul_rn(p.Q_reg, y.x)));
-                    nq.y = __fmul_rn(lr, __fsub_rn(__fmul_rn(err, x.y), __fmul_rn(p.Q_reg, y.y)));
-                    nq.z = __fmul_rn(lr, __fsub_rn(__fmul_rn(err, x.z), __fmul_rn(p.Q_reg, y.z)));
-                    nq.w = __fmul_rn(lr, __fsub_rn(__fmul_rn(err, x.w), __fmul_rn(p.Q_reg, y.w)));
-                    pv[v].x = __fadd_rn(x.x, __fmul_rn(lr, __fsub_rn(__fmul_rn(err, y.x), __fmul_rn(p.P_reg, x.x))));
-                    pv[v].y = __fadd_rn(x.y, __fmul_rn(lr, __fsub_rn(__fmul_rn(err, y.y), __fmul_rn(p.P_reg, x.y))));
-                    pv[v].z = __fadd_rn(x.z, __fmul_rn(lr, __fsub_rn(__fmul_rn(err, y.z), __fmul_rn(p.P_reg, x.z))));
-                    pv[v].w = __fadd_rn(x.w, __fmul_rn(lr, __fsub_rn(__fmul_rn(err, y.w), __fmul_rn(p.P_reg, x.w))));
-                    if (p.is_train && v * L + l < vecs) red_add_v4(Qv + qo + v * L, nq);
-                }
-                if (p.is_train && l == 0)
-                    red_add_f32(p.item_bias + d.item, __fmul_rn(lr, __fsub_rn(err, __fmul_rn(p.ib_reg, ib))));
-                ub = __fadd_rn(ub, __fmul_rn(lr, __fsub_rn(err, __fmul_rn(p.ub_reg, ub))));
-            }
+            user_side_update<L, V>(pv, ub, d.item, d.rating, mine, l, vecs, Qv, p.item_bias, p.mu, lr, sc, p.is_train);
         }
         if (mine) {
 #pragma unroll
@@ -167,6 +133,132 @@ mf_sgd_user_tiles(const UserTileParams p) {
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.empty[s]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// mf_sgd_user_rounds: the same schedule with the sampler fused into the update kernel.
+//
+// The draws of a round do not depend on the model (counter-based Philox keyed by (seed), counter
+// (user, iteration)), so the warp that owns a user can draw that user's `nb` ratings itself: the
+// 32 lanes evaluate the G * nb Philox counters of the warp's G users in parallel, gather
+// (item, rating) from the user's CSR row, and park the draws in a warp-private strip of shared
+// memory; the update loop then reads them back one per step (LDS broadcast). No sampler kernel,
+// no draw buffer in HBM, no producer warp: per round the kernel reads 2 indptr words + nb gathered
+// ratings per user and moves the P row once. Bit-identical draws to sample_user_major_kernel /
+// sample_per_user_kernel, hence the same updates as mf_sgd_user_tiles.
+// Work distribution: a warp claims kRoundClaim consecutive tiles (a tile = the warp's G users) at
+// a time from a global counter. The work per tile is uniform, the SMs are not (ncu: with a static
+// split some SMs idle for 20 % of the launch while others still run), so the claim is dynamic;
+// the next claim is issued one chunk ahead so that its round trip never stalls the warp.
+// ---------------------------------------------------------------------------------------------
+constexpr int kRoundWarps = 8;
+constexpr int kRoundDrawsPerWarp = 128;   // G * nb <= 128  (nb <= 128 at k = 128, 64 at k = 64, ...)
+constexpr int kRoundStrip = kRoundDrawsPerWarp + 32;  // + one pad draw per user row (bank spread)
+constexpr int kRoundClaim = 4;            // tiles per claim
+
+struct UserRoundParams {
+    const int *indptr;          // train CSR row pointers
+    const cu2b_rating *coo;     // train triplets in CSR order
+    const int *active_users;
+    const int *user_ids;        // DSGD strips: original user id (sampler key); else null
+    int n_active;
+    unsigned long long *tile_counter;  // zeroed before the launch
+    uint32_t seed;
+    int iter0, nb;              // absolute first iteration of the round, iterations in it
+    float *P, *Q, *user_bias, *item_bias;
+    int kp;
+    float mu;
+    const float *lr;
+    float P_reg, Q_reg, ub_reg, ib_reg;
+    int is_train;
+};
+
+// PF = 1: the item row of update j+1 is requested before update j is computed (one row of
+// look-ahead per lane group; a repeated item is re-read after the atomic add so that a user's
+// updates keep their exact sequential semantics). MINB = resident CTAs per SM the register
+// allocation is bounded for.
+template <int L, int V, int PF, int MINB>
+__global__ void __launch_bounds__(kRoundWarps * 32, MINB)
+mf_sgd_user_rounds(const UserRoundParams p) {
+    __shared__ DsgdDraw sh[kRoundWarps][kRoundStrip];
+    constexpr int G = 32 / L;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane / L, l = lane % L;
+    const int vecs = p.kp >> 2;
+    const float lr = __ldg(p.lr);
+    const StepCoef sc = step_coef(lr, p.P_reg, p.Q_reg, p.ub_reg, p.ib_reg);
+    float4 *const Pv = reinterpret_cast<float4 *>(p.P);
+    float4 *const Qv = reinterpret_cast<float4 *>(p.Q);
+    DsgdDraw *const strip = sh[warp];
+    const int pitch = p.nb + 1;
+    const int total = G * p.nb;
+    const int n_tiles = (p.n_active + G - 1) / G;
+    unsigned long long claim = 0;
+    if (lane == 0) claim = atomicAdd(p.tile_counter, (unsigned long long)kRoundClaim);
+    for (;;) {
+        const long long t0 = (long long)__shfl_sync(0xffffffffu, claim, 0);
+        if (t0 >= n_tiles) break;
+        if (lane == 0) claim = atomicAdd(p.tile_counter, (unsigned long long)kRoundClaim);  // consumed next time round
+        const int t1 = (int)min((long long)n_tiles, t0 + kRoundClaim);
+    for (int tile = (int)t0; tile < t1; ++tile) {
+        const int a0 = tile * G;
+        const int a = a0 + g;
+        const bool mine = a < p.n_active;
+        const int u = mine ? __ldg(p.active_users + a) : 0;
+        // the P row does not depend on the draws: its loads fly while the lanes sample
+        const size_t po = (size_t)u * vecs + l;
+        float4 pv[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+            pv[v] = (mine && v * L + l < vecs) ? __ldcg(Pv + po + v * L) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float ub = mine ? __ldcg(p.user_bias + u) : 0.f;
+        __syncwarp();  // the previous users' draws have been consumed
+        for (int i = lane; i < total; i += 32) {
+            const int slot = i / p.nb, t = i - slot * p.nb;
+            DsgdDraw d;
+            d.item = 0; d.rating = 0.f;
+            if (a0 + slot < p.n_active) {
+                const int uu = __ldg(p.active_users + a0 + slot);
+                const uint32_t uid = p.user_ids ? (uint32_t)__ldg(p.user_ids + uu) : (uint32_t)uu;
+                const int lo = __ldg(p.indptr + uu), hi = __ldg(p.indptr + uu + 1);
+                const uint32_t r = philox4x32_10_x(uid, (uint32_t)(p.iter0 + t), 0u, PHILOX_TAG, p.seed, PHILOX_KEY1);
+                const int j = lo + (int)__umulhi(r, (uint32_t)(hi - lo));
+                d.item = __ldg(&p.coo[j].item);
+                d.rating = __ldg(&p.coo[j].rating);
+            }
+            strip[slot * pitch + t] = d;
+        }
+        __syncwarp();
+        const DsgdDraw *row = strip + g * pitch;
+        if (PF) {
+            DsgdDraw d = row[0];
+            ItemSide<V> cur;
+            item_side_load<L, V>(cur, d.item, mine, l, vecs, Qv, p.item_bias);
+            for (int j = 0; j < p.nb; ++j) {  // every lane runs nb steps (the shuffles are warp-wide)
+                const bool more = j + 1 < p.nb;
+                const DsgdDraw dn = row[more ? j + 1 : j];
+                const bool repeat = dn.item == d.item;
+                ItemSide<V> nxt;
+                item_side_load<L, V>(nxt, dn.item, mine && more && !repeat, l, vecs, Qv, p.item_bias);
+                user_side_apply<L, V>(pv, ub, cur, d.item, d.rating, mine, l, vecs, Qv, p.item_bias, p.mu, lr, sc, p.is_train);
+                if (repeat) item_side_load<L, V>(nxt, dn.item, mine && more, l, vecs, Qv, p.item_bias);
+                cur = nxt;
+                d = dn;
+            }
+        } else {
+            for (int j = 0; j < p.nb; ++j) {
+                const DsgdDraw d = row[j];
+                user_side_update<L, V>(pv, ub, d.item, d.rating, mine, l, vecs, Qv, p.item_bias, p.mu, lr, sc, p.is_train);
+            }
+        }
+        if (mine) {
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+                if (v * L + l < vecs) __stcg(Pv + po + v * L, pv[v]);
+            if (l == 0) __stcg(p.user_bias + u, ub);
+        }
+    }
     }
 }
 

@@ -18,7 +18,8 @@
 //   ORC_FLAVOUR_REF    : the op order of matrix_factorization/mf_sequential.cu:114-141
 //                        (serial ascending-f dot product, unfused mul/add);
 //   ORC_FLAVOUR_KERNEL : the op order of our CUDA update kernels (per-lane fmaf partial sums,
-//                        xor-butterfly reduction over L lanes, same unfused update ops).
+//                        xor-butterfly reduction over L lanes; update steps with the learning
+//                        rate folded in, one multiply + one fma each -- see orc_sgd_update_one).
 //                        Used for the bit-exact check of the deterministic mode.
 //   ORC_FLAVOUR_LOSS_KERNEL : same, with the lane layout of the loss kernel (up to four float4
 //                        per lane so that several ratings share a warp).
@@ -228,6 +229,24 @@ float orc_sgd_update_one(float *p, float *q, float *ub, float *ib, float rating,
     const float lr = h->learning_rate;
     float ub0 = *ub, ib0 = *ib;
     float err = rating - orc_predict(p, q, k, ub0, ib0, mu, flavour);
+    if (flavour != ORC_FLAVOUR_REF) {
+        // Op order of the CUDA kernels (sgd_kernels.cuh, sgd_step): the learning rate is folded
+        // into the error and the regularisers once (a = lr*err, c = lr*reg), every step is one
+        // multiply + one fused multiply-add, and the row takes `old + step` with one rounding
+        // (an FADD in registers or the L2 atomic add). Algebraically mf_sequential.cu:129-141.
+        const float a = lr * err;
+        const float cP = lr * h->P_reg, cQ = lr * h->Q_reg;
+        const float cU = lr * h->user_bias_reg, cI = lr * h->item_bias_reg;
+        for (int f = 0; f < k; ++f) {
+            float p_old = p[f];
+            float q_old = q[f];
+            p[f] = p_old + fmaf(a, q_old, -(cP * p_old));
+            if (h->is_train) q[f] = q_old + fmaf(a, p_old, -(cQ * q_old));
+        }
+        *ub = ub0 + fmaf(-cU, ub0, a);
+        if (h->is_train) *ib = ib0 + fmaf(-cI, ib0, a);
+        return err;
+    }
     for (int f = 0; f < k; ++f) {
         float p_old = p[f];
         float q_old = q[f];

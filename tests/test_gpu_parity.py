@@ -347,6 +347,53 @@ def test_training_rmse_parity_vs_oracle_trainer(k, round_iters):
     assert out["stats"]["updates"] == iters * U
 
 
+def _disjoint_items_problem(U, d, seed=5):
+    """Every item is rated by exactly one user: users never touch a common row, so ANY Hogwild
+    schedule must equal the sequential restatement bit for bit (sampler + update arithmetic)."""
+    rng = np.random.RandomState(seed)
+    deg = rng.randint(1, d + 1, U)
+    deg[0] = 1  # a one-rating user: every draw repeats the item (look-ahead re-read path)
+    n = int(deg.sum())
+    r = np.zeros(n, dtype=cu.RATING_DTYPE)
+    r["user"] = np.repeat(np.arange(U), deg)
+    r["item"] = rng.permutation(n)
+    r["rating"] = rng.randint(1, 6, n)
+    order = np.lexsort((r["item"], r["user"]))
+    return r[order], n
+
+
+@pytest.mark.parametrize("k,round_iters,variant", [
+    (128, 32, {}), (128, 32, {"CU2B_TUNE_PF": "1"}), (128, 7, {"CU2B_TUNE_MINB": "8"}), (64, 32, {}),
+    (64, 48, {"CU2B_TUNE_PF": "1"}), (32, 32, {}), (50, 16, {"CU2B_TUNE_PF": "1"}), (8, 8, {}), (3, 4, {"CU2B_TUNE_PF": "1"}),
+    (200, 32, {}), (256, 20, {"CU2B_TUNE_PF": "1"}), (128, 32, {"CU2B_TILE_PIPE": "tma"}), (32, 16, {"CU2B_TILE_PIPE": "tma"}),
+    (128, 1, {})])
+def test_user_major_schedules_bit_exact_on_disjoint_items(k, round_iters, variant, monkeypatch):
+    """mf_sgd_user_rounds (sampler fused into the update kernel; with and without item-row
+    look-ahead), mf_sgd_user_tiles (separate sampler + TMA tiles) and mf_sgd_hogwild (round 1)
+    against the sequential CPU restatement, KERNEL flavour: identical bits in P, Q and both biases
+    after 45 iterations (rounds of uneven length included)."""
+    for name, val in variant.items():
+        monkeypatch.setenv(name, val)
+    U = 700
+    tr, I = _disjoint_items_problem(U, 6)
+    te = tr[::3].copy()
+    mtr, mte = cu.createSparseMatrix(tr, U, I), cu.createSparseMatrix(te, U, I)
+    mu = np.float32(3.0)
+    iters = 45
+    init = lambda n: cu.initialize_normal_array(n, k)
+    P, Q, ub, ib = init(U * k), init(I * k), init(U), init(I)
+    cfg = cu.Config(total_iterations=iters, n_factors=k, check_error=20, round_iters=round_iters)
+    with cu.Session(mtr, mte, cfg, P, Q, ub, ib, mu) as s:
+        s.run(iters)
+        got = s.download()
+        glog = s.log()
+    oP, oQ, oub, oib, olog = O.train((mtr.indptr, mtr.indices, mtr.data), (mte.indptr, mte.indices, mte.data), P, Q, ub, ib, mu,
+                                     O.hyper(k), 42, iters, check_error=20, flavour=O.FLAVOUR_KERNEL)
+    for g, w, name in zip(got, (oP, oQ, oub, oib), ("P", "Q", "user_bias", "item_bias")):
+        assert np.array_equal(np.asarray(g).ravel().view(np.uint32), w.view(np.uint32)), name
+    assert [r["iteration"] for r in glog] == [r["iteration"] for r in olog]
+
+
 def test_training_schedule_on_device_follows_reference_rule():
     """training.cu:129,146-155 evaluated on the device: replaying the rule on the validation RMSE
     sequence the run itself logged must reproduce the logged learning rates exactly. The

@@ -37,6 +37,7 @@ for v in variants:
         st = s.stats()
         ev = s.eval()
     print(json.dumps({"variant": v, "sgd_Gups": st["updates"] / st["sgd_ms"] / 1e6, "sgd_ms": st["sgd_ms"],
+                      "total_Gups": st["updates"] / st["total_ms"] / 1e6, "sampler_ms": st["sampler_ms"],
                       "test_rmse": ev["test_rmse"]}), flush=True)
     for kv in parts[1:]:
         os.environ.pop(kv.split("=")[0], None)
