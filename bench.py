@@ -491,6 +491,8 @@ def run_ours_dsgd(args, rank, world):
     updates = sumreduce(st["updates"])
     sgd_ms_max = maxreduce(st["sgd_ms"])
     sampler_ms_max, loss_ms_max = maxreduce(st["sampler_ms"]), maxreduce(st["loss_ms"])
+    wait_ms_max, send_ms_max = maxreduce(st["wait_ms"]), maxreduce(st["send_ms"])
+    wait_ms_min = -maxreduce(-st["wait_ms"])
     launches = sumreduce(st["kernel_launches"])
     value = updates / dev_s
     bytes_per_update = 16 * k + 12
@@ -548,7 +550,10 @@ def run_ours_dsgd(args, rank, world):
             "gpu_launches": int(launches), "clocks": clk,
             "breakdown_ms_per_step_max_rank": {"sgd_subepochs": sgd_ms_max / args.steps, "sampler": sampler_ms_max / args.steps,
                                                "loss_check_incl_gather": loss_ms_max / args.steps,
-                                               "handoff_waits_and_sends": (dev_s * 1e3 - sgd_ms_max - sampler_ms_max - loss_ms_max) / args.steps},
+                                               "handoff_waits_and_sends": (dev_s * 1e3 - sgd_ms_max - sampler_ms_max - loss_ms_max) / args.steps,
+                                               "wait_kernels_max_rank": wait_ms_max / args.steps,
+                                               "wait_kernels_min_rank": wait_ms_min / args.steps,
+                                               "send_kernels_max_rank": send_ms_max / args.steps},
             "test_rmse": [round(r["test_rmse"], 5) for r in lg], "e2e_test_rmse": e2e_rmse,
             "loss_allreduce_check": {"nccl_train_rmse": nccl_rmse, "peer_memory_train_rmse": lg[-1]["train_rmse"]},
             "block_nnz_imbalance": float(part.block_nnz.max() / part.block_nnz.mean()),

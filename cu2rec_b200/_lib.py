@@ -38,7 +38,7 @@ class Metrics(C.Structure):  # cu2b_metrics
 class Stats(C.Structure):  # cu2b_stats
     _fields_ = [("sgd_ms", C.c_double), ("loss_ms", C.c_double), ("sampler_ms", C.c_double),
                 ("total_ms", C.c_double), ("updates", C.c_int64), ("kernel_launches", C.c_int64),
-                ("sgd_launches", C.c_int64)]
+                ("sgd_launches", C.c_int64), ("wait_ms", C.c_double), ("send_ms", C.c_double)]
 
 
 # every symbol include/cu2b.h declares: name -> (restype, argtypes)

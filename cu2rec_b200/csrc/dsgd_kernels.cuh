@@ -48,6 +48,14 @@ struct __align__(8) DsgdDraw {
     float rating;
 };
 
+// Issue-order-pinned load of a draw (volatile asm, like ldcg_pinned): the prefetch of the next
+// draw stays ahead of the current update's item-row loads.
+__device__ __forceinline__ DsgdDraw ld_draw_pinned(const DsgdDraw *p) {
+    DsgdDraw d;
+    asm volatile("ld.global.nc.v2.b32 {%0, %1}, [%2];" : "=r"(d.item), "=f"(d.rating) : "l"(p) : "memory");
+    return d;
+}
+
 // Sampler of one DSGD round (nb reference iterations): one WARP per active user draws that
 // user's nb ratings (same Philox stream as the single-GPU sampler, keyed by the original user
 // id) and writes them to the user's row of `draws` grouped by item block, iteration order kept
@@ -130,6 +138,7 @@ struct UserRunParams {
     const int *row_off;   // [n_active][world + 1]
     const int *active_users;
     int n_active, pitch, world, block;
+    unsigned long long *tile_counter;  // dynamic tile claims (a tile = the G users of one warp); zeroed before launch
     float *P, *Q, *user_bias, *item_bias;
     int kp;
     float mu;
@@ -143,14 +152,24 @@ __global__ void __launch_bounds__(256)
 mf_sgd_user_runs(const UserRunParams p) {
     constexpr int G = 32 / L;
     const int lane = threadIdx.x & 31, g = lane / L, l = lane % L;
-    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int n_groups = ((gridDim.x * blockDim.x) >> 5) * G;
     const int vecs = p.kp >> 2;
     const float lr = __ldg(p.lr);
     const StepCoef sc = step_coef(lr, p.P_reg, p.Q_reg, p.ub_reg, p.ib_reg);
     float4 *const Pv = reinterpret_cast<float4 *>(p.P);
     float4 *const Qv = reinterpret_cast<float4 *>(p.Q);
-    for (int a0 = warp_global * G; a0 < p.n_active; a0 += n_groups) {
+    // Warps claim kRunClaim consecutive tiles at a time; the next claim is issued one chunk ahead.
+    // (The SMs do not run at one speed; a static split leaves the fast ones idle at the end.)
+    constexpr int kRunClaim = 4;
+    const int n_tiles = (p.n_active + G - 1) / G;
+    unsigned long long claim = 0;
+    if (lane == 0) claim = atomicAdd(p.tile_counter, (unsigned long long)kRunClaim);
+    for (;;) {
+        const long long t0 = (long long)__shfl_sync(0xffffffffu, claim, 0);
+        if (t0 >= n_tiles) break;
+        if (lane == 0) claim = atomicAdd(p.tile_counter, (unsigned long long)kRunClaim);
+        const int t1 = (int)min((long long)n_tiles, t0 + kRunClaim);
+    for (int tile = (int)t0; tile < t1; ++tile) {
+        const int a0 = tile * G;
         const int a = a0 + g;
         int j = 0, end = 0, u = 0;
         if (a < p.n_active) {
@@ -167,15 +186,19 @@ mf_sgd_user_runs(const UserRunParams p) {
             pv[v] = (mine && v * L + l < vecs) ? __ldcg(Pv + po + v * L) : make_float4(0.f, 0.f, 0.f, 0.f);
         float ub = mine ? __ldcg(p.user_bias + u) : 0.f;
         const DsgdDraw *row = p.draws + (size_t)a * p.pitch;
-        DsgdDraw nxt;
+        // The draws are fetched two updates ahead: a draw is not part of the item row's
+        // read -> atomic-add window, and with two updates of slack its L2 round trip never
+        // delays the row request of the update that consumes it.
+        DsgdDraw nxt, nxt2;
         nxt.item = 0; nxt.rating = 0.f;
-        if (mine) nxt = row[j];
+        nxt2 = nxt;
+        if (mine) nxt = ld_draw_pinned(row + j);
+        if (j + 1 < end) nxt2 = ld_draw_pinned(row + j + 1);
         while (__any_sync(0xffffffffu, j < end)) {
             const bool ok = j < end;
             const DsgdDraw d = nxt;
-            // the next draw is fetched one update ahead: it is not part of the item row's
-            // read -> atomic-add window, so it shortens the update without adding staleness
-            if (j + 1 < end) nxt = row[j + 1];
+            nxt = nxt2;
+            if (j + 2 < end) nxt2 = ld_draw_pinned(row + j + 2);
             user_side_update<L, V>(pv, ub, d.item, d.rating, ok, l, vecs, Qv, p.item_bias, p.mu, lr, sc, p.is_train);
             ++j;
         }
@@ -185,6 +208,7 @@ mf_sgd_user_runs(const UserRunParams p) {
                 if (v * L + l < vecs) __stcg(Pv + po + v * L, pv[v]);
             if (l == 0) __stcg(p.user_bias + u, ub);
         }
+    }
     }
 }
 

@@ -531,7 +531,7 @@ int pick_chunk(long long per_segment, int resident_ctas) {
 }
 
 struct Timing {  // CUDA-event stopwatch per kernel family, resolved after a stream sync
-    enum Kind { SGD = 0, LOSS = 1, SAMPLER = 2, TOTAL = 3, NKIND = 4 };
+    enum Kind { SGD = 0, LOSS = 1, SAMPLER = 2, TOTAL = 3, WAIT = 4, SEND = 5, NKIND = 6 };
     struct Span { cudaEvent_t a, b; int kind; };
     std::vector<Span> spans;
     std::vector<cudaEvent_t> pool;
@@ -1142,7 +1142,7 @@ extern "C" cu2b_status cu2b_session_run(cu2b_session *s, int n_iterations) {
     CUDA_TRY(cudaStreamSynchronize(s->stream));  // the only host sync of the loop
     s->iter_done = end;
     CU2B_TRY(check_device_error(s));
-    double ms[Timing::NKIND] = {0, 0, 0, 0};
+    double ms[Timing::NKIND] = {0, 0, 0, 0, 0, 0};
     s->timing.collect(ms);
     s->stats.sgd_ms += ms[Timing::SGD];
     s->stats.loss_ms += ms[Timing::LOSS];
@@ -1159,7 +1159,7 @@ extern "C" cu2b_status cu2b_session_eval(cu2b_session *s, float *train_mae, floa
     DevState st;
     CUDA_TRY(cudaMemcpyAsync(&st, s->state, sizeof(st), cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
-    double ms[Timing::NKIND] = {0, 0, 0, 0};
+    double ms[Timing::NKIND] = {0, 0, 0, 0, 0, 0};
     s->timing.collect(ms);
     s->stats.loss_ms += ms[Timing::LOSS];
     if (train_rmse) *train_rmse = (float)sqrt(st.sums[0] / (double)s->train.nnz);

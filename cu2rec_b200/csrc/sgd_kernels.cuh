@@ -132,14 +132,31 @@ struct ItemSide {
     float4 q[V];
     float ib;
 };
+// Issue-order-pinned L2 loads (ld.global.cg as volatile asm): the item bias and the item row are
+// requested back to back at the top of an update. Left to the scheduler, the bias load of the
+// DSGD kernel was issued only after the dot-product butterfly, which put a second L2 round trip
+// into every update's read -> atomic-add window (measured: 0.77 us -> see profiles/r1_dsgd_window.jsonl).
+__device__ __forceinline__ float ldcg_pinned(const float *p) {
+    float v;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ldcg_pinned(const float4 *p) {
+    float4 v;
+    asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
 template <int L, int V>
 __device__ __forceinline__ void item_side_load(ItemSide<V> &it, int item, bool ok, int l, int vecs, const float4 *Qv,
                                                const float *item_bias) {
     const size_t qo = (size_t)item * vecs + l;
+    it.ib = 0.f;
+    if (ok) it.ib = ldcg_pinned(item_bias + item);
 #pragma unroll
-    for (int v = 0; v < V; ++v)
-        it.q[v] = (ok && v * L + l < vecs) ? __ldcg(Qv + qo + v * L) : make_float4(0.f, 0.f, 0.f, 0.f);
-    it.ib = ok ? __ldcg(item_bias + item) : 0.f;
+    for (int v = 0; v < V; ++v) {
+        it.q[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok && v * L + l < vecs) it.q[v] = ldcg_pinned(Qv + qo + v * L);
+    }
 }
 // The arithmetic of one update given its operands; P slice and user bias are updated in place,
 // the item row and item bias take their steps as L2 atomic adds.

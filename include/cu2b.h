@@ -190,6 +190,8 @@ typedef struct cu2b_stats {
     int64_t updates;        /* rating updates performed */
     int64_t kernel_launches;
     int64_t sgd_launches;
+    double wait_ms;         /* DSGD: device time spent waiting for a peer's item block / loss sums */
+    double send_ms;         /* DSGD: device time of the peer-memory hand-off kernels */
 } cu2b_stats;
 
 /* One call = the reference's train(): uploads the matrices, trains cfg->total_iterations
