@@ -49,6 +49,9 @@ WORKLOADS = {
     "netflix": (480189, 17770, 100480507, True, 128),
     "ml20m": (138493, 26744, 20000263, False, 64),
     "ml100k": (943, 1682, 100000, False, 32),
+    # one DSGD item block of the netflix shape at 8 GPUs (all users, 1/8 of the items and ratings):
+    # single-GPU stand-in for the item-popularity concentration a rank sees inside a sub-epoch
+    "nfblock8": (480189, 2221, 12560000, True, 128),
 }
 DATA_SEED = 20240607
 METRIC = "sgd_rating_updates_per_sec"
@@ -573,7 +576,7 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="netflix", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="netflix", choices=sorted(WORKLOADS))  # nfblock8: tools only
     ap.add_argument("--k", type=int, default=0)
     ap.add_argument("--iters-per-step", type=int, default=500)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
