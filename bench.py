@@ -383,23 +383,41 @@ def run_ours(args):
 
     oP, oQ, oub, oib = pin(P0), pin(Q0), pin(ub0), pin(ib0)  # page-locked result buffers
 
-    def e2e_once():
+    def e2e_cold_once():  # everything a first train() call pays: allocation, set-up, teardown
         with cu.Session(ptr, pte, cfg_e, hP, hQ, hub, hib, mu) as s:
             s.run(T)
             out = s.download(out=(oP, oQ, oub, oib))
             rm = s.log()[-1]["test_rmse"]
         return out, rm
 
-    e2e_once()  # warm-up
-    e2e_times = []
-    for _ in range(e2e_steps):
-        t0 = time.perf_counter()
-        _, e2e_rmse = e2e_once()
-        e2e_times.append(time.perf_counter() - t0)
-    e2e_s = float(np.median(e2e_times))  # >= 3 repeats, median (host-side jitter on a shared box)
+    def median_ms(fn, reps):
+        fn()  # warm-up
+        ts, last = [], None
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            last = fn()
+            ts.append(time.perf_counter() - t0)
+        return float(np.median(ts)), [round(1e3 * t, 2) for t in ts], last
+
+    # e2e: a resident session (buffers allocated once), and per step the H2D of that step's inputs
+    # (both rating matrices + the initial model, pinned), T iterations, the D2H of the result
+    sess_e = cu.Session(ptr, pte, cfg_e, hP, hQ, hub, hib, mu)
+
+    def e2e_once():
+        sess_e.reload(ptr, pte, hP, hQ, hub, hib, mu)
+        sess_e.run(T)
+        out = sess_e.download(out=(oP, oQ, oub, oib))
+        return out, sess_e.log()[-1]["test_rmse"]
+
+    e2e_s, e2e_all, (_, e2e_rmse) = median_ms(e2e_once, e2e_steps)  # >= 3 repeats, median
+    sess_e.close()
+    cold_s, cold_all, _ = median_ms(e2e_cold_once, 3)
     e2e = {"value": T * U / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "ms_per_step": 1e3 * e2e_s, "steps": e2e_steps, "ms_all_steps": [round(1e3 * t, 2) for t in e2e_times],
-           "what": "cu2b_session_create(host CSR + model, pinned) + %d iterations + download + destroy" % T}
+           "ms_per_step": 1e3 * e2e_s, "steps": e2e_steps, "ms_all_steps": e2e_all,
+           "what": "resident session; per step: cu2b_session_reload (H2D of both rating matrices + initial model from "
+                   "pinned host memory) + %d iterations + download (D2H of P, Q, biases)" % T,
+           "cold": {"value": T * U / cold_s, "ms_per_step": 1e3 * cold_s, "ms_all_steps": cold_all,
+                    "what": "cu2b_session_create + %d iterations + download + destroy (allocation and set-up included)" % T}}
 
     # ---- CPU baseline (rank 0, bounded sample) -----------------------------------------------
     cpu = None
@@ -523,22 +541,29 @@ def run_ours_dsgd(args, rank, world):
 
     outs = tuple(pin(a) for a in (inp.P, inp.Q, inp.user_bias, inp.item_bias))  # page-locked result buffers
 
+    # e2e: resident contexts (buffers, IPC mappings and flags set up once); per step every rank
+    # uploads its strips + the initial model from pinned host memory, the ranks synchronise, run T
+    # iterations and download their strips
+    de = make(T, pinp)
+
     def e2e_once():
-        de = make(T, pinp)
+        de.reload(pinp, mu)
+        dist.barrier()
         de.run(T)
         de.download(out=outs)
-        rm = de.log()[-1]["test_rmse"]
-        de.close()
-        return rm
+        return de.log()[-1]["test_rmse"]
 
     e2e_once()
-    e2e_steps = max(1, min(args.steps, 3))
-    dist.barrier()
-    t0 = time.perf_counter()
+    e2e_steps = max(3, min(args.steps + 1, 5))
+    times = []
     for _ in range(e2e_steps):
+        dist.barrier()
+        t0 = time.perf_counter()
         e2e_rmse = e2e_once()
-    dist.barrier()
-    e2e_s = maxreduce((time.perf_counter() - t0) / e2e_steps)
+        dist.barrier()
+        times.append(maxreduce(time.perf_counter() - t0))
+    e2e_s = float(np.median(times))
+    de.close()
     h2d_all, d2h_all = sumreduce(h2d), sumreduce(d2h)
     if rank == 0:
         line = {
@@ -550,8 +575,9 @@ def run_ours_dsgd(args, rank, world):
             "roofline": roofline, "cpu_baseline": None,
             "e2e": {"value": T * U / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all),
                     "ms_per_step": 1e3 * e2e_s, "steps": e2e_steps,
-                    "what": "per rank: cu2b_dsgd_create(pinned host strips + model) + handle exchange + %d iterations "
-                            "+ download + destroy; max over ranks" % T},
+                    "ms_all_steps": [round(1e3 * t, 2) for t in times],
+                    "what": "resident DSGD contexts; per step and rank: cu2b_dsgd_reload (H2D of the rank's strips + "
+                            "initial model, pinned) + barrier + %d iterations + download; max over ranks" % T},
             "gpu_launches": int(launches), "clocks": clk,
             "breakdown_ms_per_step_max_rank": {"sgd_subepochs": sgd_ms_max / args.steps, "sampler": sampler_ms_max / args.steps,
                                                "loss_check_incl_gather": loss_ms_max / args.steps,

@@ -298,6 +298,13 @@ class Session:
     def run(self, n_iterations):
         check(self.lib.cu2b_session_run(self.h, n_iterations))
 
+    def reload(self, train_matrix, test_matrix, P, Q, user_bias, item_bias, global_bias):
+        """Start over on same-shaped data with a new initial model (cu2b_session_reload)."""
+        P, Q, ub, ib = _f32(P), _f32(Q), _f32(user_bias), _f32(item_bias)
+        tm, te = train_matrix.c(), test_matrix.c()
+        check(self.lib.cu2b_session_reload(self.h, C.byref(tm), C.byref(te), _ptr(P), _ptr(Q), _ptr(ub), _ptr(ib),
+                                           float(global_bias)))
+
     def eval(self):
         v = [C.c_float() for _ in range(4)]
         check(self.lib.cu2b_session_eval(self.h, *[C.byref(x) for x in v]))
@@ -442,6 +449,14 @@ class Dsgd:
 
     def run(self, n_iterations):
         check(self.lib.cu2b_dsgd_run(self.h, n_iterations))
+
+    def reload(self, inputs, global_bias):
+        """Same-shaped strips + a new initial model into the existing context (cu2b_dsgd_reload).
+        Synchronise the ranks (a host barrier) before the next run()."""
+        self._keep = inputs
+        tm, te = inputs.train.c(), inputs.test.c()
+        check(self.lib.cu2b_dsgd_reload(self.h, C.byref(tm), C.byref(te), _ptr(inputs.P), _ptr(inputs.Q),
+                                        _ptr(inputs.user_bias), _ptr(inputs.item_bias), float(global_bias)))
 
     def _session(self):
         return C.c_void_p(self.lib.cu2b_dsgd_session(self.h))

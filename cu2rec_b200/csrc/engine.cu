@@ -185,16 +185,25 @@ struct MatrixUpload {
     float *tmp_d = nullptr;
 };
 
-cu2b_status matrix_alloc(DevPool &pool, const cu2b_csr *m, DevMatrix *out, MatrixUpload *up) {
+// reuse: `out` already owns buffers of exactly this shape (session reload); only the staging
+// buffers are allocated.
+cu2b_status matrix_alloc(DevPool &pool, const cu2b_csr *m, DevMatrix *out, MatrixUpload *up, bool reuse = false) {
     CU2B_TRY(validate_csr(m, "upload_matrix"));
-    out->rows = m->rows;
-    out->cols = m->cols;
-    out->nnz = m->nonzeros;
     const size_t nnz = (size_t)m->nonzeros;
     up->m = m;
     up->out = out;
-    CU2B_TRY(pool.alloc(&out->indptr, (size_t)m->rows + 1));
-    CU2B_TRY(pool.alloc(&out->coo, nnz + kChunkMax + 4));
+    if (reuse) {
+        if (out->rows != m->rows || out->cols != m->cols || out->nnz != m->nonzeros)
+            return cu2b_fail(CU2B_ERR_INVALID, "reload: the matrix shape (%d x %d, %lld ratings) differs from the one the "
+                             "session was created with (%d x %d, %lld)", m->rows, m->cols, (long long)m->nonzeros,
+                             out->rows, out->cols, out->nnz);
+    } else {
+        out->rows = m->rows;
+        out->cols = m->cols;
+        out->nnz = m->nonzeros;
+        CU2B_TRY(pool.alloc(&out->indptr, (size_t)m->rows + 1));
+        CU2B_TRY(pool.alloc(&out->coo, nnz + kChunkMax + 4));
+    }
     if (!m->on_device && nnz > 0) {
         CU2B_TRY(pool.alloc(&up->tmp_i, nnz));
         CU2B_TRY(pool.alloc(&up->tmp_d, nnz));
@@ -904,6 +913,81 @@ cu2b_status enqueue_sgd_iterations(cu2b_session *s, int iter_abs, int n_seg) {
 
 }  // namespace
 
+// Device-resident schedule state as train() starts it (training.cu:102-103) + host counters.
+static cu2b_status session_reset_state(cu2b_session *s) {
+    DevState st;
+    memset(&st, 0, sizeof(st));
+    st.lr = s->cfg.learning_rate;
+    st.current_patience = (int)s->cfg.patience;  // training.cu:103
+    st.patience0 = (int)s->cfg.patience;
+    st.lr_decay = s->cfg.learning_rate_decay;
+    st.validation_rmse = FLT_MAX;                // training.cu:102
+    st.n_log = 0;
+    st.log_cap = s->log_cap;
+    CUDA_TRY(cudaMemcpyAsync(s->state, &st, sizeof(st), cudaMemcpyHostToDevice, s->stream));
+    if (s->gate) CUDA_TRY(cudaMemsetAsync(s->gate, 0, (size_t)s->chunks_per_seg * sizeof(int), s->stream));
+    s->iter_done = 0;
+    s->segs_done = 0;
+    s->blocked_budget = 0;
+    memset(&s->stats, 0, sizeof(s->stats));
+    return CU2B_OK;
+}
+
+// Host -> device traffic of a session: both rating matrices (copy + COO expansion), the active
+// user list and the model. All copies go through one copy stream; the compute stream only waits
+// for the buffer it is about to touch (the COO expansion of the training matrix overlaps the
+// upload of the model and of the test matrix). reload = the session's buffers exist already.
+static cu2b_status session_upload(cu2b_session *s, const cu2b_csr *train, const cu2b_csr *test, const float *P,
+                                  const float *Q, const float *user_bias, const float *item_bias, bool reload) {
+    struct CopyLane {
+        cudaStream_t st = nullptr;
+        cudaEvent_t ev = nullptr;
+        ~CopyLane() {
+            if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+            if (ev) cudaEventDestroy(ev);
+        }
+    } lane;
+    CUDA_TRY(cudaStreamCreateWithFlags(&lane.st, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&lane.ev, cudaEventDisableTiming));
+    std::vector<int> indptr_host;
+    CU2B_TRY(host_indptr(train, s->stream, &indptr_host));
+    // users with at least one training rating (sgd.cu:35 skips the others)
+    std::vector<int> active;
+    active.reserve(s->rows);
+    for (int u = 0; u < s->rows; ++u)
+        if (indptr_host[u + 1] > indptr_host[u]) active.push_back(u);
+    if (reload && (int)active.size() != s->n_active)
+        return cu2b_fail(CU2B_ERR_INVALID, "reload: %d users have training ratings, the session was created with %d "
+                         "(launch geometry depends on it)", (int)active.size(), s->n_active);
+    s->n_active = (int)active.size();
+    // 1. every allocation, in stream order on the compute stream
+    MatrixUpload up_train, up_test;
+    CU2B_TRY(matrix_alloc(s->pool, train, &s->train, &up_train, reload));
+    CU2B_TRY(matrix_alloc(s->pool, test, &s->test, &up_test, reload));
+    if (!reload) {
+        CU2B_TRY(s->pool.alloc(&s->active, (size_t)std::max(1, s->rows)));
+        CU2B_TRY(s->pool.alloc(&s->P, (size_t)s->rows * s->kp));
+        CU2B_TRY(s->pool.alloc(&s->Q, (size_t)s->cols * s->kp));
+        CU2B_TRY(s->pool.alloc(&s->ub, (size_t)s->rows));
+        CU2B_TRY(s->pool.alloc(&s->ib, (size_t)s->cols));
+    }
+    CU2B_TRY(stream_after(lane.st, s->stream, lane.ev));
+    // 2. copies back to back on the copy stream; each expansion waits only for its own matrix
+    if (!active.empty())  // pageable source: staged synchronously, so it goes first
+        CUDA_TRY(cudaMemcpyAsync(s->active, active.data(), active.size() * sizeof(int), cudaMemcpyHostToDevice, lane.st));
+    CU2B_TRY(matrix_copy(lane.st, up_train));
+    CU2B_TRY(stream_after(s->stream, lane.st, lane.ev));
+    CU2B_TRY(matrix_expand(s->pool, s->stream, up_train));
+    CU2B_TRY(upload_dense(lane.st, s->P, P, s->rows, s->k, s->kp));
+    CU2B_TRY(upload_dense(lane.st, s->Q, Q, s->cols, s->k, s->kp));
+    CUDA_TRY(cudaMemcpyAsync(s->ub, user_bias, (size_t)s->rows * sizeof(float), cudaMemcpyHostToDevice, lane.st));
+    CUDA_TRY(cudaMemcpyAsync(s->ib, item_bias, (size_t)s->cols * sizeof(float), cudaMemcpyHostToDevice, lane.st));
+    CU2B_TRY(matrix_copy(lane.st, up_test));
+    CU2B_TRY(stream_after(s->stream, lane.st, lane.ev));
+    CU2B_TRY(matrix_expand(s->pool, s->stream, up_test));
+    return CU2B_OK;
+}
+
 static cu2b_status session_create_impl(cu2b_session **out, int device, const cu2b_csr *train,
                                        const cu2b_csr *test, const cu2b_config *cfg, const float *P,
                                        const float *Q, const float *user_bias, const float *item_bias,
@@ -944,50 +1028,7 @@ static cu2b_status session_create_impl(cu2b_session **out, int device, const cu2
 
     Trace tr("session_create");
     tr.mark("setup");
-    // All host->device copies go through one copy stream; the compute stream only waits for the
-    // buffer it is about to touch (the COO expansion of the training matrix overlaps the upload
-    // of the model and of the test matrix).
-    struct CopyLane {
-        cudaStream_t st = nullptr;
-        cudaEvent_t ev = nullptr;
-        ~CopyLane() {
-            if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
-            if (ev) cudaEventDestroy(ev);
-        }
-    } lane;
-    CUDA_TRY(cudaStreamCreateWithFlags(&lane.st, cudaStreamNonBlocking));
-    CUDA_TRY(cudaEventCreateWithFlags(&lane.ev, cudaEventDisableTiming));
-    std::vector<int> indptr_host;
-    CU2B_TRY(host_indptr(train, s->stream, &indptr_host));
-    // users with at least one training rating (sgd.cu:35 skips the others)
-    std::vector<int> active;
-    active.reserve(s->rows);
-    for (int u = 0; u < s->rows; ++u)
-        if (indptr_host[u + 1] > indptr_host[u]) active.push_back(u);
-    s->n_active = (int)active.size();
-    // 1. every allocation, in stream order on the compute stream
-    MatrixUpload up_train, up_test;
-    CU2B_TRY(matrix_alloc(s->pool, train, &s->train, &up_train));
-    CU2B_TRY(matrix_alloc(s->pool, test, &s->test, &up_test));
-    CU2B_TRY(s->pool.alloc(&s->active, active.size()));
-    CU2B_TRY(s->pool.alloc(&s->P, (size_t)s->rows * s->kp));
-    CU2B_TRY(s->pool.alloc(&s->Q, (size_t)s->cols * s->kp));
-    CU2B_TRY(s->pool.alloc(&s->ub, (size_t)s->rows));
-    CU2B_TRY(s->pool.alloc(&s->ib, (size_t)s->cols));
-    CU2B_TRY(stream_after(lane.st, s->stream, lane.ev));
-    // 2. copies back to back on the copy stream; each expansion waits only for its own matrix
-    if (!active.empty())  // pageable source: staged synchronously, so it goes first
-        CUDA_TRY(cudaMemcpyAsync(s->active, active.data(), active.size() * sizeof(int), cudaMemcpyHostToDevice, lane.st));
-    CU2B_TRY(matrix_copy(lane.st, up_train));
-    CU2B_TRY(stream_after(s->stream, lane.st, lane.ev));
-    CU2B_TRY(matrix_expand(s->pool, s->stream, up_train));
-    CU2B_TRY(upload_dense(lane.st, s->P, P, s->rows, s->k, s->kp));
-    CU2B_TRY(upload_dense(lane.st, s->Q, Q, s->cols, s->k, s->kp));
-    CUDA_TRY(cudaMemcpyAsync(s->ub, user_bias, (size_t)s->rows * sizeof(float), cudaMemcpyHostToDevice, lane.st));
-    CUDA_TRY(cudaMemcpyAsync(s->ib, item_bias, (size_t)s->cols * sizeof(float), cudaMemcpyHostToDevice, lane.st));
-    CU2B_TRY(matrix_copy(lane.st, up_test));
-    CU2B_TRY(stream_after(s->stream, lane.st, lane.ev));
-    CU2B_TRY(matrix_expand(s->pool, s->stream, up_test));
+    CU2B_TRY(session_upload(s, train, test, P, Q, user_bias, item_bias, false));
     tr.mark("uploads + COO expansion");
     // kernels and their persistent grid sizes
     s->sgd_kernel = pick_sgd(s->L, s->V);
@@ -1091,16 +1132,7 @@ static cu2b_status session_create_impl(cu2b_session **out, int device, const cu2
     s->log_cap = cfg->total_iterations / cfg->check_error + 8;
     CU2B_TRY(s->pool.alloc(&s->log_dev, (size_t)s->log_cap));
     CU2B_TRY(s->pool.alloc(&s->state, 1));
-    DevState st;
-    memset(&st, 0, sizeof(st));
-    st.lr = cfg->learning_rate;
-    st.current_patience = (int)cfg->patience;  // training.cu:103
-    st.patience0 = (int)cfg->patience;
-    st.lr_decay = cfg->learning_rate_decay;
-    st.validation_rmse = FLT_MAX;              // training.cu:102
-    st.n_log = 0;
-    st.log_cap = s->log_cap;
-    CUDA_TRY(cudaMemcpyAsync(s->state, &st, sizeof(st), cudaMemcpyHostToDevice, s->stream));
+    CU2B_TRY(session_reset_state(s));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     tr.mark("stream/loss buffers + state");
     *out = guard.release();
@@ -1149,6 +1181,33 @@ extern "C" cu2b_status cu2b_session_run(cu2b_session *s, int n_iterations) {
     s->stats.sampler_ms += ms[Timing::SAMPLER];
     s->stats.total_ms += ms[Timing::TOTAL];
     return CU2B_OK;
+}
+
+static cu2b_status session_reload_impl(cu2b_session *s, const cu2b_csr *train, const cu2b_csr *test, const float *P,
+                                       const float *Q, const float *user_bias, const float *item_bias,
+                                       float global_bias) {
+    if (!s || !P || !Q || !user_bias || !item_bias) return cu2b_fail(CU2B_ERR_INVALID, "reload: null argument");
+    if (s->cfg.mode != CU2B_MODE_HOGWILD)
+        return cu2b_fail(CU2B_ERR_UNSUPPORTED, "reload: the deterministic mode builds its block schedule at creation");
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (s->sampler_stream) CUDA_TRY(cudaStreamSynchronize(s->sampler_stream));
+    double ms[Timing::NKIND] = {0, 0, 0, 0, 0, 0};
+    s->timing.collect(ms);  // drop spans of the previous life
+    Trace tr("session_reload");
+    CU2B_TRY(session_upload(s, train, test, P, Q, user_bias, item_bias, true));
+    s->mu = global_bias;
+    CU2B_TRY(session_reset_state(s));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    tr.mark("uploads + COO expansion + state");
+    return CU2B_OK;
+}
+
+extern "C" cu2b_status cu2b_session_reload(cu2b_session *s, const cu2b_csr *train, const cu2b_csr *test, const float *P,
+                                           const float *Q, const float *user_bias, const float *item_bias,
+                                           float global_bias) {
+    if (s && s->dsgd_child) return cu2b_fail(CU2B_ERR_INVALID, "this session belongs to a DSGD context; use cu2b_dsgd_reload");
+    return session_reload_impl(s, train, test, P, Q, user_bias, item_bias, global_bias);
 }
 
 extern "C" cu2b_status cu2b_session_eval(cu2b_session *s, float *train_mae, float *train_rmse,

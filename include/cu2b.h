@@ -226,6 +226,15 @@ cu2b_status cu2b_session_download(cu2b_session *s, float *P, float *Q, float *us
                                   float *item_bias);
 cu2b_status cu2b_session_get_config(cu2b_session *s, cu2b_config *out);
 cu2b_status cu2b_session_stats(cu2b_session *s, cu2b_stats *out, int reset);
+/* Starts over in an existing session: uploads a problem of the SAME shape (rows, cols, rating
+ * counts, number of users with ratings) and a new initial model into the buffers the session
+ * already owns, and resets the schedule state (learning rate, patience, log, iteration counter,
+ * statistics) to the configuration the session was created with. A repeated train() on
+ * same-shaped data (hyper-parameter sweeps, retraining on a refreshed snapshot) then pays the
+ * host->device copies but no allocation or set-up. Hogwild mode only. */
+cu2b_status cu2b_session_reload(cu2b_session *s, const cu2b_csr *train, const cu2b_csr *test,
+                                const float *P, const float *Q, const float *user_bias,
+                                const float *item_bias, float global_bias);
 void cu2b_session_destroy(cu2b_session *s);
 
 /* ------------------------------------------------------------------------------------
@@ -271,6 +280,13 @@ cu2b_session *cu2b_dsgd_session(cu2b_dsgd *d);
 /* This rank's latest local loss sums {train sse, train sae, test sse, test sae} (for
  * cross-checking the peer-memory combine against an NCCL / gloo all-reduce). */
 cu2b_status cu2b_dsgd_local_sums(cu2b_dsgd *d, double out[4]);
+/* cu2b_session_reload for a DSGD rank: same-shaped strips and a new initial model into the
+ * existing context; peer mappings, flags and buffers stay. Every rank calls it, and the ranks
+ * must synchronise (any host barrier) between their reloads and the next cu2b_dsgd_run, because a
+ * running peer writes item blocks into this rank's Q. */
+cu2b_status cu2b_dsgd_reload(cu2b_dsgd *d, const cu2b_csr *train_strip, const cu2b_csr *test_strip,
+                             const float *P_strip, const float *Q, const float *user_bias_strip,
+                             const float *item_bias, float global_bias);
 void cu2b_dsgd_destroy(cu2b_dsgd *d);
 
 /* ------------------------------------------------------------------------------------

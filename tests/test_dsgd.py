@@ -175,3 +175,31 @@ def test_dsgd_local_sums_add_up_to_the_logged_loss():
     assert abs(sums[3] / len(te) - last["test_mae"]) < 1e-6
     for d in ranks:
         d.close()
+
+@pytest.mark.gpu
+def test_dsgd_reload_equals_fresh_contexts():
+    """cu2b_dsgd_reload on two logical ranks: train, reload the same strips + initial model,
+    train again -> the log and the downloaded strips of freshly created contexts, bit for bit,
+    on a problem whose items are never shared between users (any schedule is deterministic)."""
+    rng = np.random.RandomState(4)
+    U, k, iters, ce, world = 600, 32, 48, 16, 2
+    deg = rng.randint(1, 6, U)
+    n = int(deg.sum())
+    tr = np.zeros(n, dtype=cu.RATING_DTYPE)
+    tr["user"], tr["item"], tr["rating"] = np.repeat(np.arange(U), deg), rng.permutation(n), rng.randint(1, 6, n)
+    tr = tr[np.lexsort((tr["item"], tr["user"]))]
+    te = tr[::3].copy()
+    part, ranks, (P, Q, ub, ib, mu) = _run_logical_ranks(world, tr, te, U, n, k, iters, ce)
+    fresh = [(d.log(), d.download()) for d in ranks]
+    inputs = [cu.dsgd_rank_inputs(tr, te, U, n, part, r, P, Q, ub, ib) for r in range(world)]
+    for d, inp in zip(ranks, inputs):
+        d.reload(inp, mu)  # every rank reloads before any rank runs (the "barrier")
+    th = [threading.Thread(target=d.run, args=(iters,)) for d in ranks]
+    [t.start() for t in th]
+    [t.join(timeout=120) for t in th]
+    assert not any(t.is_alive() for t in th)
+    for d, (lg, model) in zip(ranks, fresh):
+        assert d.log() == lg
+        for a, b in zip(d.download(), model):
+            assert np.array_equal(np.asarray(a).view(np.uint32), np.asarray(b).view(np.uint32))
+        d.close()

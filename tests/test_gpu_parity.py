@@ -438,6 +438,35 @@ def test_session_resume_equals_single_run(round_iters):
     assert abs(ev_a["test_rmse"] - log_a[-1]["test_rmse"]) < 1e-6
 
 
+def test_session_reload_equals_a_fresh_session():
+    """cu2b_session_reload: after some training, reloading the same problem + initial model and
+    running again gives the bits of a fresh session (disjoint-items problem: any Hogwild schedule
+    is deterministic there); a different shape is refused."""
+    U, k, iters = 500, 128, 40
+    tr, I = _disjoint_items_problem(U, 5, seed=9)
+    te = tr[::4].copy()
+    mtr, mte = cu.createSparseMatrix(tr, U, I), cu.createSparseMatrix(te, U, I)
+    mu = np.float32(3.0)
+    init = lambda n: cu.initialize_normal_array(n, k)
+    P, Q, ub, ib = init(U * k), init(I * k), init(U), init(I)
+    cfg = cu.Config(total_iterations=iters, n_factors=k, check_error=10)
+    with cu.Session(mtr, mte, cfg, P, Q, ub, ib, mu) as s:
+        s.run(iters)
+        fresh, fresh_log = s.download(), s.log()
+    with cu.Session(mtr, mte, cfg, P, Q, ub, ib, mu) as s:
+        s.run(17)  # leave the session mid-way, with a moved model and a non-empty log
+        s.reload(mtr, mte, P, Q, ub, ib, mu)
+        assert s.config().cur_iterations == 0 and s.stats()["updates"] == 0
+        s.run(iters)
+        again, again_log = s.download(), s.log()
+        assert again_log == fresh_log
+        for a, b in zip(again, fresh):
+            assert np.array_equal(np.asarray(a).view(np.uint32), np.asarray(b).view(np.uint32))
+        other = cu.createSparseMatrix(tr[:-3], U, I)
+        with pytest.raises(cu._lib.Cu2bError):
+            s.reload(other, mte, P, Q, ub, ib, mu)
+
+
 def test_train_edge_cases():
     # one user, one rating; users without ratings; empty test matrix is rejected only if oversized
     r = np.array([(2, 1, 4.0)], dtype=cu.RATING_DTYPE)
