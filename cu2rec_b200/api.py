@@ -4,6 +4,7 @@ Everything computes inside libcu2b.so; numpy only carries the buffers."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -521,3 +522,50 @@ def device_info(device=0):
     check(lib.cu2b_device_info(device, name, 256, C.byref(sm), C.byref(maj), C.byref(mnr), C.byref(fb), C.byref(tb)))
     return dict(name=name.value.decode(), sm_count=sm.value, cc=(maj.value, mnr.value), free_bytes=fb.value,
                 total_bytes=tb.value)
+
+
+# ---------------------------------------------------------------------------------------------
+# preprocessing (host only) -- the reference's preprocessing/ scripts, byte-compatible outputs
+# ---------------------------------------------------------------------------------------------
+def _mapped_name(path, suffix):
+    root, ext = os.path.splitext(path)
+    return "%s_%s%s" % (root, suffix, ext)
+
+
+def map_items(file_ratings, file_out=None, delimiter=",", has_header=True, rating_col=2, second=None, second_out=None):
+    """preprocessing/map_items.py (process_file) / map_netflix.py. Returns a dict of counts."""
+    lib = _lib.load()
+    file_out = file_out or _mapped_name(file_ratings, "mapped")
+    v = [C.c_int64() for _ in range(6)]
+    check(lib.cu2b_prep_map(os.fsencode(file_ratings), os.fsencode(file_out), delimiter.encode(), int(has_header),
+                            rating_col, os.fsencode(second) if second else None,
+                            os.fsencode(second_out) if second_out else None, *[C.byref(x) for x in v]))
+    keys = ("rows", "rows_second", "users", "items", "skipped_users", "skipped_items")
+    return dict(zip(keys, (x.value for x in v)), out=file_out)
+
+
+def sort_ratings(file_ratings, file_out=None):
+    """preprocessing/sort_ratings.py: by userId, then itemId -> <name>_sorted<ext>."""
+    lib = _lib.load()
+    file_out = file_out or _mapped_name(file_ratings, "sorted")
+    n = C.c_int64()
+    check(lib.cu2b_prep_sort(os.fsencode(file_ratings), os.fsencode(file_out), C.byref(n)))
+    return dict(rows=n.value, out=file_out)
+
+
+def split_to_test_train(file_ratings, test_ratio, seed=42, train_out=None, test_out=None):
+    """preprocessing/split_to_test_train.py (split_true) -> <name>_train<ext>, <name>_test<ext>."""
+    lib = _lib.load()
+    train_out = train_out or _mapped_name(file_ratings, "train")
+    test_out = test_out or _mapped_name(file_ratings, "test")
+    a, b = C.c_int64(), C.c_int64()
+    check(lib.cu2b_prep_split(os.fsencode(file_ratings), os.fsencode(train_out), os.fsencode(test_out),
+                              float(test_ratio), int(seed), C.byref(a), C.byref(b)))
+    return dict(train=a.value, test=b.value, train_out=train_out, test_out=test_out)
+
+
+def create_config(filename, num_iterations=1000, num_factors=100, learning_rate=0.01, seed=42, p_reg=0.02, q_reg=0.02,
+                  user_bias_reg=0.02, item_bias_reg=0.02):
+    """preprocessing/create_config.py (same defaults)."""
+    check(_lib.load().cu2b_prep_create_config(os.fsencode(filename), num_iterations, num_factors, learning_rate, seed,
+                                              p_reg, q_reg, user_bias_reg, item_bias_reg))

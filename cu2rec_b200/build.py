@@ -1,7 +1,7 @@
 """Builds every native artefact of the repository in-tree (no JIT cache, no site-packages).
 
   cu2rec_b200/lib/libcu2b.so   the product: sm_100a kernels + C ABI + host IO   (nvcc)
-  bin/mf, bin/predict          drop-in CLIs over the C ABI                       (nvcc/g++)
+  bin/mf, bin/predict, bin/prep  drop-in CLIs over the C ABI                     (g++)
 
 (The test oracle under oracle/ is built by __graft_entry__.build(), not from here: the package
 never touches it.)
@@ -61,7 +61,7 @@ def build_lib(force=False, verbose=False):
 def build_cli(force=False):
     os.makedirs(BINDIR, exist_ok=True)
     outs = []
-    for name in ("mf", "predict"):
+    for name in ("mf", "predict", "prep"):
         src = os.path.join(CSRC, "cli_%s.cpp" % name)
         if not os.path.exists(src):
             continue

@@ -1,0 +1,103 @@
+// bin/prep -- the reference's preprocessing/ scripts as one native tool, same output
+// file names and bytes:
+//   prep map_items <ratings.csv>                     -> <ratings>_mapped.csv        (map_items.py)
+//   prep map_netflix <train.txt> <test.txt> <train_out.csv> <test_out.csv>          (map_netflix.py)
+//   prep sort_ratings <ratings.csv>                  -> <ratings>_sorted.csv        (sort_ratings.py)
+//   prep split_to_test_train <ratings.csv> <test_ratio> [-s seed]
+//                                                    -> <ratings>_train.csv, <ratings>_test.csv
+//   prep create_config <file> [-n iters] [-f factors] [-l lr] [-s seed] [-p p_reg] [-q q_reg]
+//                      [-u user_bias_reg] [-i item_bias_reg]                        (create_config.py)
+// Host only (no GPU needed).
+#include <getopt.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "cu2b.h"
+
+static std::string with_suffix(const std::string &path, const char *suffix) {  // os.path.splitext
+    const size_t slash = path.find_last_of('/');
+    const size_t dot = path.find_last_of('.');
+    const bool has_ext = dot != std::string::npos && (slash == std::string::npos || dot > slash + 1) && dot != 0;
+    const std::string root = has_ext ? path.substr(0, dot) : path, ext = has_ext ? path.substr(dot) : "";
+    return root + "_" + suffix + ext;
+}
+
+static int fail() {
+    fprintf(stderr, "prep: %s\n", cu2b_last_error());
+    return 1;
+}
+
+static int usage() {
+    fprintf(stderr,
+            "usage: prep map_items <ratings.csv>\n"
+            "       prep map_netflix <train.txt> <test.txt> <train_out.csv> <test_out.csv>\n"
+            "       prep sort_ratings <ratings.csv>\n"
+            "       prep split_to_test_train <ratings.csv> <test_ratio> [-s seed]\n"
+            "       prep create_config <file> [-n N] [-f F] [-l LR] [-s SEED] [-p P] [-q Q] [-u UB] [-i IB]\n");
+    return 2;
+}
+
+int main(int argc, char **argv) {
+    if (argc < 3) return usage();
+    const std::string cmd = argv[1];
+    if (cmd == "map_items") {
+        int64_t rows = 0, users = 0, items = 0;
+        const std::string out = with_suffix(argv[2], "mapped");
+        if (cu2b_prep_map(argv[2], out.c_str(), ',', 1, 2, nullptr, nullptr, &rows, nullptr, &users, &items, nullptr, nullptr) != CU2B_OK)
+            return fail();
+        fprintf(stderr, "%lld rows, %lld users, %lld items -> %s\n", (long long)rows, (long long)users, (long long)items, out.c_str());
+        return 0;
+    }
+    if (cmd == "map_netflix") {
+        if (argc < 6) return usage();
+        int64_t rows = 0, rows2 = 0, su = 0, si = 0;
+        if (cu2b_prep_map(argv[2], argv[4], ' ', 0, 3, argv[3], argv[5], &rows, &rows2, nullptr, nullptr, &su, &si) != CU2B_OK)
+            return fail();
+        if (su > 0) printf("Skipped %lld rows because of missing users\n", (long long)su);  // map_items.py:55-58
+        if (si > 0) printf("Skipped %lld rows because of missing items\n", (long long)si);
+        return 0;
+    }
+    if (cmd == "sort_ratings") {
+        printf("sorting ratings...\n");  // sort_ratings.py:33-35
+        const std::string out = with_suffix(argv[2], "sorted");
+        if (cu2b_prep_sort(argv[2], out.c_str(), nullptr) != CU2B_OK) return fail();
+        printf("done sorting ratings...\n");
+        return 0;
+    }
+    if (cmd == "split_to_test_train") {
+        if (argc < 4) return usage();
+        long long seed = 42;
+        for (int a = 4; a + 1 < argc; ++a)
+            if (!strcmp(argv[a], "-s") || !strcmp(argv[a], "--seed")) seed = atoll(argv[a + 1]);
+        const std::string tr = with_suffix(argv[2], "train"), te = with_suffix(argv[2], "test");
+        if (cu2b_prep_split(argv[2], tr.c_str(), te.c_str(), atof(argv[3]), seed, nullptr, nullptr) != CU2B_OK) return fail();
+        return 0;
+    }
+    if (cmd == "create_config") {
+        int n = 1000, f = 100, s = 42;  // create_config.py:24-32 defaults
+        double l = 0.01, p = 0.02, q = 0.02, u = 0.02, i = 0.02;
+        const char *file = argv[2];
+        optind = 3;
+        int o;
+        while ((o = getopt(argc, argv, "n:f:l:s:p:q:u:i:t:a:d:")) != -1) {
+            switch (o) {
+                case 'n': n = atoi(optarg); break;
+                case 'f': f = atoi(optarg); break;
+                case 'l': l = atof(optarg); break;
+                case 's': s = atoi(optarg); break;
+                case 'p': p = atof(optarg); break;
+                case 'q': q = atof(optarg); break;
+                case 'u': u = atof(optarg); break;
+                case 'i': i = atof(optarg); break;
+                case 't': case 'a': case 'd': break;  // accepted and not written, like the script
+                default: return usage();
+            }
+        }
+        if (cu2b_prep_create_config(file, n, f, l, s, p, q, u, i) != CU2B_OK) return fail();
+        return 0;
+    }
+    return usage();
+}

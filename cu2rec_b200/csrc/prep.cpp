@@ -1,0 +1,374 @@
+// Native counterparts of the reference's preprocessing scripts, byte-compatible with
+// their outputs:
+//   preprocessing/map_items.py:21-96      -> cu2b_prep_map      (sequential ids in first-appearance
+//                                            order, rows grouped by ascending user, input order kept)
+//   preprocessing/map_netflix.py:9-27     -> cu2b_prep_map with a second file (shared mappings,
+//                                            rows of unknown users / items skipped), delimiter ' ',
+//                                            rating in column 3
+//   preprocessing/sort_ratings.py:29-37   -> cu2b_prep_sort     (by user, then item, stable)
+//   preprocessing/split_to_test_train.py:39-49,71-82 -> cu2b_prep_split (split_true: one shuffle of
+//                                            all rows with Python's random.seed(seed) /
+//                                            random.shuffle stream, cut, stable sort by user)
+//   preprocessing/create_config.py:10-19  -> cu2b_prep_create_config
+// The scripts hold every row as Python objects (minutes and tens of GB at the Netflix size); here the
+// file is mmap-ed, parsed once, and written with a block formatter. Ratings are parsed to double and
+// printed as Python prints a float (shortest round-trip repr, ".0" for integral values), ids as
+// 64-bit integers. Host code only; nothing here touches the GPU.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <charconv>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "cu2b_internal.h"
+
+#define CU2B_TRY_STATUS(expr)               \
+    do {                                    \
+        cu2b_status s__ = (expr);           \
+        if (s__ != CU2B_OK) return s__;     \
+    } while (0)
+
+namespace {
+
+struct Row {
+    int64_t user, item;
+    double rating;
+};
+
+struct Mapped {
+    const char *base = nullptr;
+    size_t size = 0;
+    int fd = -1;
+    ~Mapped() {
+        if (base && size) munmap((void *)base, size);
+        if (fd >= 0) close(fd);
+    }
+    cu2b_status open_file(const char *path) {
+        fd = open(path, O_RDONLY);
+        if (fd < 0) return cu2b_fail(CU2B_ERR_IO, "cannot open %s", path);
+        struct stat st;
+        if (fstat(fd, &st) != 0) return cu2b_fail(CU2B_ERR_IO, "cannot stat %s", path);
+        size = (size_t)st.st_size;
+        if (size == 0) return CU2B_OK;
+        void *p = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (p == MAP_FAILED) { size = 0; return cu2b_fail(CU2B_ERR_IO, "mmap failed for %s", path); }
+        base = (const char *)p;
+        return CU2B_OK;
+    }
+};
+
+// Splits one line into fields the way csv.reader does for these files (no quoting in them):
+// every occurrence of the delimiter separates two fields, so "a  b" with ' ' has an empty field.
+// Fields are [begin, end) pointers into the line.
+int split_fields(const char *p, const char *end, char delim, const char **fb, const char **fe, int cap) {
+    int n = 0;
+    const char *s = p;
+    for (const char *q = p;; ++q) {
+        if (q == end || *q == delim) {
+            if (n < cap) { fb[n] = s; fe[n] = q; }
+            ++n;
+            if (q == end) break;
+            s = q + 1;
+        }
+    }
+    return n;
+}
+
+// int(str): optional surrounding whitespace, optional sign, digits.
+bool parse_int(const char *b, const char *e, int64_t *out) {
+    while (b < e && (*b == ' ' || *b == '\t')) ++b;
+    while (e > b && (e[-1] == ' ' || e[-1] == '\t' || e[-1] == '\r')) --e;
+    if (b == e) return false;
+    bool neg = false;
+    if (*b == '+' || *b == '-') { neg = *b == '-'; ++b; }
+    if (b == e) return false;
+    int64_t v = 0;
+    for (; b < e; ++b) {
+        if (*b < '0' || *b > '9') return false;
+        v = v * 10 + (*b - '0');
+    }
+    *out = neg ? -v : v;
+    return true;
+}
+
+bool parse_float(const char *b, const char *e, double *out) {
+    while (b < e && (*b == ' ' || *b == '\t')) ++b;
+    while (e > b && (e[-1] == ' ' || e[-1] == '\t' || e[-1] == '\r')) --e;
+    if (b == e) return false;
+    char buf[64];
+    const size_t n = std::min<size_t>((size_t)(e - b), sizeof buf - 1);
+    memcpy(buf, b, n);
+    buf[n] = 0;
+    char *endp = nullptr;
+    *out = strtod(buf, &endp);
+    return endp == buf + n;
+}
+
+// Reads "user <d> item <d> ... rating ..." rows. rating_col is the 0-based field index of the rating.
+cu2b_status read_rows(const char *path, char delim, bool has_header, int rating_col, std::vector<Row> *rows) {
+    Mapped f;
+    CU2B_TRY_STATUS(f.open_file(path));
+    const char *p = f.base, *end = f.base + f.size;
+    int64_t line_no = 0;
+    while (p < end) {
+        const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
+        const char *le = nl ? nl : end;
+        const char *next = nl ? nl + 1 : end;
+        ++line_no;
+        if (has_header && line_no == 1) { p = next; continue; }
+        const char *lt = le;
+        if (lt > p && lt[-1] == '\r') --lt;
+        if (lt == p) { p = next; continue; }  // csv.reader yields [] for a blank line; the scripts never see one
+        const char *fb[8], *fe[8];
+        const int nf = split_fields(p, lt, delim, fb, fe, 8);
+        Row r;
+        if (nf <= rating_col || rating_col >= 8 || !parse_int(fb[0], fe[0], &r.user) || !parse_int(fb[1], fe[1], &r.item) ||
+            !parse_float(fb[rating_col], fe[rating_col], &r.rating))
+            return cu2b_fail(CU2B_ERR_IO, "%s:%lld: expected <int>%c<int>%c...<float>", path, (long long)line_no, delim, delim);
+        rows->push_back(r);
+        p = next;
+    }
+    return CU2B_OK;
+}
+
+// str(float) of Python: shortest round-trip digits; fixed notation for 1e-4 <= |x| < 1e16 with
+// ".0" appended to integral values, exponent notation otherwise.
+char *format_pyfloat(double v, char *dst) {
+    if (v != v) { memcpy(dst, "nan", 3); return dst + 3; }
+    if (v == 1.0 / 0.0) { memcpy(dst, "inf", 3); return dst + 3; }
+    if (v == -1.0 / 0.0) { memcpy(dst, "-inf", 4); return dst + 4; }
+    const double a = v < 0 ? -v : v;
+    if (a != 0 && (a < 1e-4 || a >= 1e16)) {
+        char tmp[40];
+        auto res = std::to_chars(tmp, tmp + sizeof tmp, v, std::chars_format::scientific);
+        // to_chars: d.ddde+XX ; Python: d.ddde+XX with at least two exponent digits and no ".0"
+        // mantissa padding -- identical for everything these files can contain
+        const size_t n = (size_t)(res.ptr - tmp);
+        memcpy(dst, tmp, n);
+        return dst + n;
+    }
+    auto res = std::to_chars(dst, dst + 32, v, std::chars_format::fixed);
+    char *e = res.ptr;
+    if (!memchr(dst, '.', (size_t)(e - dst))) { *e++ = '.'; *e++ = '0'; }
+    return e;
+}
+
+char *format_int(int64_t v, char *dst) {
+    auto res = std::to_chars(dst, dst + 24, v);
+    return res.ptr;
+}
+
+// write_to_file of map_items.py:78-87: header + "user,item,rating" rows, '\n' line ends.
+cu2b_status write_rows(const char *path, const std::vector<Row> &rows, const std::vector<int64_t> *order) {
+    FILE *f = fopen(path, "wb");
+    if (!f) return cu2b_fail(CU2B_ERR_IO, "cannot create %s", path);
+    std::vector<char> buf(1 << 22);
+    size_t used = 0;
+    const char *hdr = "userId,itemId,rating\n";
+    memcpy(buf.data(), hdr, strlen(hdr));
+    used = strlen(hdr);
+    const size_t n = order ? order->size() : rows.size();
+    for (size_t t = 0; t < n; ++t) {
+        const Row &r = rows[order ? (size_t)(*order)[t] : t];
+        if (used + 128 > buf.size()) {
+            if (fwrite(buf.data(), 1, used, f) != used) { fclose(f); return cu2b_fail(CU2B_ERR_IO, "short write to %s", path); }
+            used = 0;
+        }
+        char *p = buf.data() + used;
+        p = format_int(r.user, p);
+        *p++ = ',';
+        p = format_int(r.item, p);
+        *p++ = ',';
+        p = format_pyfloat(r.rating, p);
+        *p++ = '\n';
+        used = (size_t)(p - buf.data());
+    }
+    if (used && fwrite(buf.data(), 1, used, f) != used) { fclose(f); return cu2b_fail(CU2B_ERR_IO, "short write to %s", path); }
+    if (fclose(f) != 0) return cu2b_fail(CU2B_ERR_IO, "cannot close %s", path);
+    return CU2B_OK;
+}
+
+// map_rows of map_items.py:21-59: ids are replaced by 1 + (number of distinct ids seen before).
+void map_rows(std::vector<Row> *rows, std::unordered_map<int64_t, int64_t> *umap, std::unordered_map<int64_t, int64_t> *imap,
+              bool add_missing, int64_t *missing_users, int64_t *missing_items) {
+    size_t w = 0;
+    for (size_t t = 0; t < rows->size(); ++t) {
+        Row r = (*rows)[t];
+        auto u = umap->find(r.user);
+        if (u == umap->end()) {
+            if (!add_missing) { ++*missing_users; continue; }
+            u = umap->emplace(r.user, (int64_t)umap->size() + 1).first;
+        }
+        auto i = imap->find(r.item);
+        if (i == imap->end()) {
+            if (!add_missing) { ++*missing_items; continue; }
+            i = imap->emplace(r.item, (int64_t)imap->size() + 1).first;
+        }
+        r.user = u->second;
+        r.item = i->second;
+        (*rows)[w++] = r;
+    }
+    rows->resize(w);
+}
+
+// sort_by_user of map_items.py:62-75: ascending user, input order kept inside a user.
+void stable_by_user(const std::vector<Row> &rows, std::vector<int64_t> *order) {
+    order->resize(rows.size());
+    std::iota(order->begin(), order->end(), (int64_t)0);
+    std::stable_sort(order->begin(), order->end(), [&](int64_t a, int64_t b) { return rows[(size_t)a].user < rows[(size_t)b].user; });
+}
+
+// The Mersenne Twister stream of CPython's `random` module: random.seed(int) is init_by_array over
+// the 32-bit words of |seed|; getrandbits(k <= 32) is the top k bits of one output word;
+// _randbelow(n) rejects values >= n; shuffle walks i = n-1 .. 1 and swaps x[i], x[randbelow(i+1)].
+struct PyRandom {
+    uint32_t mt[624];
+    int idx = 624;
+    void init_genrand(uint32_t s) {
+        mt[0] = s;
+        for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+        idx = 624;
+    }
+    void seed(uint64_t seed_abs) {
+        uint32_t key[2] = {(uint32_t)seed_abs, (uint32_t)(seed_abs >> 32)};
+        const int klen = key[1] ? 2 : 1;
+        init_genrand(19650218u);
+        int i = 1, j = 0;
+        for (int k = 624 > klen ? 624 : klen; k; --k) {
+            mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1664525u)) + key[j] + (uint32_t)j;
+            if (++i >= 624) { mt[0] = mt[623]; i = 1; }
+            if (++j >= klen) j = 0;
+        }
+        for (int k = 623; k; --k) {
+            mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1566083941u)) - (uint32_t)i;
+            if (++i >= 624) { mt[0] = mt[623]; i = 1; }
+        }
+        mt[0] = 0x80000000u;
+        idx = 624;
+    }
+    uint32_t next() {
+        if (idx >= 624) {
+            for (int k = 0; k < 624; ++k) {
+                const uint32_t y = (mt[k] & 0x80000000u) | (mt[(k + 1) % 624] & 0x7fffffffu);
+                mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            idx = 0;
+        }
+        uint32_t y = mt[idx++];
+        y ^= y >> 11;
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= y >> 18;
+        return y;
+    }
+    uint64_t randbelow(uint64_t n) {  // n >= 1
+        int k = 0;
+        for (uint64_t t = n; t; t >>= 1) ++k;  // n.bit_length()
+        for (;;) {
+            uint64_t r;
+            if (k <= 32) {
+                r = next() >> (32 - k);
+            } else {  // getrandbits fills 32-bit words from the least significant one
+                const uint64_t lo = next();
+                const uint64_t hi = next() >> (64 - k);
+                r = (hi << 32) | lo;
+            }
+            if (r < n) return r;
+        }
+    }
+};
+
+}  // namespace
+
+extern "C" cu2b_status cu2b_prep_map(const char *in_path, const char *out_path, char delimiter, int has_header,
+                                     int rating_col, const char *in2_path, const char *out2_path, int64_t *n_rows,
+                                     int64_t *n_rows2, int64_t *n_users, int64_t *n_items, int64_t *skipped_users,
+                                     int64_t *skipped_items) {
+    if (!in_path || !out_path || rating_col < 2 || (in2_path != nullptr) != (out2_path != nullptr))
+        return cu2b_fail(CU2B_ERR_INVALID, "cu2b_prep_map: bad argument");
+    std::unordered_map<int64_t, int64_t> umap, imap;
+    std::vector<Row> rows;
+    std::vector<int64_t> order;
+    int64_t mu = 0, mi = 0;
+    CU2B_TRY_STATUS(read_rows(in_path, delimiter, has_header != 0, rating_col, &rows));
+    map_rows(&rows, &umap, &imap, true, &mu, &mi);
+    stable_by_user(rows, &order);
+    CU2B_TRY_STATUS(write_rows(out_path, rows, &order));
+    if (n_rows) *n_rows = (int64_t)rows.size();
+    if (n_rows2) *n_rows2 = 0;
+    if (in2_path) {  // map_netflix.py:20-22: the second file is mapped with the first file's tables
+        rows.clear();
+        CU2B_TRY_STATUS(read_rows(in2_path, delimiter, has_header != 0, rating_col, &rows));
+        map_rows(&rows, &umap, &imap, false, &mu, &mi);
+        stable_by_user(rows, &order);
+        CU2B_TRY_STATUS(write_rows(out2_path, rows, &order));
+        if (n_rows2) *n_rows2 = (int64_t)rows.size();
+    }
+    if (n_users) *n_users = (int64_t)umap.size();
+    if (n_items) *n_items = (int64_t)imap.size();
+    if (skipped_users) *skipped_users = mu;
+    if (skipped_items) *skipped_items = mi;
+    return CU2B_OK;
+}
+
+extern "C" cu2b_status cu2b_prep_sort(const char *in_path, const char *out_path, int64_t *n_rows) {
+    if (!in_path || !out_path) return cu2b_fail(CU2B_ERR_INVALID, "cu2b_prep_sort: null argument");
+    std::vector<Row> rows;
+    CU2B_TRY_STATUS(read_rows(in_path, ',', true, 2, &rows));
+    std::vector<int64_t> order(rows.size());
+    std::iota(order.begin(), order.end(), (int64_t)0);
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {  // sort_ratings.py:34
+        const Row &x = rows[(size_t)a], &y = rows[(size_t)b];
+        return x.user != y.user ? x.user < y.user : x.item < y.item;
+    });
+    CU2B_TRY_STATUS(write_rows(out_path, rows, &order));
+    if (n_rows) *n_rows = (int64_t)rows.size();
+    return CU2B_OK;
+}
+
+extern "C" cu2b_status cu2b_prep_split(const char *in_path, const char *train_path, const char *test_path,
+                                       double test_ratio, int64_t seed, int64_t *n_train, int64_t *n_test) {
+    if (!in_path || !train_path || !test_path) return cu2b_fail(CU2B_ERR_INVALID, "cu2b_prep_split: null argument");
+    std::vector<Row> rows;
+    CU2B_TRY_STATUS(read_rows(in_path, ',', true, 2, &rows));
+    const size_t n = rows.size();
+    std::vector<int64_t> perm(n);
+    std::iota(perm.begin(), perm.end(), (int64_t)0);
+    PyRandom rng;
+    rng.seed((uint64_t)(seed < 0 ? -seed : seed));
+    for (size_t i = n; i-- > 1;) std::swap(perm[i], perm[(size_t)rng.randbelow((uint64_t)i + 1)]);  // random.shuffle
+    const double train_percent = 1 - test_ratio;                      // split_to_test_train.py:76
+    const size_t cut = std::min(n, (size_t)std::max(0.0, (double)(int64_t)((double)n * train_percent)));  // int(num * pct)
+    auto emit = [&](size_t lo, size_t hi, const char *path) -> cu2b_status {
+        std::vector<int64_t> part(perm.begin() + (long)lo, perm.begin() + (long)hi);
+        std::stable_sort(part.begin(), part.end(), [&](int64_t a, int64_t b) { return rows[(size_t)a].user < rows[(size_t)b].user; });
+        return write_rows(path, rows, &part);
+    };
+    CU2B_TRY_STATUS(emit(0, cut, train_path));
+    CU2B_TRY_STATUS(emit(cut, n, test_path));
+    if (n_train) *n_train = (int64_t)cut;
+    if (n_test) *n_test = (int64_t)(n - cut);
+    return CU2B_OK;
+}
+
+// create_config.py:13-15: '0 {:d} {:d} {:f} {:d} {:f} {:f} {:f} {:f}', no trailing newline.
+extern "C" cu2b_status cu2b_prep_create_config(const char *path, int num_iterations, int num_factors,
+                                               double learning_rate, int seed, double p_reg, double q_reg,
+                                               double user_bias_reg, double item_bias_reg) {
+    if (!path) return cu2b_fail(CU2B_ERR_INVALID, "cu2b_prep_create_config: null path");
+    FILE *f = fopen(path, "wb");
+    if (!f) return cu2b_fail(CU2B_ERR_IO, "cannot create %s", path);
+    fprintf(f, "0 %d %d %f %d %f %f %f %f", num_iterations, num_factors, learning_rate, seed, p_reg, q_reg,
+            user_bias_reg, item_bias_reg);
+    if (fclose(f) != 0) return cu2b_fail(CU2B_ERR_IO, "cannot close %s", path);
+    return CU2B_OK;
+}

@@ -308,6 +308,31 @@ cu2b_status cu2b_device_info(int device, char *name, int name_cap, int *sm_count
                              int *cc_major, int *cc_minor, int64_t *free_bytes,
                              int64_t *total_bytes);
 
+/* ------------------------------------------------------------------------------------
+ * Preprocessing (host only): native counterparts of the reference's preprocessing/ scripts,
+ * byte-compatible with their output files.
+ * ------------------------------------------------------------------------------------ */
+/* map_items.py:21-96 (and map_netflix.py:9-27 when in2_path / out2_path are given): user and item
+ * ids -> 1-based sequential ids in first-appearance order, rows grouped by ascending user with the
+ * input order kept inside a user, written as "userId,itemId,rating". rating_col = 0-based field of
+ * the rating (2; 3 for the Netflix text files whose rating follows two spaces). The second file is
+ * mapped with the first file's tables; its rows with unknown users / items are skipped. */
+cu2b_status cu2b_prep_map(const char *in_path, const char *out_path, char delimiter, int has_header,
+                          int rating_col, const char *in2_path, const char *out2_path,
+                          int64_t *n_rows, int64_t *n_rows2, int64_t *n_users, int64_t *n_items,
+                          int64_t *skipped_users, int64_t *skipped_items);
+/* sort_ratings.py:29-37: by userId, then itemId (stable). */
+cu2b_status cu2b_prep_sort(const char *in_path, const char *out_path, int64_t *n_rows);
+/* split_to_test_train.py:39-49,71-82 (split_true): one shuffle of all rows with the stream of
+ * Python's random.seed(seed) / random.shuffle, the first int(n * (1 - test_ratio)) rows are the
+ * training set, both parts stably sorted by user. */
+cu2b_status cu2b_prep_split(const char *in_path, const char *train_path, const char *test_path,
+                            double test_ratio, int64_t seed, int64_t *n_train, int64_t *n_test);
+/* create_config.py:10-19: "0 <iterations> <factors> <lr> <seed> <p_reg> <q_reg> <ub_reg> <ib_reg>". */
+cu2b_status cu2b_prep_create_config(const char *path, int num_iterations, int num_factors,
+                                    double learning_rate, int seed, double p_reg, double q_reg,
+                                    double user_bias_reg, double item_bias_reg);
+
 #ifdef __cplusplus
 }
 #endif
