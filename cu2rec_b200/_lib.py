@@ -91,6 +91,7 @@ SYMBOLS = {
     "cu2b_dsgd_destroy": (None, [_P]),
     "cu2b_prep_map": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char, C.c_int, C.c_int, C.c_char_p, C.c_char_p] +
                       [C.POINTER(C.c_int64)] * 6),
+    "cu2b_write_ratings_csv": (C.c_int, [C.c_char_p, C.POINTER(Rating), C.c_int64]),
     "cu2b_prep_sort": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_int64)]),
     "cu2b_prep_split": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_double, C.c_int64, C.POINTER(C.c_int64),
                                   C.POINTER(C.c_int64)]),

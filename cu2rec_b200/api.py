@@ -569,3 +569,9 @@ def create_config(filename, num_iterations=1000, num_factors=100, learning_rate=
     """preprocessing/create_config.py (same defaults)."""
     check(_lib.load().cu2b_prep_create_config(os.fsencode(filename), num_iterations, num_factors, learning_rate, seed,
                                               p_reg, q_reg, user_bias_reg, item_bias_reg))
+
+
+def write_ratings_csv(path, ratings):
+    """Ratings triplets (0-based ids) -> "userId,itemId,rating" CSV with 1-based ids (readCSV's input)."""
+    ratings = np.ascontiguousarray(ratings, dtype=RATING_DTYPE)
+    check(_lib.load().cu2b_write_ratings_csv(os.fsencode(path), ratings.ctypes.data_as(C.POINTER(Rating)), len(ratings)))

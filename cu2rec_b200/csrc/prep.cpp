@@ -372,3 +372,13 @@ extern "C" cu2b_status cu2b_prep_create_config(const char *path, int num_iterati
     if (fclose(f) != 0) return cu2b_fail(CU2B_ERR_IO, "cannot close %s", path);
     return CU2B_OK;
 }
+
+// Ratings triplets (0-based ids, as every other entry point holds them) -> the reference's input
+// CSV ("userId,itemId,rating", 1-based ids; util.cu:17-45 reads it back). Used by the experiment
+// harness to materialise synthetic data sets for the bin/mf CLI.
+extern "C" cu2b_status cu2b_write_ratings_csv(const char *path, const cu2b_rating *ratings, int64_t n) {
+    if (!path || (!ratings && n > 0) || n < 0) return cu2b_fail(CU2B_ERR_INVALID, "cu2b_write_ratings_csv: bad argument");
+    std::vector<Row> rows((size_t)n);
+    for (int64_t t = 0; t < n; ++t) rows[(size_t)t] = Row{(int64_t)ratings[t].user + 1, (int64_t)ratings[t].item + 1, (double)ratings[t].rating};
+    return write_rows(path, rows, nullptr);
+}

@@ -328,6 +328,8 @@ cu2b_status cu2b_prep_sort(const char *in_path, const char *out_path, int64_t *n
  * training set, both parts stably sorted by user. */
 cu2b_status cu2b_prep_split(const char *in_path, const char *train_path, const char *test_path,
                             double test_ratio, int64_t seed, int64_t *n_train, int64_t *n_test);
+/* Ratings triplets (0-based ids) -> the reference's input CSV (header, 1-based ids; util.cu:17-45). */
+cu2b_status cu2b_write_ratings_csv(const char *path, const cu2b_rating *ratings, int64_t n);
 /* create_config.py:10-19: "0 <iterations> <factors> <lr> <seed> <p_reg> <q_reg> <ub_reg> <ib_reg>". */
 cu2b_status cu2b_prep_create_config(const char *path, int num_iterations, int num_factors,
                                     double learning_rate, int seed, double p_reg, double q_reg,

@@ -90,3 +90,24 @@ def test_mf_cli_without_config_uses_reference_defaults(tmp_path):
     its = [int(x) for x in re.findall(r"^TEST: Iteration (\d+)", p.stdout, re.M)]
     assert its == [1] + list(range(500, 5001, 500))
     assert os.path.exists(tmp_path / "a_f50_p.csv")
+
+
+@pytest.mark.gpu
+def test_experiment_grid_harness_on_ml100k_shape(tmp_path):
+    """experiments/run_grid.py (the reference's experiments/cu2rec.sh grid through bin/mf): one data set
+    x two iteration counts x one factor count, synthetic data generated on the fly."""
+    import json
+    import sys
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "experiments", "run_grid.py"), "--datasets", "ml-100k",
+                        "--iterations", "50", "200", "--factors", "50", "--data-dir", str(tmp_path / "data"),
+                        "--results-dir", str(tmp_path / "results"), "--tag", "t"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-2000:]
+    rows = [json.loads(l) for l in open(tmp_path / "results" / "t.jsonl")]
+    assert [(r["iterations"], r["factors"]) for r in rows] == [(50, 50), (200, 50)]
+    for r in rows:
+        assert r["dataset"] == "ml-100k" and r["users"] == 943 and r["items"] == 1682
+        assert r["updates_per_s"] > 0 and 0.5 < r["test_rmse"] < 2.0 and r["wall_seconds"] >= r["train_seconds"]
+    assert rows[1]["test_rmse"] < rows[0]["test_rmse"]  # more iterations, lower loss
+    log = open(tmp_path / "results" / "t.txt").read()
+    assert "Done with 50 factors with 200 iterations on ml-100k" in log and "TEST: Iteration" in log  # cu2rec.sh:17
+    assert "| ml-100k (synthetic) | 200 |" in open(tmp_path / "results" / "t.md").read()
