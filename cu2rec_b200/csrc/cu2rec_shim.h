@@ -16,7 +16,9 @@
 #ifndef CU2REC_SHIM_H_
 #define CU2REC_SHIM_H_
 
+#include <climits>
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <stdexcept>
@@ -70,6 +72,12 @@ struct CudaCSRMatrix {
             memcpy(indices, indices_, sizeof(int) * nonzeros);
             memcpy(data, data_, sizeof(float) * nonzeros);
         }
+    }
+    // Allocates without filling: createSparseMatrix() builds the arrays in place.
+    CudaCSRMatrix(int rows_, int cols_, int nonzeros_) : rows(rows_), cols(cols_), nonzeros(nonzeros_) {
+        indptr = new int[rows + 1];
+        indices = new int[nonzeros > 0 ? nonzeros : 1];
+        data = new float[nonzeros > 0 ? nonzeros : 1];
     }
     ~CudaCSRMatrix() {
         delete[] indptr;
@@ -141,11 +149,14 @@ inline float *initialize_normal_array(int size, int n_factors) { return initiali
 
 inline cu2rec::CudaCSRMatrix *createSparseMatrix(std::vector<Rating> *ratings, int rows, int cols) {
     const int64_t n = (int64_t)ratings->size();
-    std::vector<int> indptr((size_t)rows + 1), indices((size_t)(n > 0 ? n : 1));
-    std::vector<float> data((size_t)(n > 0 ? n : 1));
-    CU2B_CHECK(cu2b_build_csr(reinterpret_cast<const cu2b_rating *>(ratings->data()), n, rows, indptr.data(), indices.data(),
-                              data.data()));
-    return new cu2rec::CudaCSRMatrix(rows, cols, (int)n, indptr.data(), indices.data(), data.data());
+    if (n > INT32_MAX) throw std::runtime_error("createSparseMatrix: more than 2^31-1 ratings");
+    cu2rec::CudaCSRMatrix *m = new cu2rec::CudaCSRMatrix(rows, cols, (int)n);
+    if (cu2b_build_csr(reinterpret_cast<const cu2b_rating *>(ratings->data()), n, rows, m->indptr, m->indices, m->data) !=
+        CU2B_OK) {
+        delete m;
+        throw std::runtime_error(cu2b_last_error());
+    }
+    return m;
 }
 
 inline size_t getFreeBytes(const int where, size_t *total_bytes) {

@@ -97,6 +97,59 @@ def test_read_csv_multithreaded_path_matches_oracle(tmp_path):
     assert np.float32(gb).view(np.uint32) == np.float32(gb2).view(np.uint32)
 
 
+def _big_csv(path, rng, n, fmt, extra=lambda k: ""):
+    users = np.sort(rng.randint(1, 20000, n))
+    items = rng.randint(1, 5000, n)
+    with open(path, "w") as f:
+        f.write("userId,itemId,rating\n")
+        f.write("".join(fmt(u, i) + extra(k) for k, (u, i) in enumerate(zip(users, items))))
+    assert os.path.getsize(path) > (1 << 20)
+
+
+@pytest.mark.parametrize("case", ["blank_lines", "two_per_line", "inexact_sum", "stops_midway", "crlf"])
+def test_read_csv_parallel_slices_compaction_and_fallbacks(tmp_path, case):
+    """The threaded reader parses into per-chunk slices of one array (lines bound the records):
+    gaps are closed when lines hold no record, several records per line fall back to the serial
+    reader, the mean is summed as exact integers only when that cannot differ from util.cu:34's
+    sequential double sum, and a malformed record ends the stream like a failed operator>>."""
+    rng = np.random.RandomState(17)
+    p = tmp_path / (case + ".csv")
+    n = 150000
+    if case == "blank_lines":
+        _big_csv(p, rng, n, lambda u, i: "%d,%d,%.1f\n" % (u, i, rng.randint(1, 11) / 2), lambda k: "\n" if k % 7 == 0 else "")
+    elif case == "two_per_line":
+        _big_csv(p, rng, n, lambda u, i: "%d,%d,%d" % (u, i, rng.randint(1, 6)), lambda k: " " if k % 2 == 0 else "\n")
+    elif case == "inexact_sum":
+        _big_csv(p, rng, n, lambda u, i: "%d,%d,%s\n" % (u, i, repr(float(rng.rand() * 5 + 1e-9))))
+    elif case == "stops_midway":
+        _big_csv(p, rng, n, lambda u, i: "%d,%d,%.1f\n" % (u, i, rng.randint(1, 11) / 2), lambda k: "oops\n" if k == 100000 else "")
+    else:
+        _big_csv(p, rng, n, lambda u, i: "%d,%d,%.1f\r\n" % (u, i, rng.randint(1, 11) / 2))
+    a, rows, cols, gb = cu.readCSV(p)
+    b, rows2, cols2, gb2 = O.read_csv(p)
+    assert len(a) == len(b) == (100001 if case == "stops_midway" else n)
+    assert a.tobytes() == b.tobytes() and (rows, cols) == (rows2, cols2)
+    assert np.float32(gb).view(np.uint32) == np.float32(gb2).view(np.uint32)
+
+
+def test_build_csr_parallel_path_matches_numpy():
+    rng = np.random.RandomState(3)
+    n, U, I = 300000, 50000, 700  # > 2^16 ratings => the threaded fill; ~0.2 % of the users are missing
+    r = np.zeros(n, dtype=cu.RATING_DTYPE)
+    r["user"], r["item"], r["rating"] = np.sort(rng.randint(0, U - 5, n)), rng.randint(0, I, n), rng.randint(1, 6, n)
+    m = cu.createSparseMatrix(r, U, I)
+    assert m.indptr.tolist() == np.searchsorted(r["user"], np.arange(U + 1), side="left").tolist()
+    assert np.array_equal(m.indices, r["item"]) and np.array_equal(m.data, r["rating"])
+    bad = r.copy()
+    bad["user"][200000] = bad["user"][199999] - 1  # first violation decides the message
+    bad["user"][250000] = U + 3
+    with pytest.raises(cu._lib.Cu2bError, match="rating 200000: ratings are not grouped"):
+        cu.createSparseMatrix(bad, U, I)
+    bad["user"][100] = -1
+    with pytest.raises(cu._lib.Cu2bError, match="rating 100: user id -1 outside"):
+        cu.createSparseMatrix(bad, U, I)
+
+
 def test_read_csv_edge_cases(tmp_path):
     # a fourth column ends the parse after the first row (SURVEY 8b; util.cu:30)
     p = tmp_path / "four.csv"
@@ -169,6 +222,38 @@ def test_print_config_format():
 def test_initialize_normal_array_bits(golden_dir, size, k):
     want = np.fromfile(os.path.join(golden_dir, "ref_init_normal_%d_%d.bin" % (size, k)), dtype=np.float32)
     assert cu.initialize_normal_array(size, k).view(np.uint32).tolist() == want.view(np.uint32).tolist()
+
+
+@pytest.mark.parametrize("size,k,mean", [(1 << 18, 128, 0.0), ((1 << 18) + 1, 50, 0.0), (3_000_001, 64, 0.25), (9_000_000, 128, 0.0)])
+def test_initialize_normal_array_parallel_path_is_the_sequential_stream(size, k, mean):
+    """>= 2^18 values take the threaded path (attempts of the polar method evaluated at their fixed
+    positions of the mt19937 stream); it must reproduce std::normal_distribution bit for bit."""
+    got = cu.initialize_normal_array(size, k, mean=mean)
+    want = O.init_normal(size, k, mean=mean)
+    assert got.view(np.uint32).tobytes() == want.view(np.uint32).tobytes()
+
+
+def test_read_array_parallel_path_and_errors(tmp_path):
+    rng = np.random.RandomState(9)
+    mat = (rng.standard_normal((30000, 16)) * 10.0 ** rng.randint(-3, 5, (30000, 16))).astype(np.float32)
+    cu.writeCSV(tmp_path / "m.csv", mat.ravel(), 30000, 16)
+    assert os.path.getsize(tmp_path / "m.csv") > (1 << 20)
+    arr, r, c = cu.read_array(tmp_path / "m.csv")
+    want = np.array([np.float32(t) for t in (tmp_path / "m.csv").read_text().replace("\n", ",").split(",")[:-1]], np.float32)
+    assert (r, c) == (30000, 30000 * 16) and arr.tobytes() == want.tobytes()
+    # trailing comma yields no extra piece, an empty line is a row without values, no final newline
+    (tmp_path / "odd.csv").write_text("1.5,2.5,\n\n 3e1 ,0x10,7")
+    arr, r, c = cu.read_array(tmp_path / "odd.csv")
+    assert (r, c) == (3, 5) and arr.tolist() == [1.5, 2.5, 30.0, 16.0, 7.0]
+    # std::stof would throw on these (util.cu:63)
+    for txt in ("1.0,,2.0\n", "1.0,abc\n", "1.0\n\r\n"):
+        (tmp_path / "bad.csv").write_text(txt)
+        with pytest.raises(cu._lib.Cu2bError, match="not a number"):
+            cu.read_array(tmp_path / "bad.csv")
+    big_bad = (tmp_path / "m.csv").read_text().replace("\n", "\nx,", 20000).replace("\nx,", "\n", 19999)
+    (tmp_path / "bigbad.csv").write_text(big_bad)
+    with pytest.raises(cu._lib.Cu2bError, match="not a number: 'x'"):
+        cu.read_array(tmp_path / "bigbad.csv")
 
 
 def test_write_csv_byte_identical_to_reference(tmp_path, golden_dir):
