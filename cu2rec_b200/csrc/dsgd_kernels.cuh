@@ -42,11 +42,14 @@ __device__ __forceinline__ int item_block_of(int item, const int *sh_ptr, int wo
     return b;
 }
 
-// A sampled draw inside a user's run: the user is implied by the row.
+// A sampled draw inside a user's run: the user is implied by the row. With item-step thinning
+// (opt-in, see dsgd_sample_runs_kernel) bit 31 of `item` marks a draw whose item-side step is
+// skipped; item ids are < 2^31.
 struct __align__(8) DsgdDraw {
     int item;
     float rating;
 };
+constexpr int kDrawItemFrozen = (int)0x80000000u;
 
 // Issue-order-pinned load of a draw (volatile asm, like ldcg_pinned): the prefetch of the next
 // draw stays ahead of the current update's item-row loads.
@@ -61,12 +64,19 @@ __device__ __forceinline__ DsgdDraw ld_draw_pinned(const DsgdDraw *p) {
 // id) and writes them to the user's row of `draws` grouped by item block, iteration order kept
 // inside a block (ballot ranking => deterministic). row_off[a*(world+1)+b] = start of block b
 // inside row a. In sub-epoch b the update kernel walks exactly run [row_off[b], row_off[b+1]).
+//
+// item_keep (optional, experimental: CU2B_DSGD_THIN): keep[i] in (0, 1] is the fraction of item
+// i's draws whose ITEM-side step (Q row, item bias) is applied; for the others only the user side
+// moves (the draw is flagged with kDrawItemFrozen). The decision is the second Philox word of the
+// draw's own counter, so it is a pure function of (seed, user, iteration, keep[item]). This keeps
+// the number of not-yet-visible steps on a popular item under the asynchronous-SGD stability
+// bound without limiting how many user groups run (model: tools/async_sim).
 __global__ void __launch_bounds__(256)
 dsgd_sample_runs_kernel(const int *__restrict__ indptr, const cu2b_rating *__restrict__ coo,
                         const int *__restrict__ active_users, const int *__restrict__ user_ids,
                         int n_active, uint32_t seed, int iter0, int nb, int pitch,
                         const int *__restrict__ item_block_ptr, int world, DsgdDraw *__restrict__ draws,
-                        int *__restrict__ row_off) {
+                        int *__restrict__ row_off, const float *__restrict__ item_keep) {
     __shared__ int sh_ptr[kMaxWorld + 1];
     if (threadIdx.x <= world) sh_ptr[threadIdx.x] = item_block_ptr[threadIdx.x];
     __syncthreads();
@@ -110,11 +120,13 @@ dsgd_sample_runs_kernel(const int *__restrict__ indptr, const cu2b_rating *__res
             DsgdDraw d;
             d.item = 0; d.rating = 0.f;
             if (t < nb) {
-                const uint32_t r = philox4x32_10_x(uid, (uint32_t)(iter0 + t), 0u, PHILOX_TAG, seed, PHILOX_KEY1);
-                const int j = lo + (int)__umulhi(r, (uint32_t)n);
+                const uint2 r = philox4x32_10_xy(uid, (uint32_t)(iter0 + t), 0u, PHILOX_TAG, seed, PHILOX_KEY1);
+                const int j = lo + (int)__umulhi(r.x, (uint32_t)n);
                 d.item = __ldg(&coo[j].item);
                 d.rating = __ldg(&coo[j].rating);
                 blk = item_block_of(d.item, sh_ptr, world);
+                if (item_keep && (float)(r.y >> 8) * (1.0f / 16777216.0f) >= __ldg(&item_keep[d.item]))
+                    d.item |= kDrawItemFrozen;
             }
 #pragma unroll
             for (int b = 0; b < kMaxWorld; ++b) {
@@ -147,7 +159,9 @@ struct UserRunParams {
     int is_train;
 };
 
-template <int L, int V>
+// THIN: the draws may carry kDrawItemFrozen (item-step thinning); the default instantiation does
+// not look at the bit.
+template <int L, int V, bool THIN = false>
 __global__ void __launch_bounds__(256)
 mf_sgd_user_runs(const UserRunParams p) {
     constexpr int G = 32 / L;
@@ -199,7 +213,11 @@ mf_sgd_user_runs(const UserRunParams p) {
             const DsgdDraw d = nxt;
             nxt = nxt2;
             if (j + 2 < end) nxt2 = ld_draw_pinned(row + j + 2);
-            user_side_update<L, V>(pv, ub, d.item, d.rating, ok, l, vecs, Qv, p.item_bias, p.mu, lr, sc, p.is_train);
+            if (THIN)
+                user_side_update<L, V>(pv, ub, d.item & ~kDrawItemFrozen, d.rating, ok, l, vecs, Qv, p.item_bias, p.mu, lr, sc,
+                                       d.item < 0 ? 0 : p.is_train);
+            else
+                user_side_update<L, V>(pv, ub, d.item, d.rating, ok, l, vecs, Qv, p.item_bias, p.mu, lr, sc, p.is_train);
             ++j;
         }
         if (mine) {

@@ -404,6 +404,23 @@ UserRunKernel pick_user_runs(int L, int V) {
     }
 }
 
+UserRunKernel pick_user_runs_thin(int L, int V) {
+    switch (L) {
+        case 1: return mf_sgd_user_runs<1, 1, true>;
+        case 2: return mf_sgd_user_runs<2, 1, true>;
+        case 4: return mf_sgd_user_runs<4, 1, true>;
+        case 8: return mf_sgd_user_runs<8, 1, true>;
+        case 16: return mf_sgd_user_runs<16, 1, true>;
+        default:
+            switch (V) {
+                case 1: return mf_sgd_user_runs<32, 1, true>;
+                case 2: return mf_sgd_user_runs<32, 2, true>;
+                case 3: return mf_sgd_user_runs<32, 3, true>;
+                default: return mf_sgd_user_runs<32, 4, true>;
+            }
+    }
+}
+
 UserTileKernel pick_user_tiles(int L, int V) {
     switch (L) {
         case 1: return mf_sgd_user_tiles<1, 1>;
@@ -478,13 +495,9 @@ cu2b_status build_block_schedule(const cu2b_rating *coo, int64_t n, int rows, in
     return CU2B_OK;
 }
 
-// Share of the draws of its item block that the most frequently drawn item receives under
-// per-user sampling (one uniform draw per user per iteration). Host CSR only; 0 if unknown.
-double hot_item_share(const cu2b_csr *m, const int *item_block_ptr, int n_blocks) {
-    if (!m || m->on_device || m->nonzeros <= 0) return 0.0;
-    // An estimate is enough (it feeds a bound with a 2x safety margin): every `stride`-th user,
-    // at most ~64 K users, so that session creation does not pay a pass over all ratings.
-    const int stride = std::max(1, m->rows / 65536);
+// w[i] = expected draws of item i per iteration under per-user sampling (one uniform draw per
+// user per iteration), from every `stride`-th user. Host CSR only.
+std::vector<double> item_draw_weights(const cu2b_csr *m, int stride) {
     std::vector<double> w((size_t)m->cols, 0.0);
 #pragma omp parallel
     {
@@ -500,6 +513,16 @@ double hot_item_share(const cu2b_csr *m, const int *item_block_ptr, int n_blocks
 #pragma omp critical
         for (int i = 0; i < m->cols; ++i) w[i] += mine[i];
     }
+    return w;
+}
+
+// Share of the draws of its item block that the most frequently drawn item receives under
+// per-user sampling (one uniform draw per user per iteration). Host CSR only; 0 if unknown.
+double hot_item_share(const cu2b_csr *m, const int *item_block_ptr, int n_blocks) {
+    if (!m || m->on_device || m->nonzeros <= 0) return 0.0;
+    // An estimate is enough (it feeds a bound with a 2x safety margin): every `stride`-th user,
+    // at most ~64 K users, so that session creation does not pay a pass over all ratings.
+    const std::vector<double> w = item_draw_weights(m, std::max(1, m->rows / 65536));
     double hot = 0.0;
     for (int b = 0; b < n_blocks; ++b) {
         const int i0 = item_block_ptr ? item_block_ptr[b] : 0, i1 = item_block_ptr ? item_block_ptr[b + 1] : m->cols;
@@ -508,6 +531,27 @@ double hot_item_share(const cu2b_csr *m, const int *item_block_ptr, int n_blocks
         if (tot > 0) hot = std::max(hot, mx / tot);
     }
     return hot;
+}
+
+// Item-step thinning (experimental, CU2B_DSGD_THIN): keep[i] = fraction of item i's draws whose
+// item-side step is applied so that lr x (item's share of its block's draws) x (user groups in
+// flight) x keep stays <= budget for every item -- the per-item form of inflight_cap below.
+std::vector<float> item_keep_fractions(const cu2b_csr *m, const int *item_block_ptr, int n_blocks, float lr,
+                                       int groups_in_flight, double budget) {
+    std::vector<float> keep((size_t)m->cols, 1.0f);
+    if (m->on_device || m->nonzeros <= 0 || lr <= 0 || budget <= 0) return keep;
+    const std::vector<double> w = item_draw_weights(m, 1);
+    for (int b = 0; b < n_blocks; ++b) {
+        const int i0 = item_block_ptr ? item_block_ptr[b] : 0, i1 = item_block_ptr ? item_block_ptr[b + 1] : m->cols;
+        double tot = 0.0;
+        for (int i = i0; i < i1; ++i) tot += w[i];
+        if (tot <= 0) continue;
+        for (int i = i0; i < i1; ++i) {
+            const double load = (double)lr * (w[i] / tot) * groups_in_flight;
+            if (load > budget) keep[i] = (float)(budget / load);
+        }
+    }
+    return keep;
 }
 
 // Asynchronous SGD is only stable while (updates of one parameter in flight) x lr stays well

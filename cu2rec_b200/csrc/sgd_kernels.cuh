@@ -58,6 +58,23 @@ __device__ __forceinline__ uint32_t philox4x32_10_x(uint32_t c0, uint32_t c1, ui
     return c0;
 }
 
+// Same generator, first two output words (the second one decides the item-step thinning of the
+// DSGD sampler; the first is the rating draw and is bit-identical to philox4x32_10_x).
+__device__ __forceinline__ uint2 philox4x32_10_xy(uint32_t c0, uint32_t c1, uint32_t c2,
+                                                  uint32_t c3, uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+        uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return make_uint2(c0, c1);
+}
+
 // One draw per (iteration, active user): thread i handles draw i of n_iter * n_active and
 // writes it to segment t = i / n_active of the update stream (segment pitch seg_pitch).
 __global__ void __launch_bounds__(256)

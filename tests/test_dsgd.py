@@ -203,3 +203,60 @@ def test_dsgd_reload_equals_fresh_contexts():
         for a, b in zip(d.download(), model):
             assert np.array_equal(np.asarray(a).view(np.uint32), np.asarray(b).view(np.uint32))
         d.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# Experimental (default off, not yet measured on hardware): item-step thinning, CU2B_DSGD_THIN.
+# Run with CU2B_EXPERIMENTAL_TESTS=1 on a GPU box; the model behind it is tools/async_sim.
+# ---------------------------------------------------------------------------------------------
+_experimental = pytest.mark.skipif(not os.environ.get("CU2B_EXPERIMENTAL_TESTS"),
+                                   reason="experimental path; set CU2B_EXPERIMENTAL_TESTS=1")
+
+
+def _with_env(name, value, fn):
+    old = os.environ.get(name)
+    os.environ[name] = value
+    try:
+        return fn()
+    finally:
+        if old is None:
+            del os.environ[name]
+        else:
+            os.environ[name] = old
+
+
+@pytest.mark.gpu
+@_experimental
+def test_dsgd_thinning_with_unreachable_budget_is_the_default_path_bit_for_bit():
+    """keep = 1 for every item: the THIN kernel and the flagging sampler must reproduce the default
+    kernels exactly (disjoint items => any schedule is deterministic)."""
+    rng = np.random.RandomState(4)
+    U, k, iters, ce, world = 600, 32, 48, 16, 2
+    deg = rng.randint(1, 6, U)
+    n = int(deg.sum())
+    tr = np.zeros(n, dtype=cu.RATING_DTYPE)
+    tr["user"], tr["item"], tr["rating"] = np.repeat(np.arange(U), deg), rng.permutation(n), rng.randint(1, 6, n)
+    tr = tr[np.lexsort((tr["item"], tr["user"]))]
+    te = tr[::3].copy()
+    _, base, _ = _run_logical_ranks(world, tr, te, U, n, k, iters, ce)
+    _, thin, _ = _with_env("CU2B_DSGD_THIN", "1e9", lambda: _run_logical_ranks(world, tr, te, U, n, k, iters, ce))
+    for a, b in zip(base, thin):
+        assert a.log() == b.log()
+        for x, y in zip(a.download(), b.download()):
+            assert np.array_equal(np.asarray(x).view(np.uint32), np.asarray(y).view(np.uint32))
+        a.close()
+        b.close()
+
+
+@pytest.mark.gpu
+@_experimental
+def test_dsgd_thinning_trains_to_the_same_rmse():
+    tr, te, U, I = _problem(U=3000, I=400, n=120000)
+    k, iters, ce, world = 16, 160, 40, 4
+    _, base, _ = _run_logical_ranks(world, tr, te, U, I, k, iters, ce)
+    _, thin, _ = _with_env("CU2B_DSGD_THIN", "0.02", lambda: _run_logical_ranks(world, tr, te, U, I, k, iters, ce))
+    a, b = base[0].log()[-1], thin[0].log()[-1]
+    assert np.isfinite(b["test_rmse"]) and abs(a["test_rmse"] - b["test_rmse"]) / a["test_rmse"] < 0.01, (a, b)
+    assert base[0].log() != thin[0].log()  # some item-side steps really were skipped
+    for d in base + thin:
+        d.close()
