@@ -82,6 +82,7 @@ SYMBOLS = {
     "cu2b_session_destroy": (None, [_P]),
     "cu2b_dsgd_partition": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
     "cu2b_dsgd_extract_strip": (C.c_int, [_P, C.c_int64, _P, _P, _P, C.c_int, _P, C.POINTER(C.c_int64)]),
+    "cu2b_dsgd_item_keep": (C.c_int, [C.POINTER(Csr), _P, C.c_int, C.c_float, C.c_int, C.c_double, _P]),
     "cu2b_dsgd_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, C.POINTER(Csr), C.POINTER(Csr),
                                    C.POINTER(Config), _P, _P, _P, _P, C.c_float, _P, _P, C.c_int64, C.c_int64, C.c_int64, _P]),
     "cu2b_dsgd_connect": (C.c_int, [_P, _P]),

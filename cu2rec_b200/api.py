@@ -394,6 +394,17 @@ def dsgd_extract_strip(ratings, part, rank):
     return out
 
 
+def dsgd_item_keep(train_strip, item_block_ptr, learning_rate, groups_in_flight, budget):
+    """Item-step thinning fractions of one rank's strip (experimental; cu2b_dsgd_item_keep, host only)."""
+    keep = np.empty(train_strip.cols, dtype=np.float32)
+    iptr = None if item_block_ptr is None else np.ascontiguousarray(item_block_ptr, dtype=np.int32)
+    world = 1 if iptr is None else len(iptr) - 1
+    m = train_strip.c()
+    check(_lib.load().cu2b_dsgd_item_keep(C.byref(m), None if iptr is None else _ptr(iptr), world, learning_rate,
+                                          groups_in_flight, budget, _ptr(keep)))
+    return keep
+
+
 @dataclass
 class DsgdRankInputs:
     train: "CSRMatrix"

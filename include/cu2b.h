@@ -257,6 +257,13 @@ cu2b_status cu2b_dsgd_extract_strip(const cu2b_rating *ratings, int64_t n, const
                                     const int *user_local, const int *item_new, int rank,
                                     cu2b_rating *out, int64_t *n_out);
 
+/* Host only. Item-step thinning fractions (experimental, opt-in through the environment variable
+ * CU2B_DSGD_THIN=<budget> read by cu2b_dsgd_create): keep[i] in (0, 1] such that
+ * lr x (item i's share of the draws of its item block under per-user sampling) x groups_in_flight x
+ * keep[i] <= budget. Items under the budget keep 1. item_block_ptr == NULL: one block. */
+cu2b_status cu2b_dsgd_item_keep(const cu2b_csr *train_strip, const int *item_block_ptr, int world,
+                                float learning_rate, int groups_in_flight, double budget, float *keep);
+
 #define CU2B_DSGD_HANDLE_BYTES 512
 typedef struct cu2b_dsgd cu2b_dsgd;
 /* One context per rank (one process per GPU, or several contexts in one process). The strips use

@@ -50,6 +50,30 @@ def test_partition_and_strips_cover_the_problem_exactly(world):
     assert np.array_equal(allr, np.sort(tr, order=["user", "item"]))
 
 
+def test_item_keep_fractions_bound_every_items_load():
+    """Host part of the opt-in item-step thinning: lr x share x groups x keep <= budget for every item,
+    keep = 1 below the budget, shares taken per item block under per-user sampling."""
+    tr, te, U, I = _problem(U=3000, I=400, n=120000)
+    world, lr, groups, budget = 4, 0.01, 768, 0.1
+    part = cu.dsgd_partition(tr, U, I, world)
+    for r in range(world):
+        strip = cu.createSparseMatrix(cu.dsgd_extract_strip(tr, part, r), int(part.users_per_block[r]), I)
+        keep = cu.dsgd_item_keep(strip, part.item_block_ptr, lr, groups, budget)
+        deg = np.diff(strip.indptr)
+        w = np.bincount(strip.indices, weights=np.repeat(1.0 / np.maximum(deg, 1), deg), minlength=I)
+        blk = np.searchsorted(part.item_block_ptr, np.arange(I), side="right") - 1
+        share = w / np.bincount(blk, weights=w, minlength=world)[blk]
+        load = lr * share * groups
+        want = np.where(load > budget, budget / np.maximum(load, 1e-300), 1.0)
+        assert np.allclose(keep, want, rtol=1e-5) and keep.max() == 1.0 and 0 < keep.min() < 0.2
+        assert np.all(load * keep <= budget * (1 + 1e-5))
+        assert (keep < 1).sum() > 20  # measured on B200 with these parameters: 62-68 items per rank
+    one = cu.dsgd_item_keep(cu.createSparseMatrix(tr, U, I), None, lr, groups, 1e9)
+    assert np.all(one == 1.0)
+    with pytest.raises(cu._lib.Cu2bError):
+        cu.dsgd_item_keep(cu.createSparseMatrix(tr, U, I), np.array([0, 5, I - 1], np.int32), lr, groups, 0.5)
+
+
 _GLOO_WORKER = r'''
 import os, sys
 sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
