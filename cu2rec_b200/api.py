@@ -582,6 +582,15 @@ def create_config(filename, num_iterations=1000, num_factors=100, learning_rate=
                                               p_reg, q_reg, user_bias_reg, item_bias_reg))
 
 
+def convert_to_np(filename_in, filename_out=None):
+    """preprocessing/convert_to_np.py: CSV float matrix -> .npy as np.save(np.genfromtxt(..., delimiter=',')) writes it."""
+    if filename_out is None:
+        filename_out = os.path.splitext(filename_in)[0] + ".npy"
+    r, c = C.c_int64(), C.c_int64()
+    check(_lib.load().cu2b_prep_convert_to_np(os.fsencode(filename_in), os.fsencode(filename_out), C.byref(r), C.byref(c)))
+    return dict(rows=r.value, cols=c.value, out=filename_out)
+
+
 def write_ratings_csv(path, ratings):
     """Ratings triplets (0-based ids) -> "userId,itemId,rating" CSV with 1-based ids (readCSV's input)."""
     ratings = np.ascontiguousarray(ratings, dtype=RATING_DTYPE)

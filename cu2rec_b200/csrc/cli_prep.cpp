@@ -7,6 +7,7 @@
 //                                                    -> <ratings>_train.csv, <ratings>_test.csv
 //   prep create_config <file> [-n iters] [-f factors] [-l lr] [-s seed] [-p p_reg] [-q q_reg]
 //                      [-u user_bias_reg] [-i item_bias_reg]                        (create_config.py)
+//   prep convert_to_np <matrix.csv> [...]            -> <matrix>.npy                (convert_to_np.py)
 // Host only (no GPU needed).
 #include <getopt.h>
 
@@ -36,7 +37,8 @@ static int usage() {
             "       prep map_netflix <train.txt> <test.txt> <train_out.csv> <test_out.csv>\n"
             "       prep sort_ratings <ratings.csv>\n"
             "       prep split_to_test_train <ratings.csv> <test_ratio> [-s seed]\n"
-            "       prep create_config <file> [-n N] [-f F] [-l LR] [-s SEED] [-p P] [-q Q] [-u UB] [-i IB]\n");
+            "       prep create_config <file> [-n N] [-f F] [-l LR] [-s SEED] [-p P] [-q Q] [-u UB] [-i IB]\n"
+            "       prep convert_to_np <matrix.csv> [...]\n");
     return 2;
 }
 
@@ -97,6 +99,17 @@ int main(int argc, char **argv) {
             }
         }
         if (cu2b_prep_create_config(file, n, f, l, s, p, q, u, i) != CU2B_OK) return fail();
+        return 0;
+    }
+    if (cmd == "convert_to_np") {
+        for (int a = 2; a < argc; ++a) {
+            // convert_to_np.py:11-13: os.path.splitext(filename)[0] + ".npy"
+            const std::string in = argv[a];
+            const size_t slash = in.find_last_of('/'), dot = in.find_last_of('.');
+            const bool has_ext = dot != std::string::npos && dot != 0 && (slash == std::string::npos || dot > slash + 1);
+            const std::string out = (has_ext ? in.substr(0, dot) : in) + ".npy";
+            if (cu2b_prep_convert_to_np(in.c_str(), out.c_str(), nullptr, nullptr) != CU2B_OK) return fail();
+        }
         return 0;
     }
     return usage();

@@ -10,6 +10,8 @@
 //                                            all rows with Python's random.seed(seed) /
 //                                            random.shuffle stream, cut, stable sort by user)
 //   preprocessing/create_config.py:10-19  -> cu2b_prep_create_config
+//   preprocessing/convert_to_np.py:6-13   -> cu2b_prep_convert_to_np (np.genfromtxt(delimiter=',')
+//                                            -> np.save: float64 .npy, version 1.0 header)
 // The scripts hold every row as Python objects (minutes and tens of GB at the Netflix size); here the
 // file is mmap-ed, parsed once, and written with a block formatter. Ratings are parsed to double and
 // printed as Python prints a float (shortest round-trip repr, ".0" for integral values), ids as
@@ -19,8 +21,11 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <omp.h>
+
 #include <algorithm>
 #include <charconv>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -381,4 +386,136 @@ extern "C" cu2b_status cu2b_write_ratings_csv(const char *path, const cu2b_ratin
     std::vector<Row> rows((size_t)n);
     for (int64_t t = 0; t < n; ++t) rows[(size_t)t] = Row{(int64_t)ratings[t].user + 1, (int64_t)ratings[t].item + 1, (double)ratings[t].rating};
     return write_rows(path, rows, nullptr);
+}
+
+// convert_to_np.py:6-8: np.save(out, np.genfromtxt(in, delimiter=',')). genfromtxt drops '#' comments
+// and blank lines, splits on ',', converts every field with float() (a missing or non-numeric field
+// becomes nan), requires the same number of fields on every line, and squeezes the result: a single
+// column or a single row is saved as a 1-D array, a single value as a 0-d array. np.save writes
+// format version 1.0: "\x93NUMPY" 1 0 <u16 header length> <dict> padded with spaces to a multiple of 64
+// bytes and terminated by '\n', then the float64 values in C order.
+extern "C" cu2b_status cu2b_prep_convert_to_np(const char *in_path, const char *out_path, int64_t *n_rows,
+                                               int64_t *n_cols) {
+    if (!in_path || !out_path) return cu2b_fail(CU2B_ERR_INVALID, "cu2b_prep_convert_to_np: null argument");
+    int fd = open(in_path, O_RDONLY);
+    if (fd < 0) return cu2b_fail(CU2B_ERR_IO, "cannot open %s", in_path);
+    struct stat st;
+    fstat(fd, &st);
+    const size_t size = (size_t)st.st_size;
+    const char *base = nullptr;
+    if (size) {
+        base = (const char *)mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (base == MAP_FAILED) { close(fd); return cu2b_fail(CU2B_ERR_IO, "mmap failed for %s", in_path); }
+    }
+    close(fd);
+    const char *end = base + size;
+    int nthreads = std::max(1, omp_get_max_threads());
+    if (size < (1u << 20)) nthreads = 1;
+    std::vector<const char *> cut(nthreads + 1);
+    cut[0] = base;
+    cut[nthreads] = end;
+    for (int t = 1; t < nthreads; ++t) {
+        const char *p = base + size * t / nthreads;
+        const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
+        cut[t] = nl ? nl + 1 : end;
+    }
+    struct Part {
+        std::vector<double> vals;
+        int64_t rows = 0, cols = -1;  // cols of the chunk's first data line
+        int64_t bad_line = -1, bad_cols = 0;  // first line (0-based inside the chunk) with another width
+    };
+    std::vector<Part> part(nthreads);
+    auto is_space = [](char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\v' || c == '\f' || c == '\n'; };
+#pragma omp parallel for num_threads(nthreads) schedule(static, 1)
+    for (int t = 0; t < nthreads; ++t) {
+        Part &pt = part[t];
+        const char *p = cut[t], *e = cut[t + 1];
+        pt.vals.reserve((size_t)(e - p) / 8 + 16);
+        std::string tok;
+        int64_t line_no = 0;
+        while (p < e) {
+            const char *nl = (const char *)memchr(p, '\n', (size_t)(e - p));
+            const char *le = nl ? nl : e;
+            const char *hash = (const char *)memchr(p, '#', (size_t)(le - p));  // comments='#'
+            const char *ce = hash ? hash : le;
+            const char *a = p, *b = ce;
+            while (a < b && is_space(*a)) ++a;
+            while (b > a && is_space(b[-1])) --b;
+            if (a < b) {  // not blank
+                int64_t cols = 0;
+                const char *f = p;  // fields are split on the unstripped line, each field stripped
+                // trailing whitespace / '\r' of the line belongs to the last field and is stripped there
+                while (true) {
+                    const char *comma = (const char *)memchr(f, ',', (size_t)(ce - f));
+                    const char *fe = comma ? comma : ce;
+                    const char *x = f, *y = fe;
+                    while (x < y && is_space(*x)) ++x;
+                    while (y > x && is_space(y[-1])) --y;
+                    double v = NAN;
+                    if (x < y) {
+                        tok.assign(x, (size_t)(y - x));
+                        // float(): no hex floats, nothing may follow the number
+                        if (tok.find_first_of("xX") == std::string::npos) {
+                            char *endp = nullptr;
+                            const double d = strtod(tok.c_str(), &endp);
+                            if (endp == tok.c_str() + tok.size()) v = d;
+                        }
+                    }
+                    pt.vals.push_back(v);
+                    ++cols;
+                    if (!comma) break;
+                    f = comma + 1;
+                }
+                if (pt.cols < 0) pt.cols = cols;
+                else if (cols != pt.cols && pt.bad_line < 0) { pt.bad_line = line_no; pt.bad_cols = cols; }
+                ++pt.rows;
+            }
+            ++line_no;
+            p = nl ? nl + 1 : e;
+        }
+    }
+    if (size) munmap((void *)base, size);
+    int64_t rows = 0, cols = -1;
+    for (int t = 0; t < nthreads; ++t) {
+        if (part[t].cols < 0) continue;
+        if (cols < 0) cols = part[t].cols;
+        if (part[t].cols != cols || part[t].bad_line >= 0)
+            return cu2b_fail(CU2B_ERR_IO, "%s: lines with different numbers of columns (%lld and %lld); genfromtxt raises "
+                             "ValueError here", in_path, (long long)cols,
+                             (long long)(part[t].cols != cols ? part[t].cols : part[t].bad_cols));
+        rows += part[t].rows;
+    }
+    if (cols < 0) cols = 0;
+    // squeezed shape, printed as Python prints a tuple
+    char shape[64];
+    int64_t first_dim = -1;
+    if (rows == 0) { snprintf(shape, sizeof shape, "(0,)"); first_dim = 0; }  // genfromtxt of an empty file: empty 1-D array
+    else if (rows == 1 && cols == 1) snprintf(shape, sizeof shape, "()");
+    else if (rows == 1) { snprintf(shape, sizeof shape, "(%lld,)", (long long)cols); first_dim = cols; }
+    else if (cols == 1) { snprintf(shape, sizeof shape, "(%lld,)", (long long)rows); first_dim = rows; }
+    else { snprintf(shape, sizeof shape, "(%lld, %lld)", (long long)rows, (long long)cols); first_dim = rows; }
+    std::string dict = std::string("{'descr': '<f8', 'fortran_order': False, 'shape': ") + shape + ", }";
+    if (first_dim >= 0) {  // numpy leaves room for the first axis to grow in place (21 digits)
+        char digits[32];
+        const int nd = snprintf(digits, sizeof digits, "%lld", (long long)first_dim);
+        dict.append((size_t)std::max(0, 21 - nd), ' ');
+    }
+    const size_t hlen = dict.size() + 1;
+    const size_t padlen = 64 - ((10 + hlen) % 64);
+    dict.append(padlen, ' ');
+    dict.push_back('\n');
+    if (dict.size() > 65535) return cu2b_fail(CU2B_ERR_UNSUPPORTED, "npy header too long");
+    FILE *f = fopen(out_path, "wb");
+    if (!f) return cu2b_fail(CU2B_ERR_IO, "cannot create %s", out_path);
+    const unsigned char magic[10] = {0x93, 'N', 'U', 'M', 'P', 'Y', 1, 0, (unsigned char)(dict.size() & 0xff),
+                                     (unsigned char)(dict.size() >> 8)};
+    bool ok = fwrite(magic, 1, 10, f) == 10 && fwrite(dict.data(), 1, dict.size(), f) == dict.size();
+    for (int t = 0; t < nthreads && ok; ++t)
+        if (!part[t].vals.empty())
+            ok = fwrite(part[t].vals.data(), sizeof(double), part[t].vals.size(), f) == part[t].vals.size();
+    if (fclose(f) != 0) ok = false;
+    if (!ok) return cu2b_fail(CU2B_ERR_IO, "short write to %s", out_path);
+    if (n_rows) *n_rows = rows;
+    if (n_cols) *n_cols = cols;
+    return CU2B_OK;
 }

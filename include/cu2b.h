@@ -341,6 +341,10 @@ cu2b_status cu2b_write_ratings_csv(const char *path, const cu2b_rating *ratings,
 cu2b_status cu2b_prep_create_config(const char *path, int num_iterations, int num_factors,
                                     double learning_rate, int seed, double p_reg, double q_reg,
                                     double user_bias_reg, double item_bias_reg);
+/* convert_to_np.py:6-13: a float matrix in CSV form -> <out>.npy exactly as
+ * np.save(out, np.genfromtxt(in, delimiter=',')) writes it (float64, squeezed shape). */
+cu2b_status cu2b_prep_convert_to_np(const char *in_path, const char *out_path, int64_t *n_rows,
+                                    int64_t *n_cols);
 
 #ifdef __cplusplus
 }

@@ -74,6 +74,21 @@ def main():
             "-u", 0.01, "-i", 0.125)
         shutil.copy(os.path.join(tmp, "a.cfg"), os.path.join(OUT, "config_defaults.cfg"))
         shutil.copy(os.path.join(tmp, "b.cfg"), os.path.join(OUT, "config_custom.cfg"))
+        # convert_to_np.py on factor files as writeCSV produces them and on the shapes genfromtxt squeezes
+        npy_inputs = {
+            "np_matrix.csv": "".join(",".join("%f" % rng.gauss(0, 0.3) for _ in range(5)) + "\n" for _ in range(24)),
+            "np_column.csv": "".join("%f\n" % rng.gauss(0, 1) for _ in range(17)),
+            "np_scalar.csv": "3.529860\n",
+            "np_row.csv": "1.5,-2.25,1e-3,4\n",
+            "np_odd.csv": "# header comment\n1.0, 2.5 ,abc\n\n4,,6.0  # trailing comment\r\n  \n7,8,nan\n-inf,0x10,1e400",
+            "np_empty_lines_only.csv": "\n\n",
+        }
+        for name, text in npy_inputs.items():
+            with open(os.path.join(OUT, name), "w", newline="") as f:
+                f.write(text)
+            work = shutil.copy(os.path.join(OUT, name), os.path.join(tmp, name))
+            run("convert_to_np.py", work)
+            shutil.copy(os.path.splitext(work)[0] + ".npy", os.path.join(OUT, os.path.splitext(name)[0] + ".npy"))
     finally:
         shutil.rmtree(tmp)
     print("wrote", sorted(os.listdir(OUT)))
