@@ -19,4 +19,7 @@ cu2b_status cu2b_fail(cu2b_status code, const char *fmt, ...)
 // can be moved with 128-bit accesses. Padding elements are zero and stay zero under the update.
 static inline int cu2b_padded_factors(int k) { return (k + 3) & ~3; }
 
+// Threshold below which the chunked file readers stay single-threaded (host_io.cpp).
+size_t cu2b_io_parallel_min_bytes();
+
 #endif  // CU2B_INTERNAL_H_

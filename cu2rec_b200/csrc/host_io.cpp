@@ -40,6 +40,13 @@ extern "C" const char *cu2b_last_error(void) { return g_err; }
 extern "C" int cu2b_version(void) { return CU2B_VERSION; }
 extern "C" void cu2b_free(void *p) { free(p); }
 
+// Files smaller than this are parsed by one thread (CU2B_IO_PARALLEL_MIN_BYTES overrides the
+// 1 MiB default; the tests use it to drive the chunked readers over small, nasty inputs).
+size_t cu2b_io_parallel_min_bytes() {
+    if (const char *e = getenv("CU2B_IO_PARALLEL_MIN_BYTES")) return (size_t)strtoull(e, nullptr, 10);
+    return (size_t)1 << 20;
+}
+
 // ------------------------------------------------------------------------------------------
 // config
 // ------------------------------------------------------------------------------------------
@@ -268,7 +275,7 @@ extern "C" cu2b_status cu2b_read_csv(const char *path, cu2b_rating **ratings, in
 
     int nthreads = std::max(1, omp_get_max_threads());
     size_t body_size = (size_t)(end - body);
-    if (body_size < (1u << 20)) nthreads = 1;
+    if (body_size < cu2b_io_parallel_min_bytes()) nthreads = 1;
     // split at newline boundaries
     std::vector<const char *> cut(nthreads + 1);
     cut[0] = body;
@@ -450,7 +457,7 @@ extern "C" cu2b_status cu2b_read_array(const char *path, float **data, int *n_ro
     close(fd);
     const char *end = base + size;
     int nthreads = std::max(1, omp_get_max_threads());
-    if (size < (1u << 20)) nthreads = 1;
+    if (size < cu2b_io_parallel_min_bytes()) nthreads = 1;
     std::vector<const char *> cut(nthreads + 1);  // line-aligned chunks
     cut[0] = base;
     cut[nthreads] = end;

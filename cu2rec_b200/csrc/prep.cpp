@@ -410,7 +410,7 @@ extern "C" cu2b_status cu2b_prep_convert_to_np(const char *in_path, const char *
     close(fd);
     const char *end = base + size;
     int nthreads = std::max(1, omp_get_max_threads());
-    if (size < (1u << 20)) nthreads = 1;
+    if (size < cu2b_io_parallel_min_bytes()) nthreads = 1;
     std::vector<const char *> cut(nthreads + 1);
     cut[0] = base;
     cut[nthreads] = end;

@@ -132,6 +132,67 @@ def test_read_csv_parallel_slices_compaction_and_fallbacks(tmp_path, case):
     assert np.float32(gb).view(np.uint32) == np.float32(gb2).view(np.uint32)
 
 
+@pytest.fixture
+def tiny_chunks(monkeypatch):
+    """Forces the chunked readers onto every file, however small (8 chunks of a 200-byte file)."""
+    monkeypatch.setenv("CU2B_IO_PARALLEL_MIN_BYTES", "0")
+
+
+def test_read_csv_chunked_reader_fuzz_against_oracle(tmp_path, tiny_chunks):
+    """Chunk cuts land anywhere in small messy files: records straddling a cut, blank lines, several
+    records on a line, garbage that ends the stream, no final newline, chunks without a record."""
+    rng = np.random.RandomState(123)
+    seps = [",", ", ", " ,", " , ", "\t", ";", "|"]
+    for case in range(250):
+        n = rng.randint(0, 60)
+        parts, u = ["userId,itemId,rating" + ("\n" if rng.rand() < 0.95 else "")], 1
+        for r in range(n):
+            u += rng.randint(0, 3)
+            sep = seps[rng.randint(len(seps))]
+            val = rng.choice(["%d" % rng.randint(1, 6), "%.1f" % (rng.randint(1, 11) / 2), "%.3f" % (rng.rand() * 5),
+                              repr(float(rng.rand() * 5)), "%.2e" % (rng.rand() * 5)])
+            rec = "%s%d%s%d%s%s" % (" " * rng.randint(0, 3), u, sep, rng.randint(1, 5000), sep, val)
+            x = rng.rand()
+            end = "\n" if x < 0.7 else "\r\n" if x < 0.8 else " " if x < 0.9 else "\n\n  \n"
+            if rng.rand() < 0.01:
+                rec = "oops" + rec
+            parts.append(rec + end)
+        text = "".join(parts)
+        if rng.rand() < 0.3:
+            text = text.rstrip("\n ")
+        p = tmp_path / ("f%d.csv" % case)
+        p.write_text(text, newline="")
+        a, rows, cols, gb = cu.readCSV(p)
+        b, rows2, cols2, gb2 = O.read_csv(p)
+        assert a.tobytes() == b.tobytes() and (rows, cols) == (rows2, cols2), (case, text)
+        if len(a):
+            assert np.float32(gb).view(np.uint32) == np.float32(gb2).view(np.uint32), (case, text)
+
+
+def test_read_array_and_convert_to_np_chunked_readers_fuzz(tmp_path, tiny_chunks):
+    rng = np.random.RandomState(77)
+    for case in range(150):
+        rows, cols = rng.randint(1, 30), rng.randint(1, 7)
+        lines = []
+        for r in range(rows):
+            toks = []
+            for c in range(cols):
+                v = rng.standard_normal() * 10.0 ** rng.randint(-4, 5)
+                t = rng.choice(["%f" % v, "%d" % int(v), "%.3e" % v, repr(float(np.float32(v)))])
+                toks.append(" " * rng.randint(0, 2) + t + " " * rng.randint(0, 2))
+            lines.append(",".join(toks))
+        text = "\n".join(lines) + ("\n" if rng.rand() < 0.7 else "")
+        p = tmp_path / ("m%d.csv" % case)
+        p.write_text(text)
+        arr, r, c = cu.read_array(p)
+        want = np.array([np.float32(t) for ln in lines for t in ln.split(",")], np.float32)
+        assert (r, c) == (rows, rows * cols) and arr.tobytes() == want.tobytes(), (case, text)
+        info = cu.convert_to_np(str(p))
+        got = np.load(info["out"])
+        assert np.array_equal(got, np.squeeze(np.array([[float(t) for t in ln.split(",")] for ln in lines]))), (case, text)
+        assert (tmp_path / ("m%d.npy" % case)).read_bytes()[:6] == b"\x93NUMPY"
+
+
 def test_build_csr_parallel_path_matches_numpy():
     rng = np.random.RandomState(3)
     n, U, I = 300000, 50000, 700  # > 2^16 ratings => the threaded fill; ~0.2 % of the users are missing
