@@ -413,12 +413,65 @@ def run_ours(args):
         return out, sess_e.log()[-1]["test_rmse"]
 
     e2e_s, e2e_all, (_, e2e_rmse) = median_ms(e2e_once, e2e_steps)  # >= 3 repeats, median
+
+    # The same steps with the input feed double-buffered, as a training loop prefetches its next batch: two
+    # resident sessions; while one runs step i and hands back its result, a second host thread uploads step
+    # i + 1's inputs into the other (ctypes releases the GIL inside the library). Every step still pays its
+    # full H2D, its 500 iterations and its D2H inside the timed region; the first upload is not overlapped.
+    pipelined = None
+    try:
+        sess_f = cu.Session(ptr, pte, cfg_e, hP, hQ, hub, hib, mu)
+        pair = (sess_e, sess_f)
+
+        def upload(sx, box):
+            try:
+                sx.reload(ptr, pte, hP, hQ, hub, hib, mu)
+            except Exception as exc:  # surfaced on the main thread
+                box.append(exc)
+
+        def pipelined_once(n_steps):
+            errs, rmses = [], []
+            t0 = time.perf_counter()
+            th = threading.Thread(target=upload, args=(pair[0], errs))
+            th.start()
+            for i in range(n_steps):
+                th.join()
+                if errs:
+                    raise errs[0]
+                if i + 1 < n_steps:
+                    th = threading.Thread(target=upload, args=(pair[(i + 1) % 2], errs))
+                    th.start()
+                cur = pair[i % 2]
+                cur.run(T)
+                cur.download(out=(oP, oQ, oub, oib))
+                rmses.append(cur.log()[-1]["test_rmse"])
+            return (time.perf_counter() - t0) / n_steps, rmses
+
+        pipelined_once(2)  # warm-up
+        p_s, p_rmse = pipelined_once(e2e_steps)
+        if all(abs(r - e2e_rmse) / e2e_rmse < 0.005 for r in p_rmse):
+            pipelined = {"value": T * U / p_s, "ms_per_step": 1e3 * p_s, "steps": e2e_steps,
+                         "test_rmse": [round(r, 5) for r in p_rmse],
+                         "what": "two resident sessions, double-buffered input feed: step i+1's cu2b_session_reload (H2D of "
+                                 "both rating matrices + initial model, pinned) is issued from a second host thread while "
+                                 "step i runs its %d iterations and downloads (D2H of P, Q, biases); wall clock of %d "
+                                 "consecutive steps / %d, the first upload not overlapped" % (T, e2e_steps, e2e_steps)}
+        else:
+            log("[bench] pipelined e2e: RMSE mismatch %s vs %s; not reported" % (p_rmse, e2e_rmse))
+        sess_f.close()
+    except Exception as exc:
+        log("[bench] pipelined e2e not measured: %r" % (exc,))
     sess_e.close()
     cold_s, cold_all, _ = median_ms(e2e_cold_once, 3)
-    e2e = {"value": T * U / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "ms_per_step": 1e3 * e2e_s, "steps": e2e_steps, "ms_all_steps": e2e_all,
-           "what": "resident session; per step: cu2b_session_reload (H2D of both rating matrices + initial model from "
-                   "pinned host memory) + %d iterations + download (D2H of P, Q, biases)" % T,
+    seq_what = ("resident session; per step: cu2b_session_reload (H2D of both rating matrices + initial model from "
+                "pinned host memory) + %d iterations + download (D2H of P, Q, biases), one step after the other" % T)
+    sequential = {"value": T * U / e2e_s, "ms_per_step": 1e3 * e2e_s, "steps": e2e_steps, "ms_all_steps": e2e_all,
+                  "what": seq_what}
+    # headline = the better of the two feeds of the SAME per-step work (both are listed)
+    best = pipelined if pipelined is not None and pipelined["value"] > sequential["value"] else sequential
+    e2e = {"value": best["value"], "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "ms_per_step": best["ms_per_step"], "steps": e2e_steps, "feed": "pipelined" if best is pipelined else "sequential",
+           "what": best["what"], "sequential": sequential, "pipelined": pipelined,
            "cold": {"value": T * U / cold_s, "ms_per_step": 1e3 * cold_s, "ms_all_steps": cold_all,
                     "what": "cu2b_session_create + %d iterations + download + destroy (allocation and set-up included)" % T}}
 
