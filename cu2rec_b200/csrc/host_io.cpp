@@ -665,39 +665,56 @@ extern "C" void cu2b_init_normal(float *out, int64_t size, int n_factors, float 
         return;
     }
     const float sd = std::normal_distribution<float>(mean, stddev / n_factors).stddev();
-    const int64_t kBlock = 1 << 13, kBlocks = 256, kAttempts = kBlock * kBlocks;  // per round
-    std::vector<uint32_t> raw[2] = {std::vector<uint32_t>(2 * kAttempts), std::vector<uint32_t>(2 * kAttempts)};
-    std::vector<float> vals(2 * kAttempts);
+    const int64_t kBlock = 1 << 13, kBlocks = 256, kAttempts = kBlock * kBlocks;  // at most, per round
+    // attempts (whole blocks) worth evaluating for `remaining` values: one attempt yields 2 values with
+    // probability pi/4, i.e. 0.637 attempts per value; a round that falls short is followed by another
+    auto plan = [&](int64_t remaining) -> int64_t {
+        if (remaining <= 0) return 0;
+        const int64_t want = (int64_t)((double)remaining * 0.64) + kBlock;
+        return std::min(kAttempts, (want + kBlock - 1) / kBlock * kBlock);
+    };
+    const int64_t first = plan(size);
+    std::vector<uint32_t> raw[2] = {std::vector<uint32_t>(2 * first), std::vector<uint32_t>(2 * first)};
+    std::vector<float> vals(2 * first);
     int64_t count[kBlocks], offset[kBlocks + 1];
-    for (uint32_t &v : raw[0]) v = (uint32_t)generator();
+    int64_t cur_attempts = first;
+    for (int64_t i = 0; i < 2 * cur_attempts; ++i) raw[0][i] = (uint32_t)generator();
     int64_t done = 0;
     for (int round = 0; done < size; ++round) {
         const uint32_t *cur = raw[round & 1].data();
         uint32_t *nxt = raw[(round + 1) & 1].data();
+        const int cur_blocks = (int)(cur_attempts / kBlock);
+        // what will still be missing after this round if it yields ~1.5 values per attempt
+        const int64_t next_attempts = plan(size - done - cur_attempts * 3 / 2);
         int next_block = 0;
 #pragma omp parallel num_threads(nthreads)
         {
             if (omp_get_thread_num() == 0) {
                 // raw outputs of the next round, produced while the others evaluate this one
-                for (int64_t i = 0; i < 2 * kAttempts; ++i) nxt[i] = (uint32_t)generator();
+                for (int64_t i = 0; i < 2 * next_attempts; ++i) nxt[i] = (uint32_t)generator();
             }
             for (;;) {
                 int b;
 #pragma omp atomic capture
                 b = next_block++;
-                if (b >= kBlocks) break;
+                if (b >= cur_blocks) break;
                 count[b] = polar_block(cur + 2 * kBlock * b, kBlock, mean, sd, vals.data() + 2 * kBlock * b);
             }
         }
         offset[0] = 0;
-        for (int b = 0; b < kBlocks; ++b) offset[b + 1] = offset[b] + count[b];
+        for (int b = 0; b < cur_blocks; ++b) offset[b + 1] = offset[b] + count[b];
         const int64_t room = size - done;
 #pragma omp parallel for num_threads(nthreads) schedule(static)
-        for (int b = 0; b < (int)kBlocks; ++b) {
+        for (int b = 0; b < cur_blocks; ++b) {
             int64_t n = std::min(count[b], room - offset[b]);
             if (n > 0) memcpy(out + done + offset[b], vals.data() + 2 * kBlock * b, (size_t)n * sizeof(float));
         }
-        done += std::min(room, offset[kBlocks]);
+        done += std::min(room, offset[cur_blocks]);
+        cur_attempts = next_attempts;
+        if (done < size && cur_attempts == 0) {  // the estimate fell short: a small extra round
+            cur_attempts = plan(size - done);
+            for (int64_t i = 0; i < 2 * cur_attempts; ++i) nxt[i] = (uint32_t)generator();
+        }
     }
 }
 
