@@ -107,8 +107,9 @@ inline std::vector<Rating> readCSV(const std::string &filename, int *rows, int *
         fprintf(stderr, "ERROR: The file isnt open.\n");  // util.cu:42
         return out;
     }
-    out.resize((size_t)n);
-    if (n) memcpy(out.data(), r, sizeof(Rating) * (size_t)n);
+    // one pass (no zero-fill before the copy): the file may hold 10^8 ratings
+    const Rating *first = reinterpret_cast<const Rating *>(r);
+    if (n) out.assign(first, first + n);
     cu2b_free(r);
     return out;
 }
