@@ -291,3 +291,72 @@ def test_dsgd_thinning_trains_to_the_same_rmse():
     assert base[0].log() != thin[0].log()  # some item-side steps really were skipped
     for d in base + thin:
         d.close()
+
+
+@pytest.mark.gpu
+@_experimental
+def test_dsgd_thinning_bit_exact_against_oracle_replay_on_disjoint_items():
+    """With items never shared between users every schedule is deterministic, so the thinned DSGD run can be
+    replayed on the CPU: a user's draws of a round grouped by item block in the rank's sub-epoch order, the
+    item side frozen for the draws whose second Philox word falls above keep[item] (cu2b_dsgd_item_keep)."""
+    import ctypes as C
+    rng = np.random.RandomState(8)
+    U, k, iters, ce, world, grid, budget, lr = 400, 32, 48, 16, 2, 2, 2e-4, 0.01
+    deg = rng.randint(1, 6, U)
+    n = int(deg.sum())
+    tr = np.zeros(n, dtype=cu.RATING_DTYPE)
+    tr["user"], tr["item"], tr["rating"] = np.repeat(np.arange(U), deg), rng.permutation(n), rng.randint(1, 6, n)
+    tr = tr[np.lexsort((tr["item"], tr["user"]))]
+    te = tr[::3].copy()
+
+    def run():
+        return _with_env("CU2B_DSGD_GRID", str(grid), lambda: _with_env(
+            "CU2B_DSGD_THIN", repr(budget), lambda: _run_logical_ranks(world, tr, te, U, n, k, iters, ce)))
+    part, ranks, (P, Q, ub, ib, mu) = run()
+    groups = grid * 8 * (32 // 8)  # kp = 32 -> 8 lanes per rating, 4 lane groups per warp, 8 warps per CTA
+    keeps = []
+    for r in range(world):
+        strip = cu.createSparseMatrix(cu.dsgd_extract_strip(tr, part, r), int(part.users_per_block[r]), n)
+        keeps.append(cu.dsgd_item_keep(strip, part.item_block_ptr, lr, groups, budget))
+        assert 0.02 < keeps[-1].min() < 0.9  # thinning is really active
+    # replay in original ids
+    full = cu.createSparseMatrix(tr, U, n)
+    item_blk = np.searchsorted(part.item_block_ptr, part.item_new, side="right") - 1
+    Po, Qo, ubo, ibo = P.copy(), Q.copy(), ub.copy(), ib.copy()
+    h1, h0 = O.hyper(k), O.hyper(k)
+    h0.is_train = 0
+    bounds = [0, 1] + list(range(ce, iters + 1, ce))  # segments end after every check iteration (1, 16, 32, 48)
+    out, key = (C.c_uint32 * 4)(), (C.c_uint32 * 2)(42, 0x43553242)
+    frozen_total = 0
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        draws = O.sample_per_user(full.indptr, full.indices, full.data, 42, a, b - a).reshape(b - a, U)
+        stream, flags = [], []
+        for u in range(U):
+            r = int(part.user_block[u])
+            for sub in range(world):
+                blk = (r + sub) % world
+                for t in range(b - a):
+                    d = draws[t, u]
+                    if item_blk[d["item"]] != blk:
+                        continue
+                    O.lib().orc_philox4x32_10((C.c_uint32 * 4)(u, a + t, 0, 0x53474431), key, out)
+                    frozen = np.float32(out[1] >> 8) * np.float32(1.0 / 16777216.0) >= keeps[r][part.item_new[d["item"]]]
+                    stream.append(d)
+                    flags.append(bool(frozen))
+        stream, flags = np.array(stream, dtype=O.TRIPLET), np.array(flags)
+        frozen_total += int(flags.sum())
+        cuts = np.flatnonzero(np.diff(flags.astype(np.int8))) + 1
+        for lo, hi in zip(np.r_[0, cuts], np.r_[cuts, len(stream)]):
+            Po, Qo, ubo, ibo = O.sgd_apply_stream(stream[lo:hi], Po, Qo, ubo, ibo, mu, h0 if flags[lo] else h1, O.FLAVOUR_KERNEL)
+    assert frozen_total > iters * U // 10
+    Qg = ibg = None
+    for r, d in enumerate(ranks):
+        Ps, Qn, ubs, ibn = d.download()
+        users = np.flatnonzero(part.user_block == r)
+        assert np.array_equal(Ps.view(np.uint32), Po.reshape(U, k)[users].view(np.uint32))
+        assert np.array_equal(ubs.view(np.uint32), ubo[users].view(np.uint32))
+        if r == 0:
+            Qg, ibg = Qn[part.item_new], ibn[part.item_new]
+        d.close()
+    assert np.array_equal(Qg.view(np.uint32), Qo.reshape(n, k).view(np.uint32))
+    assert np.array_equal(ibg.view(np.uint32), ibo.view(np.uint32))
