@@ -1,6 +1,7 @@
 """BASELINE config 5: batched predict of the whole Netflix-shape catalogue (480 189 x 17 770, k=128),
 top-10 unrated items per user, on the tensor cores; a random sample of users is checked against
-the CPU brute force. Prints one JSON line."""
+the CPU brute force (the oracle: this script lives under tests/ because only tests may use it).
+Prints one JSON line (profiles/r1_predict.json).   python tests/predict_full_size.py"""
 import json
 import os
 import sys
@@ -10,7 +11,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import bench  # noqa: E402
 import cu2rec_b200 as cu  # noqa: E402
 import oracle as O  # noqa: E402
