@@ -231,7 +231,11 @@ cu2b_status cu2b_session_stats(cu2b_session *s, cu2b_stats *out, int reset);
  * already owns, and resets the schedule state (learning rate, patience, log, iteration counter,
  * statistics) to the configuration the session was created with. A repeated train() on
  * same-shaped data (hyper-parameter sweeps, retraining on a refreshed snapshot) then pays the
- * host->device copies but no allocation or set-up. Hogwild mode only. */
+ * host->device copies but no allocation or set-up. Hogwild mode only. The launch geometry,
+ * including the bound on concurrently applied updates that keeps asynchronous SGD stable (it
+ * depends on the most popular item's share of the draws and on the learning rate), is fixed at
+ * creation: reload data whose item popularity is markedly more concentrated, or a larger learning
+ * rate, into a NEW session instead. */
 cu2b_status cu2b_session_reload(cu2b_session *s, const cu2b_csr *train, const cu2b_csr *test,
                                 const float *P, const float *Q, const float *user_bias,
                                 const float *item_bias, float global_bias);
