@@ -270,7 +270,7 @@ def config_dict(args, k):
             "l2": "inputs larger than L2 (P %d MB + rating/update streams >> 126 MB)" % (U * k * 4 >> 20),
             "lr": 0.01, "reg": 0.02, "check_error": args.iters_per_step,
             # experiment switches that change what runs (none set = the defaults DESIGN.md describes)
-            **{"env": {n: os.environ[n] for n in ("CU2B_DSGD_THIN", "CU2B_DSGD_ROUND", "CU2B_INFLIGHT_LR", "CU2B_ROUND",
+            **{"env": {n: os.environ[n] for n in ("CU2B_DSGD_THIN", "CU2B_DSGD_THIN_BIAS", "CU2B_DSGD_ROUND", "CU2B_INFLIGHT_LR", "CU2B_ROUND",
                                                   "CU2B_TILE_PIPE") if n in os.environ}}}
 
 

@@ -43,13 +43,15 @@ __device__ __forceinline__ int item_block_of(int item, const int *sh_ptr, int wo
 }
 
 // A sampled draw inside a user's run: the user is implied by the row. With item-step thinning
-// (opt-in, see dsgd_sample_runs_kernel) bit 31 of `item` marks a draw whose item-side step is
-// skipped; item ids are < 2^31.
+// (opt-in, see dsgd_sample_runs_kernel) bit 31 of `item` marks a draw whose item ROW step is
+// skipped and bit 30 one whose item BIAS step is skipped; item ids are < 2^30 then.
 struct __align__(8) DsgdDraw {
     int item;
     float rating;
 };
-constexpr int kDrawItemFrozen = (int)0x80000000u;
+constexpr int kDrawRowFrozen = (int)0x80000000u;
+constexpr int kDrawBiasFrozen = 0x40000000;
+constexpr int kDrawItemMask = 0x3fffffff;
 
 // Issue-order-pinned load of a draw (volatile asm, like ldcg_pinned): the prefetch of the next
 // draw stays ahead of the current update's item-row loads.
@@ -65,18 +67,20 @@ __device__ __forceinline__ DsgdDraw ld_draw_pinned(const DsgdDraw *p) {
 // inside a block (ballot ranking => deterministic). row_off[a*(world+1)+b] = start of block b
 // inside row a. In sub-epoch b the update kernel walks exactly run [row_off[b], row_off[b+1]).
 //
-// item_keep (optional, experimental: CU2B_DSGD_THIN): keep[i] in (0, 1] is the fraction of item
-// i's draws whose ITEM-side step (Q row, item bias) is applied; for the others only the user side
-// moves (the draw is flagged with kDrawItemFrozen). The decision is the second Philox word of the
-// draw's own counter, so it is a pure function of (seed, user, iteration, keep[item]). This keeps
-// the number of not-yet-visible steps on a popular item under the asynchronous-SGD stability
-// bound without limiting how many user groups run (model: tools/async_sim).
+// keep_row / keep_bias (optional, opt-in: CU2B_DSGD_THIN / CU2B_DSGD_THIN_BIAS): keep[i] in (0, 1] is the
+// fraction of item i's draws whose item ROW step / item BIAS step is applied; a draw that skips one is
+// flagged with kDrawRowFrozen / kDrawBiasFrozen (the user side always moves). The decision is the second
+// Philox word of the draw's own counter compared with keep[item], so it is a pure function of (seed, user,
+// iteration, keep[item]) and the two events are nested. This keeps the number of not-yet-visible steps on
+// a popular item under the asynchronous-SGD stability bound without limiting how many user groups run
+// (model: tools/async_sim: the bound is set by the item BIAS, whose curvature is 1).
 __global__ void __launch_bounds__(256)
 dsgd_sample_runs_kernel(const int *__restrict__ indptr, const cu2b_rating *__restrict__ coo,
                         const int *__restrict__ active_users, const int *__restrict__ user_ids,
                         int n_active, uint32_t seed, int iter0, int nb, int pitch,
                         const int *__restrict__ item_block_ptr, int world, DsgdDraw *__restrict__ draws,
-                        int *__restrict__ row_off, const float *__restrict__ item_keep) {
+                        int *__restrict__ row_off, const float *__restrict__ keep_row,
+                        const float *__restrict__ keep_bias) {
     __shared__ int sh_ptr[kMaxWorld + 1];
     if (threadIdx.x <= world) sh_ptr[threadIdx.x] = item_block_ptr[threadIdx.x];
     __syncthreads();
@@ -125,8 +129,13 @@ dsgd_sample_runs_kernel(const int *__restrict__ indptr, const cu2b_rating *__res
                 d.item = __ldg(&coo[j].item);
                 d.rating = __ldg(&coo[j].rating);
                 blk = item_block_of(d.item, sh_ptr, world);
-                if (item_keep && (float)(r.y >> 8) * (1.0f / 16777216.0f) >= __ldg(&item_keep[d.item]))
-                    d.item |= kDrawItemFrozen;
+                if (keep_row || keep_bias) {
+                    const float x = (float)(r.y >> 8) * (1.0f / 16777216.0f);
+                    int flags = 0;
+                    if (keep_row && x >= __ldg(&keep_row[d.item])) flags |= kDrawRowFrozen;
+                    if (keep_bias && x >= __ldg(&keep_bias[d.item])) flags |= kDrawBiasFrozen;
+                    d.item |= flags;
+                }
             }
 #pragma unroll
             for (int b = 0; b < kMaxWorld; ++b) {
@@ -159,8 +168,8 @@ struct UserRunParams {
     int is_train;
 };
 
-// THIN: the draws may carry kDrawItemFrozen (item-step thinning); the default instantiation does
-// not look at the bit.
+// THIN: the draws may carry kDrawRowFrozen / kDrawBiasFrozen (item-step thinning); the default
+// instantiation does not look at the bits.
 template <int L, int V, bool THIN = false>
 __global__ void __launch_bounds__(256)
 mf_sgd_user_runs(const UserRunParams p) {
@@ -214,8 +223,8 @@ mf_sgd_user_runs(const UserRunParams p) {
             nxt = nxt2;
             if (j + 2 < end) nxt2 = ld_draw_pinned(row + j + 2);
             if (THIN)
-                user_side_update<L, V>(pv, ub, d.item & ~kDrawItemFrozen, d.rating, ok, l, vecs, Qv, p.item_bias, p.mu, lr, sc,
-                                       d.item < 0 ? 0 : p.is_train);
+                user_side_update<L, V, true>(pv, ub, d.item & kDrawItemMask, d.rating, ok, l, vecs, Qv, p.item_bias, p.mu, lr, sc,
+                                             p.is_train ? ((d.item < 0 ? 0 : 1) | ((d.item & kDrawBiasFrozen) ? 0 : 2)) : 0);
             else
                 user_side_update<L, V>(pv, ub, d.item, d.rating, ok, l, vecs, Qv, p.item_bias, p.mu, lr, sc, p.is_train);
             ++j;

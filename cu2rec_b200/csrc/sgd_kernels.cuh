@@ -177,7 +177,9 @@ __device__ __forceinline__ void item_side_load(ItemSide<V> &it, int item, bool o
 }
 // The arithmetic of one update given its operands; P slice and user bias are updated in place,
 // the item row and item bias take their steps as L2 atomic adds.
-template <int L, int V>
+// MASKED (the thinning instantiations of the DSGD kernel only): is_train is a bit mask, bit 0 = the item
+// row takes its step, bit 1 = the item bias takes its step; otherwise it is the plain 0 / 1 flag.
+template <int L, int V, bool MASKED = false>
 __device__ __forceinline__ void user_side_apply(float4 (&pv)[V], float &ub, const ItemSide<V> &it, int item, float rating,
                                                 bool ok, int l, int vecs, float4 *Qv, float *item_bias, float mu,
                                                 float lr, const StepCoef &sc, int is_train) {
@@ -207,21 +209,21 @@ __device__ __forceinline__ void user_side_apply(float4 (&pv)[V], float &ub, cons
             pv[v].y = __fadd_rn(x.y, sgd_step(ea, y.y, sc.cP, x.y));
             pv[v].z = __fadd_rn(x.z, sgd_step(ea, y.z, sc.cP, x.z));
             pv[v].w = __fadd_rn(x.w, sgd_step(ea, y.w, sc.cP, x.w));
-            if (is_train && v * L + l < vecs) red_add_v4(Qv + qo + v * L, nq);
+            if ((MASKED ? (is_train & 1) : is_train) && v * L + l < vecs) red_add_v4(Qv + qo + v * L, nq);
         }
-        if (is_train && l == 0) red_add_f32(item_bias + item, bias_step(ea, sc.cI, it.ib));
+        if ((MASKED ? (is_train & 2) : is_train) && l == 0) red_add_f32(item_bias + item, bias_step(ea, sc.cI, it.ib));
         ub = __fadd_rn(ub, bias_step(ea, sc.cU, ub));
     }
 }
 // One update with the user side held in registers (the user-major kernels: mf_sgd_user_rounds,
 // mf_sgd_user_tiles, mf_sgd_user_runs). `ok` false => the group idles through the warp-wide shuffles.
-template <int L, int V>
+template <int L, int V, bool MASKED = false>
 __device__ __forceinline__ void user_side_update(float4 (&pv)[V], float &ub, int item, float rating, bool ok, int l,
                                                  int vecs, float4 *Qv, float *item_bias, float mu, float lr,
                                                  const StepCoef &sc, int is_train) {
     ItemSide<V> it;
     item_side_load<L, V>(it, item, ok, l, vecs, Qv, item_bias);
-    user_side_apply<L, V>(pv, ub, it, item, rating, ok, l, vecs, Qv, item_bias, mu, lr, sc, is_train);
+    user_side_apply<L, V, MASKED>(pv, ub, it, item, rating, ok, l, vecs, Qv, item_bias, mu, lr, sc, is_train);
 }
 
 // Model rows are read-write data shared by every SM: they are read with ld.global.cg and, on

@@ -49,7 +49,8 @@ typedef struct {
     int n_factors;
     float learning_rate;
     float P_reg, Q_reg, user_bias_reg, item_bias_reg;
-    int is_train;  // 0 => Q and item_bias frozen (predict.cu:105 intent)
+    int is_train;  // 0 => Q and item_bias frozen (predict.cu:105 intent); 1 => both trained;
+                   // 2 => only item_bias, 3 => only the Q row (the two halves of our DSGD item-step thinning)
 } orc_hyper;
 
 // ---------------------------------------------------------------------------------------
@@ -228,6 +229,7 @@ float orc_sgd_update_one(float *p, float *q, float *ub, float *ib, float rating,
     const int k = h->n_factors;
     const float lr = h->learning_rate;
     float ub0 = *ub, ib0 = *ib;
+    const bool train_row = h->is_train == 1 || h->is_train == 3, train_bias = h->is_train == 1 || h->is_train == 2;
     float err = rating - orc_predict(p, q, k, ub0, ib0, mu, flavour);
     if (flavour != ORC_FLAVOUR_REF) {
         // Op order of the CUDA kernels (sgd_kernels.cuh, sgd_step): the learning rate is folded
@@ -241,10 +243,10 @@ float orc_sgd_update_one(float *p, float *q, float *ub, float *ib, float rating,
             float p_old = p[f];
             float q_old = q[f];
             p[f] = p_old + fmaf(a, q_old, -(cP * p_old));
-            if (h->is_train) q[f] = q_old + fmaf(a, p_old, -(cQ * q_old));
+            if (train_row) q[f] = q_old + fmaf(a, p_old, -(cQ * q_old));
         }
         *ub = ub0 + fmaf(-cU, ub0, a);
-        if (h->is_train) *ib = ib0 + fmaf(-cI, ib0, a);
+        if (train_bias) *ib = ib0 + fmaf(-cI, ib0, a);
         return err;
     }
     for (int f = 0; f < k; ++f) {
@@ -253,14 +255,14 @@ float orc_sgd_update_one(float *p, float *q, float *ub, float *ib, float rating,
         float gp = err * q_old;
         float rp = h->P_reg * p_old;
         p[f] = p_old + lr * (gp - rp);
-        if (h->is_train) {
+        if (train_row) {
             float gq = err * p_old;
             float rq = h->Q_reg * q_old;
             q[f] = q_old + lr * (gq - rq);
         }
     }
     *ub = ub0 + lr * (err - h->user_bias_reg * ub0);
-    if (h->is_train) *ib = ib0 + lr * (err - h->item_bias_reg * ib0);
+    if (train_bias) *ib = ib0 + lr * (err - h->item_bias_reg * ib0);
     return err;
 }
 

@@ -290,7 +290,8 @@ def test_dsgd_thinning_trains_to_the_same_rmse():
 
 
 @pytest.mark.gpu
-def test_dsgd_thinning_bit_exact_against_oracle_replay_on_disjoint_items():
+@pytest.mark.parametrize("what", ["rows_and_bias", "bias_only", "rows_0.0002_bias_0.0001"])
+def test_dsgd_thinning_bit_exact_against_oracle_replay_on_disjoint_items(what):
     """With items never shared between users every schedule is deterministic, so the thinned DSGD run can be
     replayed on the CPU: a user's draws of a round grouped by item block in the rank's sub-epoch order, the
     item side frozen for the draws whose second Philox word falls above keep[item] (cu2b_dsgd_item_keep)."""
@@ -304,22 +305,38 @@ def test_dsgd_thinning_bit_exact_against_oracle_replay_on_disjoint_items():
     tr = tr[np.lexsort((tr["item"], tr["user"]))]
     te = tr[::3].copy()
 
-    def run():
-        return _with_env("CU2B_DSGD_GRID", str(grid), lambda: _with_env(
-            "CU2B_DSGD_THIN", repr(budget), lambda: _run_logical_ranks(world, tr, te, U, n, k, iters, ce)))
+    # budgets of the row steps and of the bias steps (0 = that switch is not set); a draw that skips the row
+    # step always skips the bias step too
+    b_rows, b_bias = {"rows_and_bias": (budget, 0.0), "bias_only": (0.0, budget), "rows_0.0002_bias_0.0001": (budget, budget / 2)}[what]
+    env = {"CU2B_DSGD_GRID": str(grid)}
+    if b_rows:
+        env["CU2B_DSGD_THIN"] = repr(b_rows)
+    if b_bias:
+        env["CU2B_DSGD_THIN_BIAS"] = repr(b_bias)
+
+    def run(names=tuple(env)):
+        if not names:
+            return _run_logical_ranks(world, tr, te, U, n, k, iters, ce)
+        return _with_env(names[0], env[names[0]], lambda: run(names[1:]))
     part, ranks, (P, Q, ub, ib, mu) = run()
     groups = grid * 8 * (32 // 8)  # kp = 32 -> 8 lanes per rating, 4 lane groups per warp, 8 warps per CTA
-    keeps = []
+    keeps_row, keeps_bias = [], []
     for r in range(world):
         strip = cu.createSparseMatrix(cu.dsgd_extract_strip(tr, part, r), int(part.users_per_block[r]), n)
-        keeps.append(cu.dsgd_item_keep(strip, part.item_block_ptr, lr, groups, budget))
-        assert 0.02 < keeps[-1].min() < 0.9  # thinning is really active
+        one = np.ones(n, np.float32)
+        kr = cu.dsgd_item_keep(strip, part.item_block_ptr, lr, groups, b_rows) if b_rows else one
+        kb = np.minimum(kr, cu.dsgd_item_keep(strip, part.item_block_ptr, lr, groups, b_bias)) if b_bias else kr
+        keeps_row.append(kr)
+        keeps_bias.append(kb)
+        assert 0.01 < kb.min() < 0.9  # thinning is really active
     # replay in original ids
     full = cu.createSparseMatrix(tr, U, n)
     item_blk = np.searchsorted(part.item_block_ptr, part.item_new, side="right") - 1
     Po, Qo, ubo, ibo = P.copy(), Q.copy(), ub.copy(), ib.copy()
-    h1, h0 = O.hyper(k), O.hyper(k)
-    h0.is_train = 0
+    hyp = {}
+    for code in (0, 1, 2, 3):  # oracle is_train codes: 0 none, 1 row + bias, 2 bias only, 3 row only
+        hyp[code] = O.hyper(k)
+        hyp[code].is_train = code
     bounds = [0, 1] + list(range(ce, iters + 1, ce))  # segments end after every check iteration (1, 16, 32, 48)
     out, key = (C.c_uint32 * 4)(), (C.c_uint32 * 2)(42, 0x43553242)
     frozen_total = 0
@@ -335,14 +352,16 @@ def test_dsgd_thinning_bit_exact_against_oracle_replay_on_disjoint_items():
                     if item_blk[d["item"]] != blk:
                         continue
                     O.lib().orc_philox4x32_10((C.c_uint32 * 4)(u, a + t, 0, 0x53474431), key, out)
-                    frozen = np.float32(out[1] >> 8) * np.float32(1.0 / 16777216.0) >= keeps[r][part.item_new[d["item"]]]
+                    x = np.float32(out[1] >> 8) * np.float32(1.0 / 16777216.0)
+                    new_id = part.item_new[d["item"]]
+                    row_on, bias_on = x < keeps_row[r][new_id], x < keeps_bias[r][new_id]
                     stream.append(d)
-                    flags.append(bool(frozen))
+                    flags.append({(True, True): 1, (False, True): 2, (True, False): 3, (False, False): 0}[(bool(row_on), bool(bias_on))])
         stream, flags = np.array(stream, dtype=O.TRIPLET), np.array(flags)
-        frozen_total += int(flags.sum())
-        cuts = np.flatnonzero(np.diff(flags.astype(np.int8))) + 1
+        frozen_total += int((flags != 1).sum())
+        cuts = np.flatnonzero(np.diff(flags)) + 1
         for lo, hi in zip(np.r_[0, cuts], np.r_[cuts, len(stream)]):
-            Po, Qo, ubo, ibo = O.sgd_apply_stream(stream[lo:hi], Po, Qo, ubo, ibo, mu, h0 if flags[lo] else h1, O.FLAVOUR_KERNEL)
+            Po, Qo, ubo, ibo = O.sgd_apply_stream(stream[lo:hi], Po, Qo, ubo, ibo, mu, hyp[int(flags[lo])], O.FLAVOUR_KERNEL)
     assert frozen_total > iters * U // 10
     Qg = ibg = None
     for r, d in enumerate(ranks):

@@ -17,8 +17,9 @@
 // of its users that fall into item block (g + s) mod G. Ranks never share a row, so they are
 // simulated one after the other.
 //
-// item_scale (optional) multiplies the item-side steps of an item (staleness-aware step), or, with
-// thin != 0, is the fraction of the item's draws whose item-side step is applied at all.
+// item_scale (optional): per-item factor m <= 1 for the items whose load exceeds the budget; `mode` says how
+// it is used (0 scale both item-side steps, 1 thin both, 2 scale the bias step only, 3 thin the bias step
+// only, 4 thin the row step only).
 //
 // The update itself follows mf_sequential.cu:114-141 (right-hand sides use the pre-update values).
 #include <cmath>
@@ -68,7 +69,7 @@ extern "C" int async_sim_train(int rows, int cols, const int *indptr, const int 
                                const int *te_indptr, const int *te_indices, const float *te_data, float *P, float *Q,
                                float *ub, float *ib, float mu, int k, float lr, float reg, int seed,
                                int total_iterations, int check_error, int G, const int *user_block,
-                               const int *item_block, int round_iters, int inflight, float stale_factor, const float *item_scale, int thin,
+                               const int *item_block, int round_iters, int inflight, float stale_factor, const float *item_scale, int mode,
                                double *log /* rows of {iteration, test_rmse, max unseen steps at a read} */, int log_cap) {
     (void)cols;
     int n_log = 0;
@@ -134,31 +135,41 @@ extern "C" int async_sim_train(int rows, int cols, const int *indptr, const int 
                         float pred = mu + ub[u] + ib[i];
                         for (int f = 0; f < k; ++f) pred += q[f] * p[f];
                         const float err = data[j] - pred;
-                        float m = item_scale ? item_scale[i] : 1.0f;
+                        const float m = item_scale ? item_scale[i] : 1.0f;
                         if (unseen[i] > max_conc) max_conc = unseen[i];
-                        if (thin && m < 1.0f) {
-                            // thinning instead of scaling: the item side takes the full step for a fraction m
-                            // of its draws (decided by a hash of the draw) and none for the others
-                            uint32_t ctr[4] = {(uint32_t)u, (uint32_t)(it0 + gr.pos), 1u, 0x53474431u}, key[2] = {(uint32_t)seed, 0x43553242u}, r[4];
-                            philox4x32_10(ctr, key, r);
-                            if ((float)(r[0] >> 8) * (1.0f / 16777216.0f) >= m) {
-                                for (int f = 0; f < k; ++f) p[f] = p[f] + lr * (err * q[f] - reg * p[f]);
-                                ub[u] = ub[u] + lr * (err - reg * ub[u]);
-                                ++started;
-                                ++gr.pos;
-                                if (!advance(gr)) --busy;
-                                continue;
+                        // what the item side of this draw takes: mode 0 scales both steps by m; 1 applies both for
+                        // a fraction m of the draws (thinning); 2 / 3 scale / thin the bias step only; 4 thins the
+                        // row step only
+                        float m_row = 1.0f, m_bias = 1.0f;
+                        if (m < 1.0f) {
+                            bool keep = true;
+                            if (mode == 1 || mode == 3 || mode == 4) {
+                                uint32_t ctr[4] = {(uint32_t)u, (uint32_t)(it0 + gr.pos), 1u, 0x53474431u}, key[2] = {(uint32_t)seed, 0x43553242u}, r[4];
+                                philox4x32_10(ctr, key, r);
+                                keep = (float)(r[0] >> 8) * (1.0f / 16777216.0f) < m;
                             }
-                            m = 1.0f;
+                            if (mode == 0) m_row = m_bias = m;
+                            else if (mode == 1) m_row = m_bias = keep ? 1.0f : 0.0f;
+                            else if (mode == 2) m_bias = m;
+                            else if (mode == 3) m_bias = keep ? 1.0f : 0.0f;
+                            else if (mode == 4) m_row = keep ? 1.0f : 0.0f;
+                        }
+                        if (m_row == 0.0f && m_bias == 0.0f) {  // nothing to add: only the user side moves
+                            for (int f = 0; f < k; ++f) p[f] = p[f] + lr * (err * q[f] - reg * p[f]);
+                            ub[u] = ub[u] + lr * (err - reg * ub[u]);
+                            ++started;
+                            ++gr.pos;
+                            if (!advance(gr)) --busy;
+                            continue;
                         }
                         const size_t e = tail % ring_cap;
                         float *step = pend_step.data() + e * (k + 1);
                         for (int f = 0; f < k; ++f) {
                             const float p_old = p[f], q_old = q[f];
                             p[f] = p_old + lr * (err * q_old - reg * p_old);
-                            step[f] = m * (lr * (err * p_old - reg * q_old));
+                            step[f] = m_row * (lr * (err * p_old - reg * q_old));
                         }
-                        step[k] = m * (lr * (err - reg * ib[i]));
+                        step[k] = m_bias * (lr * (err - reg * ib[i]));
                         ub[u] = ub[u] + lr * (err - reg * ub[u]);
                         pend_item[e] = i;
                         pend_start[e] = started;

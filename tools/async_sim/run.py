@@ -41,7 +41,8 @@ def draw_weights(mtr):
 
 def run_one(job):
     name, G, inflight, stale, scale_budget, args = job
-    thin = "thinned" in name
+    mode = {"scale": 0, "thinned": 1, "bias scaled": 2, "bias thinned": 3, "rows thinned": 4}.get(
+        next((t for t in ("bias scaled", "bias thinned", "rows thinned", "thinned", "scale") if t in name), "scale"), 0)
     import cu2rec_b200 as cu
     lib = C.CDLL(os.path.join(ROOT, "tools", "async_sim", "libasync_sim.so"))
     tr, mtr, mte, mu, (P, Q, ub, ib) = problem(args["U"], args["I"], args["n"], args["k"])
@@ -67,7 +68,7 @@ def run_one(job):
     n = lib.async_sim_train(U, I, _p(mtr.indptr), _p(mtr.indices), _p(mtr.data), _p(mte.indptr), _p(mte.indices), _p(mte.data),
                             _p(P), _p(Q), _p(ub), _p(ib), C.c_float(mu), k, C.c_float(lr), C.c_float(args["reg"]), 42,
                             args["iters"], args["check"], G, _p(user_block), _p(item_block), args["round"], inflight, C.c_float(stale),
-                            _p(scale) if scale is not None else None, int(thin), _p(log), cap)
+                            _p(scale) if scale is not None else None, mode, _p(log), cap)
     rows = log[: 3 * min(n, cap)].reshape(-1, 3)
     rm = [None if not np.isfinite(r) else round(float(r), 5) for r in rows[:, 1]]
     return {"config": name, "ranks": G, "inflight_per_rank": inflight, "hot_share_in_block": round(hot, 5),
@@ -105,6 +106,9 @@ def main():
             ("8 ranks, full occupancy, no cap", 8, full, stale, 0.0, args),
             ("8 ranks, full occupancy, item step scale (budget 0.5)", 8, full, stale, 0.5, args),
             ("8 ranks, full occupancy, item steps thinned (budget 0.5)", 8, full, stale, 0.5, args),
+            ("8 ranks, full occupancy, only the item bias scaled (budget 0.5)", 8, full, stale, 0.5, args),
+            ("8 ranks, full occupancy, only the item bias thinned (budget 0.5)", 8, full, stale, 0.5, args),
+            ("8 ranks, full occupancy, only the item rows thinned (budget 0.5)", 8, full, stale, 0.5, args),
         ]
     with mp.Pool(min(a.procs, len(jobs))) as pool, open(a.out, "w") as f:
         for res in pool.imap(run_one, jobs):
