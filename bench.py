@@ -52,6 +52,9 @@ WORKLOADS = {
     # one DSGD item block of the netflix shape at 8 GPUs (all users, 1/8 of the items and ratings):
     # single-GPU stand-in for the item-popularity concentration a rank sees inside a sub-epoch
     "nfblock8": (480189, 2221, 12560000, True, 128),
+    # the same for 4 and 2 GPUs (the regime in which round 1's 4-GPU run diverged)
+    "nfblock4": (480189, 4442, 25120000, True, 128),
+    "nfblock2": (480189, 8885, 50240000, True, 128),
 }
 DATA_SEED = 20240607
 METRIC = "sgd_rating_updates_per_sec"

@@ -161,7 +161,7 @@ struct UserRunParams {
     int n_active, pitch, world, block;
     unsigned long long *tile_counter;  // dynamic tile claims (a tile = the G users of one warp); zeroed before launch
     float *P, *Q, *user_bias, *item_bias;
-    int kp;
+    int kp, ibs;
     float mu;
     const float *lr;
     float P_reg, Q_reg, ub_reg, ib_reg;
@@ -223,10 +223,10 @@ mf_sgd_user_runs(const UserRunParams p) {
             nxt = nxt2;
             if (j + 2 < end) nxt2 = ld_draw_pinned(row + j + 2);
             if (THIN)
-                user_side_update<L, V, true>(pv, ub, d.item & kDrawItemMask, d.rating, ok, l, vecs, Qv, p.item_bias, p.mu, lr, sc,
+                user_side_update<L, V, true>(pv, ub, d.item & kDrawItemMask, d.rating, ok, l, vecs, Qv, p.item_bias, p.ibs, p.mu, lr, sc,
                                              p.is_train ? ((d.item < 0 ? 0 : 1) | ((d.item & kDrawBiasFrozen) ? 0 : 2)) : 0);
             else
-                user_side_update<L, V>(pv, ub, d.item, d.rating, ok, l, vecs, Qv, p.item_bias, p.mu, lr, sc, p.is_train);
+                user_side_update<L, V>(pv, ub, d.item, d.rating, ok, l, vecs, Qv, p.item_bias, p.ibs, p.mu, lr, sc, p.is_train);
             ++j;
         }
         if (mine) {
@@ -244,13 +244,14 @@ mf_sgd_user_runs(const UserRunParams p) {
 // dst_flag == nullptr => plain local copy without signalling.
 __global__ void __launch_bounds__(256)
 dsgd_send_block_kernel(const float4 *__restrict__ src_q, float4 *__restrict__ dst_q, long long n_vec,
-                       const float *__restrict__ src_ib, float *__restrict__ dst_ib, int n_items,
+                       const float *__restrict__ src_ib, float *__restrict__ dst_ib, int n_items, int ibs,
                        int *ticket, int *dst_flag, int value) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride)
         dst_q[i] = __ldcg(src_q + i);
+    // the biases live one per line (ItemBiasLayout): only the 4-byte values travel
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += stride)
-        dst_ib[i] = __ldcg(src_ib + i);
+        dst_ib[i * ibs] = __ldcg(src_ib + i * ibs);
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -307,6 +308,7 @@ dsgd_loss_combine_kernel(DevState *st, const double *part_train, int nblk_train,
         const float train_mae = (float)(g[1] / (double)n_train_global);
         const float test_rmse = (float)sqrt(g[2] / (double)n_test_global);
         const float test_mae = (float)(g[3] / (double)n_test_global);
+        flag_non_finite(st, train_rmse, test_rmse, n_train_global, n_test_global, iteration);
         if (apply_schedule) {
             const float last = st->validation_rmse;
             st->validation_rmse = test_rmse;

@@ -631,6 +631,13 @@ struct cu2b_session {
     int rows = 0, cols = 0;
     DevMatrix train, test;
     float *P = nullptr, *Q = nullptr, *ub = nullptr, *ib = nullptr;
+    // ItemBiasLayout: item i's bias is ib[i * ibs]. ibs = 64 floats gives every item its own 256-byte
+    // L2 hash granule: the 4-byte bias read + atomic add of every update then spread over as many L2
+    // slices as the item rows do, instead of piling onto the few lines of a dense array (a DSGD rank's
+    // item block of 2 221 items is 70 lines = 35 granules; measured in profiles/r2_l2_rows_micro.jsonl).
+    // ib_dense: [cols] staging buffer for the dense host-side array (== ib when ibs == 1).
+    int ibs = 1;
+    float *ib_dense = nullptr;
     int *active = nullptr;
     int n_active = 0;
     int *user_ids = nullptr;  // DSGD: original user id of each local user (sampler key), else null
@@ -697,9 +704,60 @@ struct cu2b_session {
 
 namespace {
 
+// ItemBiasLayout helpers (see cu2b_session::ibs)
+__global__ void __launch_bounds__(256)
+bias_scatter_kernel(const float *__restrict__ dense, float *__restrict__ padded, int n, int stride) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) padded[(size_t)i * stride] = dense[i];
+}
+__global__ void __launch_bounds__(256)
+bias_gather_kernel(const float *__restrict__ padded, float *__restrict__ dense, int n, int stride) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dense[i] = __ldcg(padded + (size_t)i * stride);
+}
+
+int item_bias_stride() {
+    int st = 64;
+    if (const char *e = getenv("CU2B_IB_STRIDE")) st = atoi(e);
+    return std::max(1, std::min(64, st));
+}
+
+cu2b_status alloc_item_bias(cu2b_session *s) {
+    s->ibs = item_bias_stride();
+    const size_t n = (size_t)std::max(1, s->cols);
+    CU2B_TRY(s->pool.alloc(&s->ib, n * s->ibs));
+    if (s->ibs == 1) {
+        s->ib_dense = s->ib;
+    } else {
+        CU2B_TRY(s->pool.alloc(&s->ib_dense, n));
+        CUDA_TRY(cudaMemsetAsync(s->ib, 0, n * s->ibs * sizeof(float), s->stream));
+    }
+    return CU2B_OK;
+}
+
+// ib_dense (host order, dense) -> ib (one bias per line); call on a stream ordered after the H2D copy
+cu2b_status scatter_item_bias(cu2b_session *s, cudaStream_t st) {
+    if (s->ibs == 1 || s->cols == 0) return CU2B_OK;
+    bias_scatter_kernel<<<std::max(1, std::min((s->cols + 255) / 256, 592)), 256, 0, st>>>(s->ib_dense, s->ib, s->cols, s->ibs);
+    CUDA_TRY(cudaGetLastError());
+    return CU2B_OK;
+}
+
+cu2b_status download_item_bias(cu2b_session *s, float *host) {
+    if (s->cols == 0) return CU2B_OK;
+    if (s->ibs != 1) {
+        bias_gather_kernel<<<std::max(1, std::min((s->cols + 255) / 256, 592)), 256, 0, s->stream>>>(s->ib, s->ib_dense, s->cols, s->ibs);
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaMemcpyAsync(host, s->ib_dense, (size_t)s->cols * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    return CU2B_OK;
+}
+
 cu2b_status check_device_error(cu2b_session *s) {
     DevState st;
     CUDA_TRY(cudaMemcpy(&st, s->state, sizeof(st), cudaMemcpyDeviceToHost));
+    if (st.error < 0)
+        return cu2b_fail(CU2B_ERR_DIVERGED, "the model became non-finite (NaN/inf RMSE at the loss check of iteration %d): "
+                         "asynchronous SGD diverged; lower the learning rate or the number of concurrently applied updates "
+                         "(CU2B_INFLIGHT_LR)", -st.error - 1);
     if (st.error)
         return cu2b_fail(CU2B_ERR_CUDA, "device-side wait timed out (code %d = site*1e6 + need*100 + seen): %s", st.error,
                          st.error == 2 ? "per-user ordering gate" : "DSGD peer did not deliver");
@@ -710,6 +768,7 @@ cu2b_status launch_loss(cu2b_session *s, const DevMatrix &m, double *partials, i
     LossParams lp;
     lp.sv = flat_view(m.coo, m.nnz, s->loss_chunk);
     lp.P = s->P; lp.Q = s->Q; lp.user_bias = s->ub; lp.item_bias = s->ib;
+    lp.ibs = s->ibs;
     lp.kp = s->kp;
     lp.mu = s->mu;
     lp.partials = partials;
@@ -741,6 +800,7 @@ cu2b_status launch_sgd(cu2b_session *s, const StreamView &sv, int *gate, int seg
     SgdParams sp;
     sp.sv = sv;
     sp.P = s->P; sp.Q = s->Q; sp.user_bias = s->ub; sp.item_bias = s->ib;
+    sp.ibs = s->ibs;
     sp.kp = s->kp;
     sp.mu = s->mu;
     sp.lr = &s->state->lr;
@@ -780,6 +840,7 @@ cu2b_status enqueue_blocked_pass(cu2b_session *s, const cu2b_rating *sched, cons
     sp.dyn_range = nullptr;
     sp.error_flag = nullptr;
     sp.P = s->P; sp.Q = s->Q; sp.user_bias = s->ub; sp.item_bias = s->ib;
+    sp.ibs = s->ibs;
     sp.kp = s->kp;
     sp.mu = s->mu;
     sp.lr = &s->state->lr;
@@ -822,6 +883,7 @@ cu2b_status enqueue_fused_rounds(cu2b_session *s, int iter_abs, int n_seg) {
     rp.n_active = s->n_active;
     rp.seed = (uint32_t)s->cfg.seed;
     rp.P = s->P; rp.Q = s->Q; rp.user_bias = s->ub; rp.item_bias = s->ib;
+    rp.ibs = s->ibs;
     rp.kp = s->kp;
     rp.mu = s->mu;
     rp.lr = &s->state->lr;
@@ -897,6 +959,7 @@ cu2b_status enqueue_tiled_iterations(cu2b_session *s, int iter_abs, int n_seg) {
         tp.tile_counter = s->counters + s->counter_next;
         s->counter_next = (s->counter_next + 1) % s->counter_slots;
         tp.P = s->P; tp.Q = s->Q; tp.user_bias = s->ub; tp.item_bias = s->ib;
+        tp.ibs = s->ibs;
         tp.kp = s->kp;
         tp.mu = s->mu;
         tp.lr = &s->state->lr;
@@ -1013,7 +1076,7 @@ static cu2b_status session_upload(cu2b_session *s, const cu2b_csr *train, const 
         CU2B_TRY(s->pool.alloc(&s->P, (size_t)s->rows * s->kp));
         CU2B_TRY(s->pool.alloc(&s->Q, (size_t)s->cols * s->kp));
         CU2B_TRY(s->pool.alloc(&s->ub, (size_t)s->rows));
-        CU2B_TRY(s->pool.alloc(&s->ib, (size_t)s->cols));
+        CU2B_TRY(alloc_item_bias(s));
     }
     CU2B_TRY(stream_after(lane.st, s->stream, lane.ev));
     // 2. copies back to back on the copy stream; each expansion waits only for its own matrix
@@ -1025,9 +1088,10 @@ static cu2b_status session_upload(cu2b_session *s, const cu2b_csr *train, const 
     CU2B_TRY(upload_dense(lane.st, s->P, P, s->rows, s->k, s->kp));
     CU2B_TRY(upload_dense(lane.st, s->Q, Q, s->cols, s->k, s->kp));
     CUDA_TRY(cudaMemcpyAsync(s->ub, user_bias, (size_t)s->rows * sizeof(float), cudaMemcpyHostToDevice, lane.st));
-    CUDA_TRY(cudaMemcpyAsync(s->ib, item_bias, (size_t)s->cols * sizeof(float), cudaMemcpyHostToDevice, lane.st));
+    CUDA_TRY(cudaMemcpyAsync(s->ib_dense, item_bias, (size_t)s->cols * sizeof(float), cudaMemcpyHostToDevice, lane.st));
     CU2B_TRY(matrix_copy(lane.st, up_test));
     CU2B_TRY(stream_after(s->stream, lane.st, lane.ev));
+    CU2B_TRY(scatter_item_bias(s, s->stream));
     CU2B_TRY(matrix_expand(s->pool, s->stream, up_test));
     return CU2B_OK;
 }
@@ -1217,14 +1281,13 @@ extern "C" cu2b_status cu2b_session_run(cu2b_session *s, int n_iterations) {
     s->timing.end(tot_id, s->stream);
     CUDA_TRY(cudaStreamSynchronize(s->stream));  // the only host sync of the loop
     s->iter_done = end;
-    CU2B_TRY(check_device_error(s));
     double ms[Timing::NKIND] = {0, 0, 0, 0, 0, 0};
     s->timing.collect(ms);
     s->stats.sgd_ms += ms[Timing::SGD];
     s->stats.loss_ms += ms[Timing::LOSS];
     s->stats.sampler_ms += ms[Timing::SAMPLER];
     s->stats.total_ms += ms[Timing::TOTAL];
-    return CU2B_OK;
+    return check_device_error(s);  // a timed-out device-side wait, or a non-finite loss check (CU2B_ERR_DIVERGED)
 }
 
 static cu2b_status session_reload_impl(cu2b_session *s, const cu2b_csr *train, const cu2b_csr *test, const float *P,
@@ -1293,7 +1356,7 @@ extern "C" cu2b_status cu2b_session_download(cu2b_session *s, float *P, float *Q
     if (P) CU2B_TRY(download_dense(s->stream, P, s->P, s->rows, s->k, s->kp));
     if (Q) CU2B_TRY(download_dense(s->stream, Q, s->Q, s->cols, s->k, s->kp));
     if (user_bias) CUDA_TRY(cudaMemcpyAsync(user_bias, s->ub, (size_t)s->rows * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
-    if (item_bias) CUDA_TRY(cudaMemcpyAsync(item_bias, s->ib, (size_t)s->cols * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    if (item_bias) CU2B_TRY(download_item_bias(s, item_bias));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     tr.mark("D2H");
     return CU2B_OK;
@@ -1403,11 +1466,12 @@ struct Scratch {
         CU2B_TRY(s.pool.alloc(&s.P, (size_t)rows * s.kp));
         CU2B_TRY(s.pool.alloc(&s.Q, (size_t)cols * s.kp));
         CU2B_TRY(s.pool.alloc(&s.ub, (size_t)rows));
-        CU2B_TRY(s.pool.alloc(&s.ib, (size_t)cols));
+        CU2B_TRY(alloc_item_bias(&s));
         CU2B_TRY(upload_dense(s.stream, s.P, P, rows, k, s.kp));
         CU2B_TRY(upload_dense(s.stream, s.Q, Q, cols, k, s.kp));
         CUDA_TRY(cudaMemcpyAsync(s.ub, ub, (size_t)rows * sizeof(float), cudaMemcpyHostToDevice, s.stream));
-        CUDA_TRY(cudaMemcpyAsync(s.ib, ib, (size_t)cols * sizeof(float), cudaMemcpyHostToDevice, s.stream));
+        CUDA_TRY(cudaMemcpyAsync(s.ib_dense, ib, (size_t)cols * sizeof(float), cudaMemcpyHostToDevice, s.stream));
+        CU2B_TRY(scatter_item_bias(&s, s.stream));
         s.sgd_kernel = pick_sgd(s.L, s.V);
         s.loss_kernel = pick_loss(s.kp);
         int occ = 0;
@@ -1541,7 +1605,7 @@ extern "C" cu2b_status cu2b_sgd_apply(const cu2b_rating *stream, int64_t n, floa
     CU2B_TRY(download_dense(s.stream, P, s.P, rows, s.k, s.kp));
     CU2B_TRY(download_dense(s.stream, Q, s.Q, cols, s.k, s.kp));
     CUDA_TRY(cudaMemcpyAsync(ub, s.ub, (size_t)rows * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
-    CUDA_TRY(cudaMemcpyAsync(ib, s.ib, (size_t)cols * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    CU2B_TRY(download_item_bias(&s, ib));
     CUDA_TRY(cudaStreamSynchronize(s.stream));
     return CU2B_OK;
 }
@@ -1572,7 +1636,7 @@ extern "C" cu2b_status cu2b_sgd_blocked(const cu2b_rating *coo, int64_t n, float
     CU2B_TRY(download_dense(s.stream, P, s.P, rows, s.k, s.kp));
     CU2B_TRY(download_dense(s.stream, Q, s.Q, cols, s.k, s.kp));
     CUDA_TRY(cudaMemcpyAsync(ub, s.ub, (size_t)rows * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
-    CUDA_TRY(cudaMemcpyAsync(ib, s.ib, (size_t)cols * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    CU2B_TRY(download_item_bias(&s, ib));
     CUDA_TRY(cudaStreamSynchronize(s.stream));
     return CU2B_OK;
 }

@@ -18,6 +18,7 @@ struct LossParams {
     StreamView sv;  // flat stream over the matrix' COO triplets
     const float *P, *Q, *user_bias, *item_bias;
     int kp;
+    int ibs;           // item_bias stride in floats
     float mu;
     double *partials;  // [gridDim.x][2] = {sum err^2, sum |err|}
     float *err_out;    // optional residual vector (stream order), may be nullptr
@@ -79,7 +80,7 @@ mf_loss_fused(const LossParams p) {
                 }
             }
             const float ub = ok ? __ldg(p.user_bias + rt.user) : 0.f;
-            const float ib = ok ? __ldg(p.item_bias + rt.item) : 0.f;
+            const float ib = ok ? __ldg(p.item_bias + (size_t)rt.item * p.ibs) : 0.f;
             const float dot = group_sum<L>(acc);
             const float pred = __fadd_rn(__fadd_rn(__fadd_rn(p.mu, ub), ib), dot);
             const float err = __fsub_rn(rt.rating, pred);
@@ -142,6 +143,17 @@ struct DevState {
     double sums[4];         // last evaluated {train sse, train sae, test sse, test sae}
 };
 
+// Divergence guard: asynchronous SGD can blow up (too large a learning rate for the number of
+// concurrently applied updates on a popular item). A non-finite metric at a loss check
+// is recorded as error = -(iteration + 1); the host turns it into CU2B_ERR_DIVERGED, so a diverged
+// run can never report throughput with rc 0. (A NaN also blinds the reference's patience rule,
+// training.cu:146: `last < NaN` is false.)
+__device__ __forceinline__ void flag_non_finite(DevState *st, float train_rmse, float test_rmse, long long n_train,
+                                                long long n_test, int iteration) {
+    const bool bad = (n_train > 0 && !isfinite(train_rmse)) || (n_test > 0 && !isfinite(test_rmse));
+    if (bad) atomicCAS(&st->error, 0, -(max(iteration, 0) + 1));
+}
+
 // Sums the per-CTA partials of one matrix in a fixed order. One block of 256 threads.
 __device__ __forceinline__ void reduce_partials(const double *partials, int nblk, double *out2,
                                                 double (*sh)[2]) {
@@ -174,6 +186,7 @@ loss_finalize_kernel(DevState *st, const double *part_train, int nblk_train, lon
         const float train_mae = (float)(tot[1] / (double)n_train);
         const float test_rmse = (float)sqrt(tot[2] / (double)n_test);
         const float test_mae = (float)(tot[3] / (double)n_test);
+        flag_non_finite(st, train_rmse, test_rmse, n_train, n_test, iteration);
         if (apply_schedule) {
             const float last = st->validation_rmse;
             st->validation_rmse = test_rmse;

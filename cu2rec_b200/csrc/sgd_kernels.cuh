@@ -22,6 +22,7 @@ struct SgdParams {
     StreamView sv;              // the update stream (device memory)
     float *P, *Q, *user_bias, *item_bias;
     int kp;                     // row pitch in floats (multiple of 4)
+    int ibs;                    // item_bias stride in floats: item i's bias is item_bias[i * ibs] (ItemBiasLayout)
     float mu;
     const float *lr;            // device scalar: current learning rate (decayed on device)
     float P_reg, Q_reg, ub_reg, ib_reg;
@@ -165,10 +166,10 @@ __device__ __forceinline__ float4 ldcg_pinned(const float4 *p) {
 }
 template <int L, int V>
 __device__ __forceinline__ void item_side_load(ItemSide<V> &it, int item, bool ok, int l, int vecs, const float4 *Qv,
-                                               const float *item_bias) {
+                                               const float *item_bias, int ibs) {
     const size_t qo = (size_t)item * vecs + l;
     it.ib = 0.f;
-    if (ok) it.ib = ldcg_pinned(item_bias + item);
+    if (ok) it.ib = ldcg_pinned(item_bias + (size_t)item * ibs);
 #pragma unroll
     for (int v = 0; v < V; ++v) {
         it.q[v] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -181,7 +182,7 @@ __device__ __forceinline__ void item_side_load(ItemSide<V> &it, int item, bool o
 // row takes its step, bit 1 = the item bias takes its step; otherwise it is the plain 0 / 1 flag.
 template <int L, int V, bool MASKED = false>
 __device__ __forceinline__ void user_side_apply(float4 (&pv)[V], float &ub, const ItemSide<V> &it, int item, float rating,
-                                                bool ok, int l, int vecs, float4 *Qv, float *item_bias, float mu,
+                                                bool ok, int l, int vecs, float4 *Qv, float *item_bias, int ibs, float mu,
                                                 float lr, const StepCoef &sc, int is_train) {
     const size_t qo = (size_t)item * vecs + l;
     float acc = 0.f;
@@ -211,7 +212,7 @@ __device__ __forceinline__ void user_side_apply(float4 (&pv)[V], float &ub, cons
             pv[v].w = __fadd_rn(x.w, sgd_step(ea, y.w, sc.cP, x.w));
             if ((MASKED ? (is_train & 1) : is_train) && v * L + l < vecs) red_add_v4(Qv + qo + v * L, nq);
         }
-        if ((MASKED ? (is_train & 2) : is_train) && l == 0) red_add_f32(item_bias + item, bias_step(ea, sc.cI, it.ib));
+        if ((MASKED ? (is_train & 2) : is_train) && l == 0) red_add_f32(item_bias + (size_t)item * ibs, bias_step(ea, sc.cI, it.ib));
         ub = __fadd_rn(ub, bias_step(ea, sc.cU, ub));
     }
 }
@@ -219,11 +220,11 @@ __device__ __forceinline__ void user_side_apply(float4 (&pv)[V], float &ub, cons
 // mf_sgd_user_tiles, mf_sgd_user_runs). `ok` false => the group idles through the warp-wide shuffles.
 template <int L, int V, bool MASKED = false>
 __device__ __forceinline__ void user_side_update(float4 (&pv)[V], float &ub, int item, float rating, bool ok, int l,
-                                                 int vecs, float4 *Qv, float *item_bias, float mu, float lr,
+                                                 int vecs, float4 *Qv, float *item_bias, int ibs, float mu, float lr,
                                                  const StepCoef &sc, int is_train) {
     ItemSide<V> it;
-    item_side_load<L, V>(it, item, ok, l, vecs, Qv, item_bias);
-    user_side_apply<L, V, MASKED>(pv, ub, it, item, rating, ok, l, vecs, Qv, item_bias, mu, lr, sc, is_train);
+    item_side_load<L, V>(it, item, ok, l, vecs, Qv, item_bias, ibs);
+    user_side_apply<L, V, MASKED>(pv, ub, it, item, rating, ok, l, vecs, Qv, item_bias, ibs, mu, lr, sc, is_train);
 }
 
 // Model rows are read-write data shared by every SM: they are read with ld.global.cg and, on
@@ -258,7 +259,7 @@ __device__ __forceinline__ void sgd_update_slots(const SgdParams &p, const cu2b_
             }
         }
         ub[x] = ok[x] ? __ldcg(p.user_bias + rt[x].user) : 0.f;
-        ib[x] = ok[x] ? __ldcg(p.item_bias + rt[x].item) : 0.f;
+        ib[x] = ok[x] ? __ldcg(p.item_bias + (size_t)rt[x].item * p.ibs) : 0.f;
     }
 #pragma unroll
     for (int x = 0; x < UNR; ++x) {
@@ -312,8 +313,8 @@ __device__ __forceinline__ void sgd_update_slots(const SgdParams &p, const cu2b_
             else __stcg(p.user_bias + rt[x].user, __fadd_rn(ub[x], ustep));
             if (p.is_train) {
                 const float step = bias_step(ea, sc.cI, ib[x]);
-                if (ATOMQ) red_add_f32(p.item_bias + rt[x].item, step);
-                else __stcg(p.item_bias + rt[x].item, __fadd_rn(ib[x], step));
+                if (ATOMQ) red_add_f32(p.item_bias + (size_t)rt[x].item * p.ibs, step);
+                else __stcg(p.item_bias + (size_t)rt[x].item * p.ibs, __fadd_rn(ib[x], step));
             }
         }
     }

@@ -34,7 +34,7 @@ struct UserTileParams {
     int n_tiles;
     unsigned long long *tile_counter;
     float *P, *Q, *user_bias, *item_bias;
-    int kp;
+    int kp, ibs;
     float mu;
     const float *lr;
     float P_reg, Q_reg, ub_reg, ib_reg;
@@ -123,7 +123,7 @@ mf_sgd_user_tiles(const UserTileParams p) {
             DsgdDraw d;
             d.item = 0; d.rating = 0.f;
             if (mine) d = row[j];
-            user_side_update<L, V>(pv, ub, d.item, d.rating, mine, l, vecs, Qv, p.item_bias, p.mu, lr, sc, p.is_train);
+            user_side_update<L, V>(pv, ub, d.item, d.rating, mine, l, vecs, Qv, p.item_bias, p.ibs, p.mu, lr, sc, p.is_train);
         }
         if (mine) {
 #pragma unroll
@@ -167,7 +167,7 @@ struct UserRoundParams {
     uint32_t seed;
     int iter0, nb;              // absolute first iteration of the round, iterations in it
     float *P, *Q, *user_bias, *item_bias;
-    int kp;
+    int kp, ibs;
     float mu;
     const float *lr;
     float P_reg, Q_reg, ub_reg, ib_reg;
@@ -234,22 +234,22 @@ mf_sgd_user_rounds(const UserRoundParams p) {
         if (PF) {
             DsgdDraw d = row[0];
             ItemSide<V> cur;
-            item_side_load<L, V>(cur, d.item, mine, l, vecs, Qv, p.item_bias);
+            item_side_load<L, V>(cur, d.item, mine, l, vecs, Qv, p.item_bias, p.ibs);
             for (int j = 0; j < p.nb; ++j) {  // every lane runs nb steps (the shuffles are warp-wide)
                 const bool more = j + 1 < p.nb;
                 const DsgdDraw dn = row[more ? j + 1 : j];
                 const bool repeat = dn.item == d.item;
                 ItemSide<V> nxt;
-                item_side_load<L, V>(nxt, dn.item, mine && more && !repeat, l, vecs, Qv, p.item_bias);
-                user_side_apply<L, V>(pv, ub, cur, d.item, d.rating, mine, l, vecs, Qv, p.item_bias, p.mu, lr, sc, p.is_train);
-                if (repeat) item_side_load<L, V>(nxt, dn.item, mine && more, l, vecs, Qv, p.item_bias);
+                item_side_load<L, V>(nxt, dn.item, mine && more && !repeat, l, vecs, Qv, p.item_bias, p.ibs);
+                user_side_apply<L, V>(pv, ub, cur, d.item, d.rating, mine, l, vecs, Qv, p.item_bias, p.ibs, p.mu, lr, sc, p.is_train);
+                if (repeat) item_side_load<L, V>(nxt, dn.item, mine && more, l, vecs, Qv, p.item_bias, p.ibs);
                 cur = nxt;
                 d = dn;
             }
         } else {
             for (int j = 0; j < p.nb; ++j) {
                 const DsgdDraw d = row[j];
-                user_side_update<L, V>(pv, ub, d.item, d.rating, mine, l, vecs, Qv, p.item_bias, p.mu, lr, sc, p.is_train);
+                user_side_update<L, V>(pv, ub, d.item, d.rating, mine, l, vecs, Qv, p.item_bias, p.ibs, p.mu, lr, sc, p.is_train);
             }
         }
         if (mine) {

@@ -34,7 +34,9 @@ typedef enum cu2b_status {
     CU2B_ERR_IO = 2,          /* file could not be opened / parsed */
     CU2B_ERR_CUDA = 3,        /* CUDA runtime error, no device, wrong architecture */
     CU2B_ERR_NOMEM = 4,
-    CU2B_ERR_UNSUPPORTED = 5  /* e.g. n_factors > 512 */
+    CU2B_ERR_UNSUPPORTED = 5, /* e.g. n_factors > 512 */
+    CU2B_ERR_DIVERGED = 6     /* a loss check saw a non-finite RMSE: the run's results are void (no
+                                 reference counterpart: training.cu:134-158 prints nan and carries on) */
 } cu2b_status;
 
 const char *cu2b_last_error(void);

@@ -18,7 +18,7 @@ inp = cu.dsgd_rank_inputs(tr, te, U, I, part, 0, P, Q, ub, ib)
 os.environ["CU2B_DSGD_ROUND"] = os.environ.get("SWEEP_ROUND", "64")
 for g in sys.argv[1:]:
     budget = os.environ.get("SWEEP_THIN", "0.5")
-    for thin in ("", "bias", "rows+bias"):  # default kernel (grid forced, no cap), bias steps only, row and bias steps
+    for thin in os.environ.get("SWEEP_VARIANTS", ",bias,rows+bias").split(","):  # default kernel (grid forced, no cap), bias steps only, row and bias steps
         os.environ["CU2B_DSGD_GRID"] = g
         os.environ.pop("CU2B_DSGD_THIN", None)
         os.environ.pop("CU2B_DSGD_THIN_BIAS", None)
@@ -28,10 +28,21 @@ for g in sys.argv[1:]:
             os.environ["CU2B_DSGD_THIN"] = budget
         d = cu.Dsgd(0, 1, inp, part, cu.Config(total_iterations=2 * iters, n_factors=k, check_error=iters), mu)
         d.connect([d.handle])
-        d.run(iters); d.stats(reset=True); d.run(iters)
+        diverged = None
+        try:
+            d.run(iters); d.stats(reset=True); d.run(iters)
+        except cu._lib.Cu2bError as exc:  # CU2B_ERR_DIVERGED: the device-side non-finite guard
+            diverged = str(exc)[:160]
         st = d.stats()
+        if diverged or not st["sgd_ms"]:
+            print(json.dumps({"grid": int(g), "thinned": thin or None, "budget": budget if thin else None, "diverged": diverged,
+                              "workload": os.environ.get("SWEEP_WORKLOAD", "nfblock8"), "ib_stride": os.environ.get("CU2B_IB_STRIDE"),
+                              "test_rmse": [(r["iteration"], round(r["test_rmse"], 4)) for r in d.log()]}), flush=True)
+            d.close()
+            continue
         ups = st["updates"] / (st["sgd_ms"] / 1e3)
-        print(json.dumps({"grid": int(g), "thinned": thin or None, "budget": budget if thin else None, "sgd_Gups": round(ups / 1e9, 3), "sgd_ms": round(st["sgd_ms"], 2),
+        print(json.dumps({"grid": int(g), "thinned": thin or None, "budget": budget if thin else None, "workload": os.environ.get("SWEEP_WORKLOAD", "nfblock8"),
+                          "ib_stride": os.environ.get("CU2B_IB_STRIDE"), "sgd_Gups": round(ups / 1e9, 3), "sgd_ms": round(st["sgd_ms"], 2),
                           "sampler_ms": round(st["sampler_ms"], 2),
                           "test_rmse": [(r["iteration"], round(r["test_rmse"], 4)) for r in d.log()]}), flush=True)
         d.close()
