@@ -1,93 +1,139 @@
-// bin/mf -- drop-in for the reference trainer CLI (mf.cu:16-99):
+// bin/mf -- the trainer executable of the drop-in surface.
+//
 //   mf [-c <config>] <train.csv> <test.csv>
-// Same flags, same stdout line formats, same five output files next to the training file
-// (<base>_f<k>_{p,q,user_bias,item_bias,global_bias}.csv, "%f" text). Training runs on the GPU
-// through libcu2b.so; there is no CPU path.
-#include <getopt.h>
+//
+// Contract taken from the reference CLI (mf.cu:16-99; this file shares no code with it):
+//   * no arguments -> exit status 255 without output; an unknown option prints "Unknown option."
+//     and exits 1; -c is optional (defaults of config.h:23-51);
+//   * stdout: "Free memory: <bytes>" + blank line, the hyper-parameter block, the TRAIN / TEST
+//     lines of every loss check, the "Time taken" line;
+//   * five "%f" CSV files next to the training file: <stem>_f<k>_{p,q,user_bias,item_bias,global_bias}.csv,
+//     the set bin/predict (ours or the reference's) loads.
+// With config token 17 (n_gpus) > 1 the same call trains by DSGD on that many GPUs of the box.
+// Everything numeric happens on the GPU inside libcu2b.so; there is no CPU training path.
+#include <unistd.h>
 
 #include <algorithm>
-#include <iostream>
+#include <cstdio>
+#include <exception>
+#include <filesystem>
+#include <memory>
+#include <string>
+#include <vector>
 
 #include "cu2rec_shim.h"
 
-using namespace cu2rec;
-using std::string;
+namespace fs = std::filesystem;
+
+namespace {
+
+enum class ArgStatus { ok, nothing_given, bad_option, missing_files };
+
+struct CommandLine {
+    std::string config_file;  // empty: built-in defaults
+    fs::path train_file, test_file;
+};
+
+ArgStatus read_command_line(int argc, char **argv, CommandLine *cl) {
+    if (argc <= 1) return ArgStatus::nothing_given;
+    for (int opt; (opt = getopt(argc, argv, "c:")) != -1;) {
+        if (opt != 'c') return ArgStatus::bad_option;
+        cl->config_file = optarg;
+    }
+    if (argc - optind < 2) return ArgStatus::missing_files;
+    cl->train_file = argv[optind];
+    cl->test_file = argv[optind + 1];
+    return ArgStatus::ok;
+}
+
+// One ratings CSV in memory together with what the reader derives from it.
+struct RatingSet {
+    std::vector<Rating> triplets;
+    int n_users = 0, n_items = 0;
+    float mean = 0.f;
+    explicit RatingSet(const fs::path &file) { triplets = readCSV(file.string(), &n_users, &n_items, &mean); }
+};
+
+// Output files sit beside the training file and reuse its name without the extension.
+struct OutputPlace {
+    std::string directory, stem;
+    explicit OutputPlace(const fs::path &train_file) {
+        const fs::path parent = train_file.parent_path();
+        directory = parent.empty() ? std::string(".") : parent.string();
+        stem = train_file.stem().string();
+    }
+    void put(const char *component, float *values, int rows, int cols, int n_factors) const {
+        writeToFile(directory, stem, "csv", component, values, rows, cols, n_factors);
+    }
+};
+
+struct TrainedModel {  // owns what train() hands back through its pointer-to-pointer outputs
+    std::unique_ptr<float[]> user_factors, item_factors, user_bias, item_bias, validation_curve;
+};
+
+TrainedModel fit(cu2rec::CudaCSRMatrix &train_m, cu2rec::CudaCSRMatrix &test_m, config::Config &cfg, float mean_rating) {
+    float *p = nullptr, *q = nullptr, *curve = nullptr, *bu = nullptr, *bi = nullptr;
+    train(&train_m, &test_m, &cfg, &p, &q, &curve, &bu, &bi, mean_rating);
+    TrainedModel m;
+    m.user_factors.reset(p);
+    m.item_factors.reset(q);
+    m.validation_curve.reset(curve);
+    m.user_bias.reset(bu);
+    m.item_bias.reset(bi);
+    return m;
+}
+
+int run(const CommandLine &cl) {
+    size_t device_total = 0;
+    std::printf("Free memory: %ld\n\n", (long)getFreeBytes(0, &device_total));
+
+    RatingSet train_set(cl.train_file), test_set(cl.test_file);
+    // The model must cover every id that occurs in either file. (The reference sizes each matrix
+    // from its own file, mf.cu:43-51, and indexes past P / Q when the test file reaches further.)
+    const int n_users = std::max(train_set.n_users, test_set.n_users);
+    const int n_items = std::max(train_set.n_items, test_set.n_items);
+    std::unique_ptr<cu2rec::CudaCSRMatrix> train_m(createSparseMatrix(&train_set.triplets, n_users, n_items));
+    std::unique_ptr<cu2rec::CudaCSRMatrix> test_m(createSparseMatrix(&test_set.triplets, n_users, n_items));
+
+    config::Config cfg;
+    if (!cl.config_file.empty()) cfg.read_config(cl.config_file);
+    cfg.print_config();
+
+    TrainedModel model = fit(*train_m, *test_m, cfg, train_set.mean);
+
+    const OutputPlace out(cl.train_file);
+    const int k = cfg.n_factors;
+    out.put("p", model.user_factors.get(), n_users, k, k);
+    out.put("q", model.item_factors.get(), n_items, k, k);
+    out.put("user_bias", model.user_bias.get(), n_users, 1, k);
+    out.put("item_bias", model.item_bias.get(), n_items, 1, k);
+    float mean_cell = train_set.mean;
+    out.put("global_bias", &mean_cell, 1, 1, k);
+    return 0;
+}
+
+}  // namespace
 
 int main(int argc, char **argv) {
-    if (argc < 2) return -1;  // mf.cu:17-19
-    string filename_config;
-    int o;
-    while ((o = getopt(argc, argv, "c:")) != -1) {
-        switch (o) {
-            case 'c':
-                filename_config = optarg;
-                break;
-            default:
-                std::cout << "Unknown option.\n";  // mf.cu:28-29
-                return 1;
-        }
-    }
-    if (argc - optind < 2) {
-        std::cerr << "usage: mf [-c config] train.csv test.csv\n";
-        return -1;
+    CommandLine cl;
+    switch (read_command_line(argc, argv, &cl)) {
+        case ArgStatus::nothing_given:
+            return -1;
+        case ArgStatus::bad_option:
+            std::puts("Unknown option.");
+            return 1;
+        case ArgStatus::missing_files:
+            std::fputs("usage: mf [-c config] train.csv test.csv\n", stderr);
+            return -1;
+        case ArgStatus::ok:
+            break;
     }
     try {
-        size_t total_bytes;
-        const long free_bytes_before = (long)getFreeBytes(0, &total_bytes);
-        printf("Free memory: %ld\n\n", free_bytes_before);  // mf.cu:37
-
-        string file_path_train = argv[optind++];
-        int rows, cols;
-        float global_bias;
-        std::vector<Rating> train_ratings = readCSV(file_path_train, &rows, &cols, &global_bias);
-        string file_path_test = argv[optind++];
-        int r, c;
-        float gb;
-        std::vector<Rating> test_ratings = readCSV(file_path_test, &r, &c, &gb);
-        // The reference sizes the test matrix from the test file alone (mf.cu:50-51) and then
-        // reads P/Q out of bounds if it is larger; we size the model with max(train, test).
-        rows = std::max(rows, r);
-        cols = std::max(cols, c);
-        CudaCSRMatrix *train_matrix = createSparseMatrix(&train_ratings, rows, cols);
-        CudaCSRMatrix *test_matrix = createSparseMatrix(&test_ratings, rows, cols);
-
-        config::Config *cfg = new config::Config();
-        if (!filename_config.empty()) cfg->read_config(filename_config);
-        cfg->print_config();
-
-        float *P, *Q, *losses, *user_bias, *item_bias;
-        train(train_matrix, test_matrix, cfg, &P, &Q, &losses, &user_bias, &item_bias, global_bias);
-
-        // mf.cu:65-77: outputs go next to the training file
-        size_t dir_index = file_path_train.find_last_of("/");
-        string parent_dir, filename;
-        if (dir_index != string::npos) {
-            parent_dir = file_path_train.substr(0, dir_index);
-            filename = file_path_train.substr(dir_index + 1);
-        } else {
-            parent_dir = ".";
-            filename = file_path_train;
-        }
-        string basename = filename.substr(0, filename.find_last_of("."));
-        float global_bias_array[1] = {global_bias};
-        writeToFile(parent_dir, basename, "csv", "p", P, rows, cfg->n_factors, cfg->n_factors);
-        writeToFile(parent_dir, basename, "csv", "q", Q, cols, cfg->n_factors, cfg->n_factors);
-        writeToFile(parent_dir, basename, "csv", "user_bias", user_bias, rows, 1, cfg->n_factors);
-        writeToFile(parent_dir, basename, "csv", "item_bias", item_bias, cols, 1, cfg->n_factors);
-        writeToFile(parent_dir, basename, "csv", "global_bias", global_bias_array, 1, 1, cfg->n_factors);
-
-        delete cfg;
-        delete train_matrix;
-        delete test_matrix;
-        delete[] P;
-        delete[] Q;
-        delete[] losses;
-        delete[] user_bias;
-        delete[] item_bias;
-    } catch (const std::exception &e) {
-        // the reference lets std::runtime_error escape to std::terminate (util.h:27-34)
-        std::cerr << "terminate called after throwing an instance of 'std::runtime_error'\n  what():  " << e.what() << "\n";
+        return run(cl);
+    } catch (const std::exception &err) {
+        // An uncaught std::runtime_error is how the reference ends on a CUDA failure (util.h:27-34):
+        // same message shape on stderr, same abort status.
+        std::fprintf(stderr, "terminate called after throwing an instance of 'std::runtime_error'\n  what():  %s\n", err.what());
         return 134;
     }
-    return 0;
 }

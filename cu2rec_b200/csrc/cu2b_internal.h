@@ -19,6 +19,15 @@ cu2b_status cu2b_fail(cu2b_status code, const char *fmt, ...)
 // can be moved with 128-bit accesses. Padding elements are zero and stay zero under the update.
 static inline int cu2b_padded_factors(int k) { return (k + 3) & ~3; }
 
+// Row placement rule shared by the session (engine.cu) and the DSGD partition (host_io.cpp): slot[r] = row
+// offset inside a range of n rows starting at matrix row `first_row` for the item of popularity rank r.
+void cu2b_paired_slots(int n, int first_row, int rows_per_block, int *slot);
+int cu2b_rows_per_l2_block(int n_factors);  // factor rows per 1 KB
+// cu2b_dsgd_partition with the placement rule of a given row size
+cu2b_status cu2b_dsgd_partition_rows(const cu2b_rating *train, int64_t n, int rows, int cols, int world, int rows_per_block,
+                                     int *user_block, int *user_local, int *users_per_block, int *item_new,
+                                     int *item_block_ptr, int64_t *block_nnz);
+
 // Threshold below which the chunked file readers stay single-threaded (host_io.cpp).
 size_t cu2b_io_parallel_min_bytes();
 

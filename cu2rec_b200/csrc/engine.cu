@@ -133,7 +133,8 @@ struct DevMatrix {
 // thread per rating: user = last row whose indptr <= j
 __global__ void __launch_bounds__(256)
 expand_coo_kernel(const int *__restrict__ indptr, int rows, const int *__restrict__ indices,
-                  const float *__restrict__ data, long long nnz, cu2b_rating *__restrict__ coo) {
+                  const float *__restrict__ data, long long nnz, cu2b_rating *__restrict__ coo,
+                  const int *__restrict__ item_pos) {
     for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < nnz;
          j += (long long)gridDim.x * blockDim.x) {
         int lo = 0, hi = rows;  // find the largest u in [0, rows) with indptr[u] <= j
@@ -144,6 +145,7 @@ expand_coo_kernel(const int *__restrict__ indptr, int rows, const int *__restric
         cu2b_rating r;
         r.user = lo;
         r.item = __ldg(indices + j);
+        if (item_pos) r.item = __ldg(item_pos + r.item);  // the session's internal row order (ItemPlacement)
         r.rating = __ldg(data + j);
         coo[j] = r;
     }
@@ -211,26 +213,27 @@ cu2b_status matrix_alloc(DevPool &pool, const cu2b_csr *m, DevMatrix *out, Matri
     return CU2B_OK;
 }
 
-cu2b_status matrix_copy(cudaStream_t cst, const MatrixUpload &up) {
+// part 0 = row pointers + item indices, part 1 = rating values, -1 = both
+cu2b_status matrix_copy(cudaStream_t cst, const MatrixUpload &up, int part = -1) {
     const cu2b_csr *m = up.m;
     const size_t nnz = (size_t)m->nonzeros;
     const cudaMemcpyKind kind = m->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    CUDA_TRY(cudaMemcpyAsync(up.out->indptr, m->indptr, ((size_t)m->rows + 1) * sizeof(int), kind, cst));
-    if (up.tmp_i) {
-        CUDA_TRY(cudaMemcpyAsync(up.tmp_i, m->indices, nnz * sizeof(int), cudaMemcpyHostToDevice, cst));
-        CUDA_TRY(cudaMemcpyAsync(up.tmp_d, m->data, nnz * sizeof(float), cudaMemcpyHostToDevice, cst));
+    if (part != 1) {
+        CUDA_TRY(cudaMemcpyAsync(up.out->indptr, m->indptr, ((size_t)m->rows + 1) * sizeof(int), kind, cst));
+        if (up.tmp_i) CUDA_TRY(cudaMemcpyAsync(up.tmp_i, m->indices, nnz * sizeof(int), cudaMemcpyHostToDevice, cst));
     }
+    if (part != 0 && up.tmp_d) CUDA_TRY(cudaMemcpyAsync(up.tmp_d, m->data, nnz * sizeof(float), cudaMemcpyHostToDevice, cst));
     return CU2B_OK;
 }
 
-cu2b_status matrix_expand(DevPool &pool, cudaStream_t st, MatrixUpload &up) {
+cu2b_status matrix_expand(DevPool &pool, cudaStream_t st, MatrixUpload &up, const int *item_pos = nullptr) {
     const cu2b_csr *m = up.m;
     const size_t nnz = (size_t)m->nonzeros;
     if (nnz == 0) return CU2B_OK;
     const int *indices = up.tmp_i ? up.tmp_i : m->indices;
     const float *data = up.tmp_d ? up.tmp_d : m->data;
     const int grid = (int)std::min<size_t>((nnz + 255) / 256, 148 * 16);
-    expand_coo_kernel<<<grid, 256, 0, st>>>(up.out->indptr, m->rows, indices, data, (long long)nnz, up.out->coo);
+    expand_coo_kernel<<<grid, 256, 0, st>>>(up.out->indptr, m->rows, indices, data, (long long)nnz, up.out->coo, item_pos);
     CUDA_TRY(cudaGetLastError());
     if (up.tmp_i) {
         if (!pool.async) CUDA_TRY(cudaStreamSynchronize(st));  // stream-ordered frees need no sync
@@ -495,19 +498,22 @@ cu2b_status build_block_schedule(const cu2b_rating *coo, int64_t n, int rows, in
     return CU2B_OK;
 }
 
-// w[i] = expected draws of item i per iteration under per-user sampling (one uniform draw per
-// user per iteration), from every `stride`-th user. Host CSR only.
-std::vector<double> item_draw_weights(const cu2b_csr *m, int stride) {
-    std::vector<double> w((size_t)m->cols, 0.0);
+// Host version of item_draw_weight_kernel: w[i] = sum over every `user_stride`-th user u that rated i of
+// floor(2^32 / deg(u)) -- the expected draws of item i per iteration under per-user sampling (one uniform draw
+// per user per iteration, sgd.cu:27-37) in units of 2^-32. Exact integers: the device kernel, whatever its
+// summation order, produces the same numbers.
+std::vector<unsigned long long> item_draw_weights_host(const cu2b_csr *m, int user_stride) {
+    std::vector<unsigned long long> w((size_t)m->cols, 0ULL);
+    if (m->on_device) return w;
 #pragma omp parallel
     {
-        std::vector<double> mine((size_t)m->cols, 0.0);
+        std::vector<unsigned long long> mine((size_t)m->cols, 0ULL);
 #pragma omp for schedule(static) nowait
-        for (int u = 0; u < m->rows; u += stride) {
+        for (int u = 0; u < m->rows; u += user_stride) {
             const int lo = m->indptr[u], hi = m->indptr[u + 1];
             if (hi > lo) {
-                const double pu = 1.0 / (hi - lo);
-                for (int j = lo; j < hi; ++j) mine[m->indices[j]] += pu;
+                const unsigned long long share = 0x100000000ULL / (unsigned long long)(hi - lo);
+                for (int j = lo; j < hi; ++j) mine[m->indices[j]] += share;
             }
         }
 #pragma omp critical
@@ -516,48 +522,47 @@ std::vector<double> item_draw_weights(const cu2b_csr *m, int stride) {
     return w;
 }
 
-// Share of the draws of its item block that the most frequently drawn item receives under
-// per-user sampling (one uniform draw per user per iteration). Host CSR only; 0 if unknown.
-double hot_item_share(const cu2b_csr *m, const int *item_block_ptr, int n_blocks) {
-    if (!m || m->on_device || m->nonzeros <= 0) return 0.0;
-    // An estimate is enough (it feeds a bound with a 2x safety margin): every `stride`-th user,
-    // at most ~64 K users, so that session creation does not pay a pass over all ratings.
-    const std::vector<double> w = item_draw_weights(m, std::max(1, m->rows / 65536));
+// Share of the draws of its item block that the most frequently drawn item receives.
+double hot_item_share(const std::vector<unsigned long long> &w, const int *item_block_ptr, int n_blocks) {
     double hot = 0.0;
+    const int cols = (int)w.size();
     for (int b = 0; b < n_blocks; ++b) {
-        const int i0 = item_block_ptr ? item_block_ptr[b] : 0, i1 = item_block_ptr ? item_block_ptr[b + 1] : m->cols;
+        const int i0 = item_block_ptr ? item_block_ptr[b] : 0, i1 = item_block_ptr ? item_block_ptr[b + 1] : cols;
         double tot = 0.0, mx = 0.0;
-        for (int i = i0; i < i1; ++i) { tot += w[i]; mx = std::max(mx, w[i]); }
+        for (int i = i0; i < i1; ++i) { tot += (double)w[i]; mx = std::max(mx, (double)w[i]); }
         if (tot > 0) hot = std::max(hot, mx / tot);
     }
     return hot;
 }
 
-// Item-step thinning (experimental, CU2B_DSGD_THIN): keep[i] = fraction of item i's draws whose
-// item-side step is applied so that lr x (item's share of its block's draws) x (user groups in
-// flight) x keep stays <= budget for every item -- the per-item form of inflight_cap below.
-std::vector<float> item_keep_fractions(const cu2b_csr *m, const int *item_block_ptr, int n_blocks, float lr,
-                                       int groups_in_flight, double budget) {
-    std::vector<float> keep((size_t)m->cols, 1.0f);
-    if (m->on_device || m->nonzeros <= 0 || lr <= 0 || budget <= 0) return keep;
-    const std::vector<double> w = item_draw_weights(m, 1);
+// The asynchronous-SGD stability load of an item: lr x (its share of the draws of its item block) x (user
+// groups in flight) = lr x (expected number of this item's steps that a concurrent reader does not see yet).
+// Measured on B200 (profiles/r2_dsgd_stability_map.md): runs with a load of 0.5 on the hottest item bias
+// diverge or not depending on occupancy and chance; 0.25 and below never diverged. kStableLoad is that bound
+// with its 2x margin; it is applied either by capping the groups in flight (single GPU: exact updates) or,
+// on DSGD ranks, by applying only a fraction keep[i] = kStableLoad / load of the item's bias steps.
+constexpr double kStableLoad = 0.25;
+
+// keep[i] = fraction of item i's draws whose item-side step is applied so that load x keep <= budget.
+std::vector<float> item_keep_fractions(const std::vector<unsigned long long> &w, const int *item_block_ptr, int n_blocks,
+                                       float lr, int groups_in_flight, double budget) {
+    const int cols = (int)w.size();
+    std::vector<float> keep((size_t)cols, 1.0f);
+    if (lr <= 0 || budget <= 0) return keep;
     for (int b = 0; b < n_blocks; ++b) {
-        const int i0 = item_block_ptr ? item_block_ptr[b] : 0, i1 = item_block_ptr ? item_block_ptr[b + 1] : m->cols;
+        const int i0 = item_block_ptr ? item_block_ptr[b] : 0, i1 = item_block_ptr ? item_block_ptr[b + 1] : cols;
         double tot = 0.0;
-        for (int i = i0; i < i1; ++i) tot += w[i];
+        for (int i = i0; i < i1; ++i) tot += (double)w[i];
         if (tot <= 0) continue;
         for (int i = i0; i < i1; ++i) {
-            const double load = (double)lr * (w[i] / tot) * groups_in_flight;
+            const double load = (double)lr * ((double)w[i] / tot) * groups_in_flight;
             if (load > budget) keep[i] = (float)(budget / load);
         }
     }
     return keep;
 }
 
-// Asynchronous SGD is only stable while (updates of one parameter in flight) x lr stays well
-// below pi/2 (delayed-gradient bound); measured on B200: a DSGD sub-epoch with ~150 updates of
-// one item bias in flight at lr 0.01 diverges (profiles/r1_dsgd_round_sweep.jsonl). Bound the
-// number of concurrently processed ratings so that the hottest item sees <= budget / lr of them.
+// Bound on the concurrently processed ratings so that the hottest item's load stays <= budget.
 int inflight_cap(double hot_share, float lr, double budget_default) {
     double budget = budget_default;
     if (const char *e = getenv("CU2B_INFLIGHT_LR")) budget = atof(e);
@@ -638,6 +643,17 @@ struct cu2b_session {
     // ib_dense: [cols] staging buffer for the dense host-side array (== ib when ibs == 1).
     int ibs = 1;
     float *ib_dense = nullptr;
+    // ItemPlacement (Hogwild sessions): the item rows are stored in an internal order chosen for L2 slice balance
+    // (cu2b_paired_slots over the items' popularity); item_pos[external id] = internal row. The rating
+    // triplets carry internal ids; uploads / downloads of Q and item_bias translate. nullptr = identity.
+    int *item_pos = nullptr;
+    float *Q_stage = nullptr;  // [cols x k] dense staging for the permuting upload / download of Q
+    bool want_placement = false;
+    // expected draws per iteration of every item (external ids), units of 2^-32 (item_draw_weight_kernel),
+    // from every item_w_stride-th user; refreshed by every upload (create and reload)
+    std::vector<unsigned long long> item_w;
+    int item_w_stride = 1;
+    unsigned long long *item_w_dev = nullptr;
     int *active = nullptr;
     int n_active = 0;
     int *user_ids = nullptr;  // DSGD: original user id of each local user (sampler key), else null
@@ -680,6 +696,7 @@ struct cu2b_session {
     bool fused_sampler = false;
     UserRoundKernel rounds_kernel = nullptr;
     int rounds_grid = 0;
+    int sgd_grid_occ = 0, rounds_grid_occ = 0, tiles_grid_occ = 0;  // occupancy-limited grids before the stability cap
     // experiment switches (environment): CU2B_TUNE_GATE=0 drops the per-user ordering gate,
     // CU2B_TUNE_CHUNK overrides the chunk size
     bool no_gate = false;
@@ -705,13 +722,45 @@ struct cu2b_session {
 namespace {
 
 // ItemBiasLayout helpers (see cu2b_session::ibs)
+// pos (optional) = ItemPlacement: external item id -> internal row
 __global__ void __launch_bounds__(256)
-bias_scatter_kernel(const float *__restrict__ dense, float *__restrict__ padded, int n, int stride) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) padded[(size_t)i * stride] = dense[i];
+bias_scatter_kernel(const float *__restrict__ dense, float *__restrict__ padded, int n, int stride, const int *__restrict__ pos) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        padded[(size_t)(pos ? pos[i] : i) * stride] = dense[i];
 }
 __global__ void __launch_bounds__(256)
-bias_gather_kernel(const float *__restrict__ padded, float *__restrict__ dense, int n, int stride) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dense[i] = __ldcg(padded + (size_t)i * stride);
+bias_gather_kernel(const float *__restrict__ padded, float *__restrict__ dense, int n, int stride, const int *__restrict__ pos) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        dense[i] = __ldcg(padded + (size_t)(pos ? pos[i] : i) * stride);
+}
+// Item rows between the caller's dense [cols x k] order (staging buffer) and the device layout [cols x kp] in the
+// internal row order. to_device: Q[pos[i]] = stage[i] (padding zeroed); else stage[i] = Q[pos[i]].
+__global__ void __launch_bounds__(256)
+permute_rows_kernel(float *__restrict__ Q, float *__restrict__ stage, const int *__restrict__ pos, int cols, int k, int kp,
+                    int to_device) {
+    const long long total = (long long)cols * kp;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t / kp), f = (int)(t - (long long)i * kp);
+        const size_t dev = (size_t)pos[i] * kp + f;
+        if (to_device) Q[dev] = f < k ? stage[(size_t)i * k + f] : 0.f;
+        else if (f < k) stage[(size_t)i * k + f] = __ldcg(Q + dev);
+    }
+}
+// w[i] += floor(2^32 / deg(u)) for every rating (u, i) of every `user_stride`-th user: the expected number of draws
+// of item i per iteration under per-user sampling (one uniform draw per user per iteration, sgd.cu:27-37) in units
+// of 2^-32. Integer atomics => exact, order independent, identical to the host version (item_draw_weights_host).
+__global__ void __launch_bounds__(256)
+item_draw_weight_kernel(const int *__restrict__ indptr, const int *__restrict__ indices, int rows, int user_stride,
+                        unsigned long long *__restrict__ w) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long u = warp * user_stride; u < rows; u += warps * user_stride) {
+        const int lo = __ldg(indptr + u), hi = __ldg(indptr + u + 1);
+        if (hi <= lo) continue;
+        const unsigned long long share = 0x100000000ULL / (unsigned long long)(hi - lo);
+        for (int j = lo + lane; j < hi; j += 32) atomicAdd(w + __ldg(indices + j), share);
+    }
 }
 
 int item_bias_stride() {
@@ -724,7 +773,7 @@ cu2b_status alloc_item_bias(cu2b_session *s) {
     s->ibs = item_bias_stride();
     const size_t n = (size_t)std::max(1, s->cols);
     CU2B_TRY(s->pool.alloc(&s->ib, n * s->ibs));
-    if (s->ibs == 1) {
+    if (s->ibs == 1 && !s->want_placement) {
         s->ib_dense = s->ib;
     } else {
         CU2B_TRY(s->pool.alloc(&s->ib_dense, n));
@@ -735,16 +784,16 @@ cu2b_status alloc_item_bias(cu2b_session *s) {
 
 // ib_dense (host order, dense) -> ib (one bias per line); call on a stream ordered after the H2D copy
 cu2b_status scatter_item_bias(cu2b_session *s, cudaStream_t st) {
-    if (s->ibs == 1 || s->cols == 0) return CU2B_OK;
-    bias_scatter_kernel<<<std::max(1, std::min((s->cols + 255) / 256, 592)), 256, 0, st>>>(s->ib_dense, s->ib, s->cols, s->ibs);
+    if ((s->ibs == 1 && !s->item_pos) || s->cols == 0) return CU2B_OK;
+    bias_scatter_kernel<<<std::max(1, std::min((s->cols + 255) / 256, 592)), 256, 0, st>>>(s->ib_dense, s->ib, s->cols, s->ibs, s->item_pos);
     CUDA_TRY(cudaGetLastError());
     return CU2B_OK;
 }
 
 cu2b_status download_item_bias(cu2b_session *s, float *host) {
     if (s->cols == 0) return CU2B_OK;
-    if (s->ibs != 1) {
-        bias_gather_kernel<<<std::max(1, std::min((s->cols + 255) / 256, 592)), 256, 0, s->stream>>>(s->ib, s->ib_dense, s->cols, s->ibs);
+    if (s->ibs != 1 || s->item_pos) {
+        bias_gather_kernel<<<std::max(1, std::min((s->cols + 255) / 256, 592)), 256, 0, s->stream>>>(s->ib, s->ib_dense, s->cols, s->ibs, s->item_pos);
         CUDA_TRY(cudaGetLastError());
     }
     CUDA_TRY(cudaMemcpyAsync(host, s->ib_dense, (size_t)s->cols * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
@@ -1020,6 +1069,25 @@ cu2b_status enqueue_sgd_iterations(cu2b_session *s, int iter_abs, int n_seg) {
 
 }  // namespace
 
+// Launch grids from the occupancy limits and the asynchronous-SGD stability bound (kStableLoad) for the item
+// popularity of the matrix that was uploaded last (s->item_w): called at creation and after every reload.
+static void apply_stability_cap(cu2b_session *s) {
+    s->hot_share = hot_item_share(s->item_w, nullptr, 1);
+    const int cap = inflight_cap(s->hot_share, s->cfg.learning_rate, kStableLoad);
+    {   // ratings in flight per CTA: 8 consumer warps x (32/L) groups x unroll (2 for L < 32)
+        const int per_cta = kConsumerWarps * (32 / s->L) * (s->L < 32 ? 2 : 1);
+        s->sgd_grid_max = std::max(1, std::min(s->sgd_grid_occ, cap / per_cta));
+    }
+    if (s->rounds_kernel) {
+        const int per_cta = kRoundWarps * (32 / s->L);
+        s->rounds_grid = std::max(1, std::min(std::min(s->rounds_grid_occ, cap / per_cta), (s->n_active + per_cta - 1) / per_cta));
+    }
+    if (s->tiles_kernel) {
+        const int per_cta = kConsumerWarps * (32 / s->L);
+        s->tiles_grid = std::max(1, std::min(s->tiles_grid_occ, cap / per_cta));
+    }
+}
+
 // Device-resident schedule state as train() starts it (training.cu:102-103) + host counters.
 static cu2b_status session_reset_state(cu2b_session *s) {
     DevState st;
@@ -1048,14 +1116,16 @@ static cu2b_status session_upload(cu2b_session *s, const cu2b_csr *train, const 
                                   const float *Q, const float *user_bias, const float *item_bias, bool reload) {
     struct CopyLane {
         cudaStream_t st = nullptr;
-        cudaEvent_t ev = nullptr;
+        cudaEvent_t ev = nullptr, ev_vals = nullptr;
         ~CopyLane() {
             if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
             if (ev) cudaEventDestroy(ev);
+            if (ev_vals) cudaEventDestroy(ev_vals);
         }
     } lane;
     CUDA_TRY(cudaStreamCreateWithFlags(&lane.st, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&lane.ev, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&lane.ev_vals, cudaEventDisableTiming));
     std::vector<int> indptr_host;
     CU2B_TRY(host_indptr(train, s->stream, &indptr_host));
     // users with at least one training rating (sgd.cu:35 skips the others)
@@ -1077,22 +1147,67 @@ static cu2b_status session_upload(cu2b_session *s, const cu2b_csr *train, const 
         CU2B_TRY(s->pool.alloc(&s->Q, (size_t)s->cols * s->kp));
         CU2B_TRY(s->pool.alloc(&s->ub, (size_t)s->rows));
         CU2B_TRY(alloc_item_bias(s));
+        CU2B_TRY(s->pool.alloc(&s->item_w_dev, (size_t)std::max(1, s->cols)));
+        if (s->want_placement) {
+            CU2B_TRY(s->pool.alloc(&s->item_pos, (size_t)std::max(1, s->cols)));
+            CU2B_TRY(s->pool.alloc(&s->Q_stage, (size_t)std::max(1, s->cols) * s->k));
+        }
     }
     CU2B_TRY(stream_after(lane.st, s->stream, lane.ev));
-    // 2. copies back to back on the copy stream; each expansion waits only for its own matrix
+    // 2. copies back to back on the copy stream; the compute stream waits only for what it is about to touch
     if (!active.empty())  // pageable source: staged synchronously, so it goes first
         CUDA_TRY(cudaMemcpyAsync(s->active, active.data(), active.size() * sizeof(int), cudaMemcpyHostToDevice, lane.st));
-    CU2B_TRY(matrix_copy(lane.st, up_train));
+    CU2B_TRY(matrix_copy(lane.st, up_train, 0));  // row pointers + item ids
     CU2B_TRY(stream_after(s->stream, lane.st, lane.ev));
-    CU2B_TRY(matrix_expand(s->pool, s->stream, up_train));
+    // item draw weights from the ids alone, while the rating values and the model are still in flight
+    {
+        const int *ids = up_train.tmp_i ? up_train.tmp_i : train->indices;
+        // single-GPU sessions only need the popularity order and the hottest share: visit <= ~16 M ratings;
+        // DSGD strips derive per-item step fractions from the weights: every user (== cu2b_dsgd_item_keep)
+        s->item_w_stride = s->dsgd_child ? 1 : (int)std::max<long long>(1, (long long)train->nonzeros >> 24);
+        CUDA_TRY(cudaMemsetAsync(s->item_w_dev, 0, (size_t)std::max(1, s->cols) * sizeof(unsigned long long), s->stream));
+        if (train->nonzeros > 0) {
+            const int warps = (s->rows + s->item_w_stride - 1) / s->item_w_stride;
+            item_draw_weight_kernel<<<std::max(1, std::min((warps + 7) / 8, s->sm_count * 8)), 256, 0, s->stream>>>(
+                s->train.indptr, ids, s->rows, s->item_w_stride, s->item_w_dev);
+            CUDA_TRY(cudaGetLastError());
+        }
+    }
+    CU2B_TRY(matrix_copy(lane.st, up_train, 1));  // rating values
+    CUDA_TRY(cudaEventRecord(lane.ev_vals, lane.st));
     CU2B_TRY(upload_dense(lane.st, s->P, P, s->rows, s->k, s->kp));
-    CU2B_TRY(upload_dense(lane.st, s->Q, Q, s->cols, s->k, s->kp));
+    if (s->item_pos) CUDA_TRY(cudaMemcpyAsync(s->Q_stage, Q, (size_t)s->cols * s->k * sizeof(float), cudaMemcpyHostToDevice, lane.st));
+    else CU2B_TRY(upload_dense(lane.st, s->Q, Q, s->cols, s->k, s->kp));
     CUDA_TRY(cudaMemcpyAsync(s->ub, user_bias, (size_t)s->rows * sizeof(float), cudaMemcpyHostToDevice, lane.st));
     CUDA_TRY(cudaMemcpyAsync(s->ib_dense, item_bias, (size_t)s->cols * sizeof(float), cudaMemcpyHostToDevice, lane.st));
     CU2B_TRY(matrix_copy(lane.st, up_test));
-    CU2B_TRY(stream_after(s->stream, lane.st, lane.ev));
+    // 3. weights back on the host (the copies above keep streaming meanwhile): hottest share, and at creation the
+    //    internal row order
+    s->item_w.assign((size_t)s->cols, 0ULL);
+    if (s->cols > 0)
+        CUDA_TRY(cudaMemcpyAsync(s->item_w.data(), s->item_w_dev, (size_t)s->cols * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (s->item_pos && !reload) {
+        std::vector<int> order((size_t)s->cols), slot((size_t)s->cols), pos((size_t)s->cols);
+        for (int i = 0; i < s->cols; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return s->item_w[a] > s->item_w[b]; });
+        cu2b_paired_slots(s->cols, 0, cu2b_rows_per_l2_block(s->k), slot.data());
+        for (int r = 0; r < s->cols; ++r) pos[order[r]] = slot[r];
+        CUDA_TRY(cudaMemcpyAsync(s->item_pos, pos.data(), pos.size() * sizeof(int), cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));  // pos is a local
+    }
+    // 4. expansions (ratings carry internal item ids from here on) and the item side in its internal order
+    CUDA_TRY(cudaStreamWaitEvent(s->stream, lane.ev_vals, 0));  // the training matrix is complete
+    CU2B_TRY(matrix_expand(s->pool, s->stream, up_train, s->item_pos));
+    CU2B_TRY(stream_after(s->stream, lane.st, lane.ev));  // everything copied
+    if (s->item_pos && s->cols > 0) {
+        const long long total = (long long)s->cols * s->kp;
+        permute_rows_kernel<<<(int)std::max<long long>(1, std::min<long long>((total + 255) / 256, s->sm_count * 8LL)), 256, 0, s->stream>>>(
+            s->Q, s->Q_stage, s->item_pos, s->cols, s->k, s->kp, 1);
+        CUDA_TRY(cudaGetLastError());
+    }
     CU2B_TRY(scatter_item_bias(s, s->stream));
-    CU2B_TRY(matrix_expand(s->pool, s->stream, up_test));
+    CU2B_TRY(matrix_expand(s->pool, s->stream, up_test, s->item_pos));
     return CU2B_OK;
 }
 
@@ -1134,6 +1249,13 @@ static cu2b_status session_create_impl(cu2b_session **out, int device, const cu2
     CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     if (alloc_stream && !getenv("CU2B_NO_MEMPOOL")) s->pool.use_async(s->stream);
 
+    s->dsgd_child = !alloc_stream;
+    // ItemPlacement: Hogwild sessions store the item rows in an L2-slice-balanced internal order. Not for the
+    // deterministic mode (its block schedule, and the sequential replay it is compared with, cut the items in
+    // contiguous ranges of the caller's ids) and not for DSGD strips (cu2b_dsgd_partition already places the rows
+    // of every item block). CU2B_PLACEMENT=0 switches it off for A/B runs.
+    s->want_placement = alloc_stream && cfg->mode == CU2B_MODE_HOGWILD && s->cols > 1;
+    if (const char *e = getenv("CU2B_PLACEMENT")) s->want_placement = s->want_placement && atoi(e) != 0;
     Trace tr("session_create");
     tr.mark("setup");
     CU2B_TRY(session_upload(s, train, test, P, Q, user_bias, item_bias, false));
@@ -1143,16 +1265,10 @@ static cu2b_status session_create_impl(cu2b_session **out, int device, const cu2
     s->loss_kernel = pick_loss(s->kp);
     int occ = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s->sgd_kernel, kThreads, 0));
-    s->sgd_grid_max = std::max(1, occ) * s->sm_count;
+    s->sgd_grid_occ = std::max(1, occ) * s->sm_count;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s->loss_kernel, kThreads, 0));
     s->loss_grid_max = std::max(1, occ) * s->sm_count;
-    {
-        // ratings in flight per CTA: 8 consumer warps x (32/L) groups x unroll (2 for L < 32)
-        const int per_cta = kConsumerWarps * (32 / s->L) * (s->L < 32 ? 2 : 1);
-        s->hot_share = hot_item_share(train, nullptr, 1);
-        const int cap = inflight_cap(s->hot_share, cfg->learning_rate, 0.5);
-        s->sgd_grid_max = std::max(1, std::min(s->sgd_grid_max, cap / per_cta));
-    }
+    apply_stability_cap(s);  // sgd_grid_max (the iteration-synchronous kernel's grid sizes the update stream's chunks)
 
     tr.mark("occupancy + hot-item share");
     if (const char *e = getenv("CU2B_TUNE_GATE")) s->no_gate = e[0] == '0';
@@ -1164,7 +1280,6 @@ static cu2b_status session_create_impl(cu2b_session **out, int device, const cu2
     const long long cap_ratings = 48LL << 20;  // <= 576 MB of triplets per batch
     s->max_batch_segs = (int)std::max<long long>(1, std::min<long long>(cap_ratings / std::max<long long>(1, s->seg_pitch), 4096));
     s->round_iters = 1;
-    s->dsgd_child = !alloc_stream;
     if (alloc_stream && cfg->mode == CU2B_MODE_HOGWILD && cfg->round_iters > 1) {
         const char *pipe = getenv("CU2B_TILE_PIPE");
         s->fused_sampler = !(pipe && strcmp(pipe, "tma") == 0);
@@ -1187,10 +1302,7 @@ static cu2b_status session_create_impl(cu2b_session **out, int device, const cu2
         int occ_t = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, s->rounds_kernel, kRoundWarps * 32, 0));
         if (const char *e = getenv("CU2B_TUNE_OCC")) occ_t = std::max(1, std::min(occ_t, atoi(e)));
-        const int per_cta = kRoundWarps * (32 / s->L);
-        const int cap = inflight_cap(s->hot_share, cfg->learning_rate, 0.5);
-        s->rounds_grid = std::max(1, std::min(std::min(std::max(1, occ_t) * s->sm_count, cap / per_cta),
-                                              (s->n_active + per_cta - 1) / per_cta));
+        s->rounds_grid_occ = std::max(1, occ_t) * s->sm_count;
     } else if (s->round_iters > 1) {
         const int TU = kConsumerWarps * (32 / s->L);
         s->draw_pitch = std::min((s->round_iters + 3) & ~3, kTileDrawsMax / TU);
@@ -1205,10 +1317,9 @@ static cu2b_status session_create_impl(cu2b_session **out, int device, const cu2
         s->tiles_kernel = pick_user_tiles(s->L, s->V);
         int occ_t = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, s->tiles_kernel, kThreads, 0));
-        const int per_cta = kConsumerWarps * (32 / s->L);
-        const int cap = inflight_cap(s->hot_share, cfg->learning_rate, 0.5);
-        s->tiles_grid = std::max(1, std::min(std::max(1, occ_t) * s->sm_count, cap / per_cta));
+        s->tiles_grid_occ = std::max(1, occ_t) * s->sm_count;
     }
+    apply_stability_cap(s);
     if (alloc_stream && s->round_iters == 1) {
         CU2B_TRY(s->pool.alloc(&s->stream_buf, (size_t)s->max_batch_segs * s->seg_pitch + kChunkMax + 4));
         CU2B_TRY(s->pool.alloc(&s->gate, (size_t)s->chunks_per_seg));
@@ -1303,6 +1414,7 @@ static cu2b_status session_reload_impl(cu2b_session *s, const cu2b_csr *train, c
     s->timing.collect(ms);  // drop spans of the previous life
     Trace tr("session_reload");
     CU2B_TRY(session_upload(s, train, test, P, Q, user_bias, item_bias, true));
+    apply_stability_cap(s);  // the reloaded matrix may concentrate its draws differently
     s->mu = global_bias;
     CU2B_TRY(session_reset_state(s));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -1354,7 +1466,15 @@ extern "C" cu2b_status cu2b_session_download(cu2b_session *s, float *P, float *Q
     CUDA_TRY(cudaSetDevice(s->device));
     Trace tr("session_download");
     if (P) CU2B_TRY(download_dense(s->stream, P, s->P, s->rows, s->k, s->kp));
-    if (Q) CU2B_TRY(download_dense(s->stream, Q, s->Q, s->cols, s->k, s->kp));
+    if (Q && s->item_pos && s->cols > 0) {
+        const long long total = (long long)s->cols * s->kp;
+        permute_rows_kernel<<<(int)std::max<long long>(1, std::min<long long>((total + 255) / 256, s->sm_count * 8LL)), 256, 0, s->stream>>>(
+            s->Q, s->Q_stage, s->item_pos, s->cols, s->k, s->kp, 0);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(Q, s->Q_stage, (size_t)s->cols * s->k * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    } else if (Q) {
+        CU2B_TRY(download_dense(s->stream, Q, s->Q, s->cols, s->k, s->kp));
+    }
     if (user_bias) CUDA_TRY(cudaMemcpyAsync(user_bias, s->ub, (size_t)s->rows * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
     if (item_bias) CU2B_TRY(download_item_bias(s, item_bias));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -1388,6 +1508,12 @@ extern "C" void cu2b_session_destroy(cu2b_session *s) {
     tr.mark("free");
 }
 
+namespace {
+cu2b_status train_multi_gpu(const cu2b_csr *train, const cu2b_csr *test, cu2b_config *cfg, float *P, float *Q,
+                            float *user_bias, float *item_bias, float global_bias, float *losses, cu2b_metrics *log,
+                            int log_cap, int *n_log, cu2b_stats *stats);
+}
+
 extern "C" cu2b_status cu2b_train(const cu2b_csr *train, const cu2b_csr *test, cu2b_config *cfg,
                                   float *P, float *Q, float *user_bias, float *item_bias,
                                   float global_bias, int init_item_side, float *losses,
@@ -1404,6 +1530,8 @@ extern "C" cu2b_status cu2b_train(const cu2b_csr *train, const cu2b_csr *test, c
     }
     cu2b_init_normal(P, (int64_t)train->rows * k, k, 0.f, 1.f, 42);
     cu2b_init_normal(user_bias, train->rows, k, 0.f, 1.f, 42);
+    if (cfg->n_gpus > 1)  // DSGD over n_gpus devices of this box (dsgd.inc)
+        return train_multi_gpu(train, test, cfg, P, Q, user_bias, item_bias, global_bias, losses, log, log_cap, n_log, stats);
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     cu2b_session *s = nullptr;

@@ -374,3 +374,37 @@ def test_dsgd_thinning_bit_exact_against_oracle_replay_on_disjoint_items(what):
         d.close()
     assert np.array_equal(Qg.view(np.uint32), Qo.reshape(n, k).view(np.uint32))
     assert np.array_equal(ibg.view(np.uint32), ibo.view(np.uint32))
+
+
+# ---------------------------------------------------------------------------------------------
+# DSGD behind the reference's own surface: cu2b_train() / train() with config token 17 (n_gpus) > 1
+# (mf.cu:61 -> training.h:12-15). CU2B_LOGICAL_RANKS=1 lets the ranks share the one test device.
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4])
+def test_train_entry_point_runs_dsgd_when_n_gpus_is_set(world):
+    tr, te, U, I = _problem(U=3000, I=400, n=120000)
+    k, iters, ce = 16, 120, 40
+    mtr, mte = cu.createSparseMatrix(tr, U, I), cu.createSparseMatrix(te, U, I)
+    mu = np.float32(tr["rating"].astype(np.float64).mean())
+    one = cu.train(mtr, mte, cu.Config(total_iterations=iters, n_factors=k, check_error=ce), mu)
+    cfg = cu.Config(total_iterations=iters, n_factors=k, check_error=ce, n_gpus=world)
+    out = _with_env("CU2B_LOGICAL_RANKS", "1", lambda: cu.train(mtr, mte, cfg, mu))
+    assert [r["iteration"] for r in out["log"]] == [1, 40, 80, 120]
+    assert out["stats"]["updates"] == iters * U and cfg.cur_iterations == iters
+    for a, b in zip(out["log"], one["log"]):
+        for key in ("train_rmse", "test_rmse"):
+            assert abs(a[key] - b[key]) / b[key] < 0.01, (key, a, b)
+    assert abs(out["log"][-1]["test_rmse"] - one["log"][-1]["test_rmse"]) / one["log"][-1]["test_rmse"] < 0.005
+    # the returned model is in the caller's ids: the oracle's loss on it is the logged loss
+    _, rmse, _, _ = O.loss(mte.indptr, mte.indices, mte.data, out["P"], out["Q"], out["user_bias"], out["item_bias"], mu, k)
+    assert abs(rmse - out["log"][-1]["test_rmse"]) / rmse < 1e-4
+    assert np.array_equal(np.isnan(out["losses"]), np.isnan(one["losses"]))
+
+
+def test_train_entry_point_rejects_more_gpus_than_the_box_has():
+    tr, te, U, I = _problem(U=200, I=50, n=3000)
+    mtr, mte = cu.createSparseMatrix(tr, U, I), cu.createSparseMatrix(te, U, I)
+    cfg = cu.Config(total_iterations=4, n_factors=8, check_error=2, n_gpus=64)
+    with pytest.raises(cu._lib.Cu2bError):
+        cu.train(mtr, mte, cfg, 3.5)

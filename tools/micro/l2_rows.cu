@@ -46,10 +46,14 @@ __device__ __forceinline__ void red1(float *p, float v) { asm volatile("red.glob
 enum Mode { GATHER = 0, RED = 1, GATHER_RED = 2, SGD_LIKE = 3, BIAS_ONLY = 4 };
 
 // idx: [n] row ids; warp w processes idx[w * per_warp ... ), UN accesses in flight.
-template <int MODE, int UN>
+// PLANAR: line j of every row lives in plane j ([4][n_rows][128 bytes]) instead of row-major.
+template <int MODE, int UN, int PLANAR = 0>
 __global__ void __launch_bounds__(256)
-rows_kernel(float4 *rows, float *bias, int bias_stride, const int *__restrict__ idx, long long n, float *sink) {
+rows_kernel(float4 *rows, float *bias, int bias_stride, const int *__restrict__ idx, long long n, float *sink, int n_rows) {
     const int lane = threadIdx.x & 31;
+    auto at = [&](int r) -> float4 * {
+        return PLANAR ? rows + ((size_t)(lane >> 3) * n_rows + r) * 8 + (lane & 7) : rows + (size_t)r * 32 + lane;
+    };
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
     float acc = 0.f;
@@ -62,7 +66,7 @@ rows_kernel(float4 *rows, float *bias, int bias_stride, const int *__restrict__ 
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
             if (MODE == SGD_LIKE || MODE == BIAS_ONLY) b[u] = ld_cg1(bias + (size_t)r[u] * bias_stride);
-            if (MODE == GATHER || MODE == GATHER_RED || MODE == SGD_LIKE) v[u] = ld_cg4(rows + (size_t)r[u] * 32 + lane);
+            if (MODE == GATHER || MODE == GATHER_RED || MODE == SGD_LIKE) v[u] = ld_cg4(at(r[u]));
         }
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
@@ -77,7 +81,7 @@ rows_kernel(float4 *rows, float *bias, int bias_stride, const int *__restrict__ 
             acc += s;
             const float e = s * 1e-30f;  // data dependent, numerically nil
             if (MODE == RED || MODE == GATHER_RED || MODE == SGD_LIKE)
-                red4(rows + (size_t)r[u] * 32 + lane, make_float4(e, e, e, e));
+                red4(at(r[u]), make_float4(e, e, e, e));
             if ((MODE == SGD_LIKE || MODE == BIAS_ONLY) && lane == 0) red1(bias + (size_t)r[u] * bias_stride, e);
         }
     }
@@ -91,17 +95,33 @@ static uint64_t mix64(uint64_t x) {
     return x ^ (x >> 31);
 }
 
-// dist: 0 uniform, 1 Zipf-Mandelbrot (weight 1/(rank + N/300 + 1), the bench generator's law) with
-// scattered ids, 2 the same with id == popularity rank (popular items adjacent).
-static std::vector<int> make_indices(long long n, int N, int dist, uint64_t seed) {
+// dist: 0 uniform, 1 Zipf-Mandelbrot (weight 1/(rank + c), the bench generator's law) with
+// scattered ids, 2 the same with id == popularity rank (popular items adjacent), 3 "paired": rank r of the
+// popular half in row 2r, the other half fills the odd rows (one popular row per 1 KB), 4 "oct": rank r of the
+// popular eighth in row 8r, the rest fills the other seven (one popular row per 8 rows; for the planar layout).
+// law_c: Mandelbrot offset (17770 / 300 + 1 for the whole catalogue; a DSGD block of 1/G of the items keeps every
+// G-th rank, i.e. the law 1 / (G * rank + c) = (1/G) / (rank + c / G)).
+static std::vector<int> make_indices(long long n, int N, int dist, uint64_t seed, double law_c) {
     std::vector<int> out((size_t)n);
     std::vector<double> cdf(N);
     std::vector<int> perm(N);
     for (int i = 0; i < N; ++i) perm[i] = i;
     if (dist == 1)
         for (int i = N - 1; i > 0; --i) std::swap(perm[i], perm[(int)(mix64(seed + 77 + i) % (uint64_t)(i + 1))]);
+    if (dist == 3) {
+        const int h = (N + 1) / 2;
+        for (int r = 0; r < N; ++r) perm[r] = r < h ? 2 * r : 2 * (r - h) + 1;
+    }
+    if (dist == 4) {
+        const int h = (N + 7) / 8;
+        std::vector<char> used(N, 0);
+        for (int r = 0; r < h; ++r) { perm[r] = std::min(8 * r, N - 1); }
+        for (int r = 0; r < h; ++r) used[perm[r]] = 1;
+        int slot = 0;
+        for (int r = h; r < N; ++r) { while (used[slot]) ++slot; perm[r] = slot; used[slot] = 1; }
+    }
     if (dist != 0) {
-        const double c = N / 300.0 + 1.0;
+        const double c = law_c;
         double acc = 0;
         for (int i = 0; i < N; ++i) { acc += 1.0 / (i + c); cdf[i] = acc; }
         for (int i = 0; i < N; ++i) cdf[i] /= acc;
@@ -121,8 +141,9 @@ static std::vector<int> make_indices(long long n, int N, int dist, uint64_t seed
     return out;
 }
 
-typedef void (*Kern)(float4 *, float *, int, const int *, long long, float *);
-static Kern pick(int mode, int un) {
+typedef void (*Kern)(float4 *, float *, int, const int *, long long, float *, int);
+static Kern pick(int mode, int un, int planar) {
+    if (planar) return mode == GATHER_RED ? (Kern)rows_kernel<GATHER_RED, 1, 1> : (Kern)rows_kernel<SGD_LIKE, 1, 1>;
 #define ROW(M) (un == 1 ? (Kern)rows_kernel<M, 1> : un == 2 ? (Kern)rows_kernel<M, 2> : (Kern)rows_kernel<M, 4>)
     switch (mode) {
         case GATHER: return ROW(GATHER);
@@ -136,6 +157,7 @@ static Kern pick(int mode, int un) {
 
 int main(int argc, char **argv) {
     const bool quick = argc > 1 && !strcmp(argv[1], "quick");
+    const bool placement = argc > 1 && !strcmp(argv[1], "placement");
     const long long n = quick ? (1LL << 22) : (1LL << 24);
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, 0));
@@ -154,15 +176,15 @@ int main(int argc, char **argv) {
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
     const char *mode_name[] = {"gather", "red", "gather_red", "sgd_like", "bias_only"};
-    const char *dist_name[] = {"uniform", "zipf_scattered", "zipf_sorted_ids"};
-    auto run = [&](int mode, int dist, int N, int stride, int ctas_per_sm, int un) {
-        Kern k = pick(mode, un);
+    const char *dist_name[] = {"uniform", "zipf_scattered", "zipf_sorted_ids", "zipf_paired", "zipf_oct"};
+    auto run = [&](int mode, int dist, int N, int stride, int ctas_per_sm, int un, int planar = 0) {
+        Kern k = pick(mode, un, planar);
         const int grid = sms * ctas_per_sm;
-        for (int w = 0; w < 2; ++w) k<<<grid, 256>>>(rows, bias, stride, idx_dev, n, sink);
+        for (int w = 0; w < 2; ++w) k<<<grid, 256>>>(rows, bias, stride, idx_dev, n, sink, N);
         float best = 1e30f;
         for (int rep = 0; rep < 3; ++rep) {
             CK(cudaEventRecord(e0));
-            k<<<grid, 256>>>(rows, bias, stride, idx_dev, n, sink);
+            k<<<grid, 256>>>(rows, bias, stride, idx_dev, n, sink, N);
             CK(cudaEventRecord(e1));
             CK(cudaEventSynchronize(e1));
             float ms;
@@ -177,15 +199,30 @@ int main(int argc, char **argv) {
         if (mode == GATHER_RED) bytes = 1024;
         if (mode == SGD_LIKE) bytes = 1032;
         if (mode == BIAS_ONLY) bytes = 8;
-        printf("{\"mode\": \"%s\", \"dist\": \"%s\", \"rows\": %d, \"bias_stride_floats\": %d, \"ctas_per_sm\": %d, \"unroll\": %d, "
-               "\"ms\": %.4f, \"G_rows_per_s\": %.3f, \"l2_TB_per_s\": %.3f}\n",
-               mode_name[mode], dist_name[dist], N, stride, ctas_per_sm, un, best, rows_s / 1e9, rows_s * bytes / 1e12);
+        printf("{\"mode\": \"%s\", \"dist\": \"%s\", \"layout\": \"%s\", \"rows\": %d, \"bias_stride_floats\": %d, \"ctas_per_sm\": %d, "
+               "\"unroll\": %d, \"ms\": %.4f, \"G_rows_per_s\": %.3f, \"l2_TB_per_s\": %.3f}\n",
+               mode_name[mode], dist_name[dist], planar ? "planar" : "row_major", N, stride, ctas_per_sm, un, best, rows_s / 1e9,
+               rows_s * bytes / 1e12);
         fflush(stdout);
     };
     auto load = [&](int N, int dist) {
-        std::vector<int> h = make_indices(n, N, dist, 20240607);
+        std::vector<int> h = make_indices(n, N, dist, 20240607, N / 300.0 + 1.0);
         CK(cudaMemcpy(idx_dev, h.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
     };
+    if (placement) {
+        // Which internal row order balances the L2 slices? (bias padded to one per 256 bytes throughout)
+        for (int N : {17770, 8885, 4442, 2221}) {
+            for (int dist : {0, 1, 2, 3, 4}) {
+                load(N, dist);
+                for (int planar : {0, 1})
+                    for (int c : {4, 8}) {
+                        run(GATHER_RED, dist, N, 64, c, 1, planar);
+                        run(SGD_LIKE, dist, N, 64, c, 1, planar);
+                    }
+            }
+        }
+        return 0;
+    }
     // 1. peaks on the full catalogue: uniform vs Zipf, each traffic class alone and combined
     for (int dist = 0; dist < 3; ++dist) {
         load(17770, dist);
