@@ -253,7 +253,11 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, args.steps), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_dict(args, k),
+        # the arm's step is a bounded sample of the workload (the whole step would take hours on one core)
+        "config": dict(config_dict(args, k), iters_per_step=ref.iters, updates_per_step=ref.iters * ref.U,
+                       users_in_sample=ref.U, train_ratings_in_sample=int(len(ref.tr)),
+                       step="%d reference iterations on the first %d users (bounded sample; per-update cost does not depend "
+                            "on the sample size) incl. the reference's loss checks" % (ref.iters, ref.U)),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": ref.kind, "sample": ref.sample_desc(),
                          "host_cores_available": os.cpu_count(), "final_test_rmse": rmse},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -274,7 +278,7 @@ def config_dict(args, k):
             "lr": 0.01, "reg": 0.02, "check_error": args.iters_per_step,
             # experiment switches that change what runs (none set = the defaults DESIGN.md describes)
             **{"env": {n: os.environ[n] for n in ("CU2B_DSGD_THIN", "CU2B_DSGD_THIN_BIAS", "CU2B_DSGD_ROUND", "CU2B_INFLIGHT_LR", "CU2B_ROUND",
-                                                  "CU2B_TILE_PIPE") if n in os.environ}}}
+                                                  "CU2B_TILE_PIPE", "CU2B_PLACEMENT", "CU2B_IB_STRIDE", "CU2B_DSGD_FUSED", "CU2B_DSGD_GRID") if n in os.environ}}}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -288,6 +292,33 @@ def peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def l2_row_peak():
+    """Measured peak of the update kernels' binding resource: a warp reads a 512-byte row from L2 and adds a 512-byte
+    step to it with red.global.add.v4.f32, uniformly random rows (no popularity skew, no bias side traffic).
+    Live from tools/micro/l2_rows (a few seconds on this box) when the binary is there, else the committed
+    profile of the same tool. -> (G rows/s, L2 TB/s, source)"""
+    exe = os.path.join(ROOT, "tools", "micro", "l2_rows")
+    rows = []
+    src = None
+    if os.path.exists(exe):
+        try:
+            out = subprocess.run([exe, "peak"], capture_output=True, text=True, timeout=120).stdout
+            rows = [json.loads(l) for l in out.splitlines() if l.startswith("{")]
+            src = "measured in this run (tools/micro/l2_rows peak)"
+        except Exception as exc:  # pragma: no cover
+            log("[bench] l2_rows peak failed: %r" % (exc,))
+    if not rows:
+        prof = os.path.join(ROOT, "profiles", "r2_l2_rows_micro.jsonl")
+        if os.path.exists(prof):
+            rows = [json.loads(l) for l in open(prof) if l.startswith("{")]
+            src = "profiles/r2_l2_rows_micro.jsonl (measured on this pool's B200, round 2)"
+    best = [r for r in rows if r["mode"] == "gather_red" and r["dist"] == "uniform" and r["rows"] == 17770]
+    if not best:
+        return None, None, "unavailable"
+    top = max(best, key=lambda r: r["G_rows_per_s"])
+    return top["G_rows_per_s"], top["l2_TB_per_s"], src
 
 
 def traffic_from_profiles(kernel, k):
@@ -330,16 +361,24 @@ def run_ours(args):
     clocks = ClockSampler()
     clocks.start()
     t0 = time.perf_counter()
+    step_ms, prev = [], 0.0
     for _ in range(args.steps):
-        sess.run(T)  # each call ends with a stream synchronize
+        sess.run(T)  # each call ends with a stream synchronize; raises on a non-finite loss check (CU2B_ERR_DIVERGED)
+        now = sess.stats()["total_ms"]
+        step_ms.append(now - prev)
+        prev = now
     wall = time.perf_counter() - t0
     clk = clocks.stop()
     st = sess.stats()
     lg = sess.log()
     sess.close()
+    if not all(np.isfinite(r["test_rmse"]) and np.isfinite(r["train_rmse"]) for r in lg):
+        raise SystemExit("[bench] non-finite RMSE in the training log: %r" % ([r["test_rmse"] for r in lg],))
     updates = st["updates"]
     dev_s = st["total_ms"] / 1e3
     value = updates / dev_s
+    spread = {"steps_ms": [round(x, 3) for x in step_ms], "min_ms": min(step_ms), "median_ms": float(np.median(step_ms)),
+              "max_ms": max(step_ms), "value_best_step": T * U / (min(step_ms) / 1e3), "value_worst_step": T * U / (max(step_ms) / 1e3)}
     bytes_per_update = 16 * k + 12
     sgd_gbs = updates * bytes_per_update / (st["sgd_ms"] / 1e3) / 1e9
     peak, peak_src = peaks()
@@ -347,17 +386,31 @@ def run_ours(args):
     kernel_name = ("mf_sgd_hogwild" if cfg.round_iters <= 1 else
                    "mf_sgd_user_tiles" if os.environ.get("CU2B_TILE_PIPE") == "tma" else "mf_sgd_user_rounds")
     bpu = traffic_from_profiles(kernel_name, k)
-    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": sgd_gbs, "peak": peak, "unit": "GB/s",
-                "frac": sgd_gbs / peak, "peak_source": peak_src,
+    kernel_ups = updates / (st["sgd_ms"] / 1e3)
+    # The kernel keeps a user's P row in registers for a whole round, so HBM sees ~80 B/update; what binds is the
+    # L2: every update reads an item row (4 k bytes) and adds a step to it with 128-bit atomics (4 k bytes), plus
+    # 4 + 4 bytes of item bias. Bound = that traffic / the measured peak of exactly this access pattern with
+    # uniformly random rows (tools/micro/l2_rows; no popularity skew, which only the data decides).
+    l2_bytes_per_update = 8 * k + 8
+    peak_rows, peak_tbs, peak_l2_src = l2_row_peak()
+    l2_achieved = kernel_ups * l2_bytes_per_update / 1e9
+    l2_peak = None if peak_tbs is None else peak_tbs * 1e3 * (512.0 / 512.0)
+    roofline = {"bound": "l2_atomic", "kernel": kernel_name, "achieved": l2_achieved, "peak": l2_peak, "unit": "GB/s",
+                "frac": None if not l2_peak else l2_achieved / l2_peak, "peak_source": peak_l2_src,
+                "what": "L2 bytes moved by the item side of the updates (row read + 128-bit atomic add of the row + bias) per "
+                        "second vs the measured peak of 'read a 512-byte row, red.global.add.v4.f32 a 512-byte step' on "
+                        "uniformly random rows",
+                "l2_bytes_per_update": l2_bytes_per_update, "peak_G_rows_per_s": peak_rows,
                 # per launch, like `achieved`: ncu dram__bytes_read+write per update x updates per launch
                 "traffic": None if bpu is None else bpu * updates / launches,
-                "traffic_bytes_per_update": bpu, "algorithmic_bytes_per_update": bytes_per_update,
-                "algorithmic_bytes_per_launch": bytes_per_update * updates / launches,
+                "traffic_bytes_per_update": bpu,
                 "launches": launches, "kernel_ms_per_launch": st["sgd_ms"] / launches,
-                "kernel_ms_per_step": st["sgd_ms"] / args.steps,
-                "kernel_updates_per_s": updates / (st["sgd_ms"] / 1e3),
-                "note": "Q (9 MB at k=128) stays in L2, so about half of the algorithmic bytes never reach "
-                        "HBM; frac > 1 of the copy peak is possible, traffic is the physical DRAM volume"}
+                "kernel_ms_per_step": st["sgd_ms"] / args.steps, "kernel_updates_per_s": kernel_ups,
+                # the north star's accounting, kept as a labelled secondary: 16k+12 algorithmic bytes per update
+                # against the HBM copy peak. It exceeds 1 because P rows live in registers for 32 updates and Q in L2.
+                "hbm_algorithmic": {"bytes_per_update": bytes_per_update, "achieved": sgd_gbs, "peak": peak, "unit": "GB/s",
+                                    "frac": sgd_gbs / peak, "peak_source": peak_src,
+                                    "note": "not a bound for this kernel: physical DRAM traffic is `traffic`"}}
 
     # ---- the reference's iteration-synchronous order (round_iters = 1), for comparison ----------
     variants = {}
@@ -470,13 +523,13 @@ def run_ours(args):
                 "pinned host memory) + %d iterations + download (D2H of P, Q, biases), one step after the other" % T)
     sequential = {"value": T * U / e2e_s, "ms_per_step": 1e3 * e2e_s, "steps": e2e_steps, "ms_all_steps": e2e_all,
                   "what": seq_what}
-    # headline = the better of the two feeds of the SAME per-step work (both are listed)
-    best = pipelined if pipelined is not None and pipelined["value"] > sequential["value"] else sequential
-    e2e = {"value": best["value"], "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "ms_per_step": best["ms_per_step"], "steps": e2e_steps, "feed": "pipelined" if best is pipelined else "sequential",
-           "what": best["what"], "sequential": sequential, "pipelined": pipelined,
-           "cold": {"value": T * U / cold_s, "ms_per_step": 1e3 * cold_s, "ms_all_steps": cold_all,
-                    "what": "cu2b_session_create + %d iterations + download + destroy (allocation and set-up included)" % T}}
+    # headline = the single call a user of train() / bin/mf makes: create + run + download + destroy, every step.
+    # The resident-session feeds of the same per-step work are listed beside it as named variants.
+    e2e = {"value": T * U / cold_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "ms_per_step": 1e3 * cold_s, "steps": 3, "ms_all_steps": cold_all, "feed": "single_call",
+           "what": "cu2b_session_create (allocation, H2D of both rating matrices + initial model from pinned host memory, "
+                   "set-up) + %d iterations with their loss checks + download (D2H of P, Q, biases) + destroy; median of 3" % T,
+           "resident_sequential": sequential, "resident_pipelined": pipelined}
 
     # ---- CPU baseline (rank 0, bounded sample) -----------------------------------------------
     cpu = None
@@ -488,7 +541,7 @@ def run_ours(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * dev_s / args.steps, "wall_ms_per_step": 1e3 * wall / args.steps,
+        "ms_per_step": 1e3 * dev_s / args.steps, "wall_ms_per_step": 1e3 * wall / args.steps, "spread": spread,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": config_dict(args, k), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": int(st["kernel_launches"]), "clocks": clk,
@@ -564,6 +617,8 @@ def run_ours_dsgd(args, rank, world):
     clk = clocks.stop() if rank == 0 else None
     st = d.stats()
     lg = d.log()
+    if not all(np.isfinite(r["test_rmse"]) and np.isfinite(r["train_rmse"]) for r in lg):
+        raise SystemExit("[bench] rank %d: non-finite RMSE in the DSGD training log: %r" % (rank, [r["test_rmse"] for r in lg]))
     # NCCL all-reduce of the rank-local loss sums must reproduce the peer-memory combine
     sums = torch.tensor(d.local_sums(), dtype=torch.float64, device="cuda")
     dist.all_reduce(sums)
@@ -580,13 +635,18 @@ def run_ours_dsgd(args, rank, world):
     bytes_per_update = 16 * k + 12
     peak, peak_src = peaks()
     my_gbs = st["updates"] * bytes_per_update / (st["sgd_ms"] / 1e3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "mf_sgd_user_runs", "achieved": my_gbs, "peak": peak, "unit": "GB/s",
-                "frac": my_gbs / peak, "traffic": None, "peak_source": peak_src, "scope": "rank 0, per GPU",
-                "algorithmic_bytes_per_update": bytes_per_update, "kernel_ms_per_step_max_rank": sgd_ms_max / args.steps,
-                "note": "DSGD sub-epoch kernel: a lane group keeps its user's P row in registers over the user's run, "
-                        "item rows are L2-resident (per-rank P strip %d MB); in-flight updates are capped for "
-                        "asynchronous-SGD stability (see DESIGN.md), so this is latency-, not bandwidth-bound" % (
-                            inp.P.nbytes >> 20)}
+    my_ups = st["updates"] / (st["sgd_ms"] / 1e3)
+    peak_rows, peak_tbs, peak_l2_src = l2_row_peak() if rank == 0 else (None, None, None)
+    l2_bytes_per_update = 8 * k + 8
+    roofline = {"bound": "l2_atomic", "kernel": "mf_sgd_user_runs (fused wait + sub-epoch + hand-off)", "scope": "rank 0, per GPU",
+                "achieved": my_ups * l2_bytes_per_update / 1e9, "peak": None if peak_tbs is None else peak_tbs * 1e3, "unit": "GB/s",
+                "frac": None if not peak_tbs else my_ups * l2_bytes_per_update / 1e9 / (peak_tbs * 1e3), "peak_source": peak_l2_src,
+                "l2_bytes_per_update": l2_bytes_per_update, "kernel_updates_per_s": my_ups, "traffic": None,
+                "kernel_ms_per_step_max_rank": sgd_ms_max / args.steps,
+                "note": "the kernel time of a linked sub-epoch includes waiting for the upstream rank's hand-off; a rank sees 1/N "
+                        "of the catalogue at a time, so item popularity concentrates its L2 traffic on fewer slices than on one GPU",
+                "hbm_algorithmic": {"bytes_per_update": bytes_per_update, "achieved": my_gbs, "peak": peak, "unit": "GB/s",
+                                    "frac": my_gbs / peak, "peak_source": peak_src}}
 
     # end to end: per rank H2D of its strips + model, T iterations, download, destroy
     pinp = cu.api.DsgdRankInputs(

@@ -77,9 +77,19 @@ def build_cli(force=False):
     return outs
 
 
+def build_micro(force=False):
+    """tools/micro/l2_rows: the L2 row-traffic micro-benchmark bench.py takes its roofline denominator from."""
+    src = os.path.join(ROOT, "tools", "micro", "l2_rows.cu")
+    out = os.path.join(ROOT, "tools", "micro", "l2_rows")
+    if os.path.exists(src) and (force or _newer(out, [src])):
+        _run([NVCC, *ARCH, "-lineinfo", "-O3", "-Xcompiler", "-fopenmp", "-o", out, src])
+    return out
+
+
 def build_all(force=False, verbose=False):
     build_lib(force, verbose)
     build_cli(force)
+    build_micro(force)
 
 
 if __name__ == "__main__":

@@ -154,6 +154,27 @@ dsgd_sample_runs_kernel(const int *__restrict__ indptr, const cu2b_rating *__res
 // order (exact sequential semantics on the user side, P traffic once per run instead of once per
 // update), and adds the item-side steps with 128-bit L2 atomics (other users update the same
 // item rows concurrently). Same arithmetic as sgd_update_slots.
+// What ties a sub-epoch kernel to its neighbours on the ring when wait, update and hand-off run as ONE launch
+// (mf_sgd_user_runs<..., LINKED = true>): the prologue polls this rank's own arrive word for the item block
+// (written by the upstream rank through NVLink), the epilogue -- executed by whichever CTA leaves last -- copies
+// the block's rows and biases into the downstream rank's arrays with peer stores and publishes its arrive word.
+struct SubEpochLink {
+    const int *wait_flag;       // nullptr: the block is already here (first sub-epoch of the first round)
+    int wait_need;
+    const float4 *src_q;        // nullptr: nothing to hand off
+    float4 *dst_q;
+    long long n_vec;
+    const float *src_ib;
+    float *dst_ib;
+    int n_items;
+    int *dst_flag;
+    int value;
+    unsigned int *done;         // CTAs that have left; the last one resets it
+    int *error_flag;
+    long long timeout_cycles;
+    int site;
+};
+
 struct UserRunParams {
     const DsgdDraw *draws;
     const int *row_off;   // [n_active][world + 1]
@@ -166,15 +187,29 @@ struct UserRunParams {
     const float *lr;
     float P_reg, Q_reg, ub_reg, ib_reg;
     int is_train;
+    SubEpochLink link;          // used by the LINKED instantiations only
 };
 
 // THIN: the draws may carry kDrawRowFrozen / kDrawBiasFrozen (item-step thinning); the default
-// instantiation does not look at the bits.
-template <int L, int V, bool THIN = false>
-__global__ void __launch_bounds__(256)
+// instantiation does not look at the bits. LINKED: fused wait + sub-epoch + hand-off (SubEpochLink).
+template <int L, int V, bool THIN = false, bool LINKED = false>
+__global__ void __launch_bounds__(256, (V == 1 ? 8 : 4))
 mf_sgd_user_runs(const UserRunParams p) {
     constexpr int G = 32 / L;
     const int lane = threadIdx.x & 31, g = lane / L, l = lane % L;
+    if (LINKED) {
+        if (p.link.wait_flag && threadIdx.x == 0) {
+            const long long t0 = clock64();
+            while (ld_acquire_sys(p.link.wait_flag) < p.link.wait_need) {
+                __nanosleep(100);
+                if (clock64() - t0 > p.link.timeout_cycles) {
+                    atomicCAS(p.link.error_flag, 0, p.link.site * 1000000 + p.link.wait_need * 100 + (ld_acquire_sys(p.link.wait_flag) % 100));
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+    }
     const int vecs = p.kp >> 2;
     const float lr = __ldg(p.lr);
     const StepCoef sc = step_coef(lr, p.P_reg, p.Q_reg, p.ub_reg, p.ib_reg);
@@ -236,6 +271,35 @@ mf_sgd_user_runs(const UserRunParams p) {
             if (l == 0) __stcg(p.user_bias + u, ub);
         }
     }
+    }
+    if (LINKED) {
+        if (p.link.src_q == nullptr) return;
+        // Last CTA out hands the block over. Every thread's atomic adds are performed device-wide before its CTA
+        // counts itself out (fence, then barrier, then the counter), so the copier reads final rows from L2.
+        __shared__ int last_out;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) last_out = atomicAdd(p.link.done, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (!last_out) return;
+        __threadfence();
+        for (long long i = threadIdx.x; i < p.link.n_vec; i += 4 * 256) {
+            float4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (i + j * 256 < p.link.n_vec) v[j] = __ldcg(p.link.src_q + i + j * 256);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (i + j * 256 < p.link.n_vec) p.link.dst_q[i + j * 256] = v[j];
+        }
+        for (int i = threadIdx.x; i < p.link.n_items; i += 256)
+            p.link.dst_ib[(size_t)i * p.ibs] = __ldcg(p.link.src_ib + (size_t)i * p.ibs);
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            *p.link.done = 0u;
+            st_release_sys(p.link.dst_flag, p.link.value);
+        }
     }
 }
 

@@ -407,6 +407,25 @@ UserRunKernel pick_user_runs(int L, int V) {
     }
 }
 
+// fused wait + sub-epoch + hand-off instantiations (multi-GPU DSGD, one rank per device)
+template <bool THIN>
+UserRunKernel pick_user_runs_linked(int L, int V) {
+    switch (L) {
+        case 1: return mf_sgd_user_runs<1, 1, THIN, true>;
+        case 2: return mf_sgd_user_runs<2, 1, THIN, true>;
+        case 4: return mf_sgd_user_runs<4, 1, THIN, true>;
+        case 8: return mf_sgd_user_runs<8, 1, THIN, true>;
+        case 16: return mf_sgd_user_runs<16, 1, THIN, true>;
+        default:
+            switch (V) {
+                case 1: return mf_sgd_user_runs<32, 1, THIN, true>;
+                case 2: return mf_sgd_user_runs<32, 2, THIN, true>;
+                case 3: return mf_sgd_user_runs<32, 3, THIN, true>;
+                default: return mf_sgd_user_runs<32, 4, THIN, true>;
+            }
+    }
+}
+
 UserRunKernel pick_user_runs_thin(int L, int V) {
     switch (L) {
         case 1: return mf_sgd_user_runs<1, 1, true>;

@@ -49,9 +49,17 @@ enum Mode { GATHER = 0, RED = 1, GATHER_RED = 2, SGD_LIKE = 3, BIAS_ONLY = 4 };
 // PLANAR: line j of every row lives in plane j ([4][n_rows][128 bytes]) instead of row-major.
 template <int MODE, int UN, int PLANAR = 0>
 __global__ void __launch_bounds__(256)
-rows_kernel(float4 *rows, float *bias, int bias_stride, const int *__restrict__ idx, long long n, float *sink, int n_rows) {
+rows_kernel(float4 *rows, float *bias, int bias_stride, const int *__restrict__ idx, long long n, float *sink, int n_rows,
+            float4 *hot, int n_hot) {
     const int lane = threadIdx.x & 31;
+    // PLANAR == 2: "hot table": rows with id < n_hot (the popular ones; ids are popularity ranks here) are stored
+    // sector-scattered -- sector j (32 bytes, lanes 2j and 2j+1) of hot row h starts 1 KB block h * 16 + j of a
+    // separate table, so one hot row spreads over 16 L2 slice pairs; the other rows stay row-major.
     auto at = [&](int r) -> float4 * {
+        if (PLANAR == 2) {
+            if (r < n_hot) return hot + (((size_t)r * 16 + (lane >> 1)) * 64 + (lane & 1));
+            return rows + (size_t)r * 32 + lane;
+        }
         return PLANAR ? rows + ((size_t)(lane >> 3) * n_rows + r) * 8 + (lane & 7) : rows + (size_t)r * 32 + lane;
     };
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -141,8 +149,9 @@ static std::vector<int> make_indices(long long n, int N, int dist, uint64_t seed
     return out;
 }
 
-typedef void (*Kern)(float4 *, float *, int, const int *, long long, float *, int);
+typedef void (*Kern)(float4 *, float *, int, const int *, long long, float *, int, float4 *, int);
 static Kern pick(int mode, int un, int planar) {
+    if (planar == 2) return mode == GATHER_RED ? (Kern)rows_kernel<GATHER_RED, 1, 2> : (Kern)rows_kernel<SGD_LIKE, 1, 2>;
     if (planar) return mode == GATHER_RED ? (Kern)rows_kernel<GATHER_RED, 1, 1> : (Kern)rows_kernel<SGD_LIKE, 1, 1>;
 #define ROW(M) (un == 1 ? (Kern)rows_kernel<M, 1> : un == 2 ? (Kern)rows_kernel<M, 2> : (Kern)rows_kernel<M, 4>)
     switch (mode) {
@@ -171,6 +180,11 @@ int main(int argc, char **argv) {
     CK(cudaMalloc(&bias, (size_t)maxN * max_stride * 4));
     CK(cudaMemset(bias, 0, (size_t)maxN * max_stride * 4));
     CK(cudaMalloc(&sink, 4));
+    float4 *hot;
+    const int max_hot = 1024;
+    CK(cudaMalloc(&hot, (size_t)max_hot * 16 * 1024));
+    CK(cudaMemset(hot, 0, (size_t)max_hot * 16 * 1024));
+    int n_hot = 0;
     CK(cudaMalloc(&idx_dev, (size_t)n * 4));
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
@@ -180,11 +194,11 @@ int main(int argc, char **argv) {
     auto run = [&](int mode, int dist, int N, int stride, int ctas_per_sm, int un, int planar = 0) {
         Kern k = pick(mode, un, planar);
         const int grid = sms * ctas_per_sm;
-        for (int w = 0; w < 2; ++w) k<<<grid, 256>>>(rows, bias, stride, idx_dev, n, sink, N);
+        for (int w = 0; w < 2; ++w) k<<<grid, 256>>>(rows, bias, stride, idx_dev, n, sink, N, hot, n_hot);
         float best = 1e30f;
         for (int rep = 0; rep < 3; ++rep) {
             CK(cudaEventRecord(e0));
-            k<<<grid, 256>>>(rows, bias, stride, idx_dev, n, sink, N);
+            k<<<grid, 256>>>(rows, bias, stride, idx_dev, n, sink, N, hot, n_hot);
             CK(cudaEventRecord(e1));
             CK(cudaEventSynchronize(e1));
             float ms;
@@ -199,9 +213,10 @@ int main(int argc, char **argv) {
         if (mode == GATHER_RED) bytes = 1024;
         if (mode == SGD_LIKE) bytes = 1032;
         if (mode == BIAS_ONLY) bytes = 8;
-        printf("{\"mode\": \"%s\", \"dist\": \"%s\", \"layout\": \"%s\", \"rows\": %d, \"bias_stride_floats\": %d, \"ctas_per_sm\": %d, "
+        printf("{\"mode\": \"%s\", \"dist\": \"%s\", \"layout\": \"%s\", \"n_hot\": %d, \"rows\": %d, \"bias_stride_floats\": %d, \"ctas_per_sm\": %d, "
                "\"unroll\": %d, \"ms\": %.4f, \"G_rows_per_s\": %.3f, \"l2_TB_per_s\": %.3f}\n",
-               mode_name[mode], dist_name[dist], planar ? "planar" : "row_major", N, stride, ctas_per_sm, un, best, rows_s / 1e9,
+               mode_name[mode], dist_name[dist], planar == 2 ? "hot_table" : planar ? "planar" : "row_major", planar == 2 ? n_hot : 0, N, stride,
+               ctas_per_sm, un, best, rows_s / 1e9,
                rows_s * bytes / 1e12);
         fflush(stdout);
     };
@@ -209,6 +224,28 @@ int main(int argc, char **argv) {
         std::vector<int> h = make_indices(n, N, dist, 20240607, N / 300.0 + 1.0);
         CK(cudaMemcpy(idx_dev, h.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
     };
+    if (argc > 1 && !strcmp(argv[1], "peak")) {
+        // the roofline denominator bench.py uses: row read + atomic row add, uniformly random rows of the whole catalogue
+        load(17770, 0);
+        for (int un : {1, 4})
+            for (int c : {4, 8}) run(GATHER_RED, 0, 17770, 1, c, un);
+        for (int c : {4, 8}) run(SGD_LIKE, 0, 17770, 64, c, 1);
+        return 0;
+    }
+    if (argc > 1 && !strcmp(argv[1], "hot")) {
+        // hot table: ids are popularity ranks (dist 2); the cold rows keep the plain popularity order
+        for (int N : {17770, 4442, 2221}) {
+            load(N, 2);
+            for (int h : {0, 8, 32, 128, 512}) {
+                n_hot = std::min(h, N);
+                for (int c : {4, 8}) {
+                    run(GATHER_RED, 2, N, 64, c, 1, h ? 2 : 0);
+                    run(SGD_LIKE, 2, N, 64, c, 1, h ? 2 : 0);
+                }
+            }
+        }
+        return 0;
+    }
     if (placement) {
         // Which internal row order balances the L2 slices? (bias padded to one per 256 bytes throughout)
         for (int N : {17770, 8885, 4442, 2221}) {
