@@ -100,6 +100,7 @@ SYMBOLS = {
     "cu2b_prep_create_config": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_double, C.c_int] + [C.c_double] * 4),
     "cu2b_predict_topk": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, C.c_float, C.c_int, C.POINTER(Csr), C.c_int, _P, _P,
                                     C.POINTER(C.c_double)]),
+    "cu2b_release_cache": (C.c_int, []),
     "cu2b_device_info": (C.c_int, [C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                    C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
 }

@@ -49,6 +49,7 @@ struct __align__(8) DsgdDraw {
     int item;
     float rating;
 };
+constexpr int kDrawsPerLane = 8;  // dsgd_sample_runs_kernel keeps a round's draws in registers: rounds of <= 256 iterations
 constexpr int kDrawRowFrozen = (int)0x80000000u;
 constexpr int kDrawBiasFrozen = 0x40000000;
 constexpr int kDrawItemMask = 0x3fffffff;
@@ -90,16 +91,37 @@ dsgd_sample_runs_kernel(const int *__restrict__ indptr, const cu2b_rating *__res
         const int u = __ldg(&active_users[a]);
         const uint32_t uid = user_ids ? (uint32_t)__ldg(&user_ids[u]) : (uint32_t)u;
         const int lo = __ldg(&indptr[u]), n = __ldg(&indptr[u + 1]) - lo;
-        // pass 1: block histogram of the nb draws
+        // The lane's draws (iterations lane, lane + 32, ...) are evaluated once and kept in registers: Philox,
+        // the gather of (item, rating), the item block and the thinning flags. kDrawsPerLane * 32 bounds the round.
+        DsgdDraw mine[kDrawsPerLane];
+        int blk_of[kDrawsPerLane];
         int cnt[kMaxWorld];
 #pragma unroll
         for (int b = 0; b < kMaxWorld; ++b) cnt[b] = 0;
-        for (int t = lane; t < nb; t += 32) {
-            const uint32_t r = philox4x32_10_x(uid, (uint32_t)(iter0 + t), 0u, PHILOX_TAG, seed, PHILOX_KEY1);
-            const int j = lo + (int)__umulhi(r, (uint32_t)n);
-            const int blk = item_block_of(__ldg(&coo[j].item), sh_ptr, world);
 #pragma unroll
-            for (int b = 0; b < kMaxWorld; ++b) cnt[b] += (blk == b);
+        for (int q = 0; q < kDrawsPerLane; ++q) {
+            const int t = q * 32 + lane;
+            mine[q].item = 0; mine[q].rating = 0.f;
+            blk_of[q] = -1;
+            if (t < nb) {
+                const uint2 r = philox4x32_10_xy(uid, (uint32_t)(iter0 + t), 0u, PHILOX_TAG, seed, PHILOX_KEY1);
+                const int j = lo + (int)__umulhi(r.x, (uint32_t)n);
+                DsgdDraw d;
+                d.item = __ldg(&coo[j].item);
+                d.rating = __ldg(&coo[j].rating);
+                const int blk = item_block_of(d.item, sh_ptr, world);
+                if (keep_row || keep_bias) {
+                    const float x = (float)(r.y >> 8) * (1.0f / 16777216.0f);
+                    int flags = 0;
+                    if (keep_row && x >= __ldg(&keep_row[d.item])) flags |= kDrawRowFrozen;
+                    if (keep_bias && x >= __ldg(&keep_bias[d.item])) flags |= kDrawBiasFrozen;
+                    d.item |= flags;
+                }
+                mine[q] = d;
+                blk_of[q] = blk;
+#pragma unroll
+                for (int b = 0; b < kMaxWorld; ++b) cnt[b] += (blk == b);
+            }
         }
         int off[kMaxWorld + 1];
         off[0] = 0;
@@ -116,32 +138,16 @@ dsgd_sample_runs_kernel(const int *__restrict__ indptr, const cu2b_rating *__res
             for (int b = 0; b <= kMaxWorld; ++b) v = (lane == b) ? off[b] : v;
             row_off[(size_t)a * (world + 1) + lane] = v;
         }
-        // pass 2: place the draws, stable inside a block
+        // place the draws, iteration order kept inside a block (ballot ranking)
         DsgdDraw *row = draws + (size_t)a * pitch;
-        for (int t0 = 0; t0 < nb; t0 += 32) {
-            const int t = t0 + lane;
-            int blk = -1;
-            DsgdDraw d;
-            d.item = 0; d.rating = 0.f;
-            if (t < nb) {
-                const uint2 r = philox4x32_10_xy(uid, (uint32_t)(iter0 + t), 0u, PHILOX_TAG, seed, PHILOX_KEY1);
-                const int j = lo + (int)__umulhi(r.x, (uint32_t)n);
-                d.item = __ldg(&coo[j].item);
-                d.rating = __ldg(&coo[j].rating);
-                blk = item_block_of(d.item, sh_ptr, world);
-                if (keep_row || keep_bias) {
-                    const float x = (float)(r.y >> 8) * (1.0f / 16777216.0f);
-                    int flags = 0;
-                    if (keep_row && x >= __ldg(&keep_row[d.item])) flags |= kDrawRowFrozen;
-                    if (keep_bias && x >= __ldg(&keep_bias[d.item])) flags |= kDrawBiasFrozen;
-                    d.item |= flags;
-                }
-            }
+#pragma unroll
+        for (int q = 0; q < kDrawsPerLane; ++q) {
+            if (q * 32 >= nb) break;  // warp-uniform
 #pragma unroll
             for (int b = 0; b < kMaxWorld; ++b) {
                 if (b < world) {
-                    const unsigned m = __ballot_sync(0xffffffffu, blk == b);
-                    if (blk == b) row[off[b] + __popc(m & ((1u << lane) - 1u))] = d;
+                    const unsigned m = __ballot_sync(0xffffffffu, blk_of[q] == b);
+                    if (blk_of[q] == b) row[off[b] + __popc(m & ((1u << lane) - 1u))] = mine[q];
                     off[b] += __popc(m);
                 }
             }
@@ -274,31 +280,39 @@ mf_sgd_user_runs(const UserRunParams p) {
     }
     if (LINKED) {
         if (p.link.src_q == nullptr) return;
-        // Last CTA out hands the block over. Every thread's atomic adds are performed device-wide before its CTA
-        // counts itself out (fence, then barrier, then the counter), so the copier reads final rows from L2.
-        __shared__ int last_out;
+        // Hand-off by the whole grid. Every thread's atomic adds are performed device-wide before its CTA counts
+        // itself out (fence, barrier, counter); when the counter reaches the grid size the block is final and
+        // every CTA copies its share of the rows into the downstream rank's array with peer stores. The grid is
+        // sized to be co-resident (occupancy x SMs) and the rank owns its device, so the counter barrier cannot
+        // starve; it is bounded by the same timeout as the other device-side waits anyway.
         __threadfence();
         __syncthreads();
-        if (threadIdx.x == 0) last_out = atomicAdd(p.link.done, 1u) == gridDim.x - 1;
-        __syncthreads();
-        if (!last_out) return;
-        __threadfence();
-        for (long long i = threadIdx.x; i < p.link.n_vec; i += 4 * 256) {
-            float4 v[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (i + j * 256 < p.link.n_vec) v[j] = __ldcg(p.link.src_q + i + j * 256);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (i + j * 256 < p.link.n_vec) p.link.dst_q[i + j * 256] = v[j];
+        if (threadIdx.x == 0) {
+            atomicAdd(p.link.done, 1u);
+            const long long t0 = clock64();
+            while (ld_acquire_gpu((const int *)p.link.done) < (int)gridDim.x) {
+                __nanosleep(64);
+                if (clock64() - t0 > p.link.timeout_cycles) {
+                    atomicCAS(p.link.error_flag, 0, (20 + p.link.site) * 1000000);
+                    break;
+                }
+            }
         }
-        for (int i = threadIdx.x; i < p.link.n_items; i += 256)
-            p.link.dst_ib[(size_t)i * p.ibs] = __ldcg(p.link.src_ib + (size_t)i * p.ibs);
+        __syncthreads();
+        const long long stride = (long long)gridDim.x * blockDim.x;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.link.n_vec; i += stride)
+            p.link.dst_q[i] = __ldcg(p.link.src_q + i);
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.link.n_items; i += stride)
+            p.link.dst_ib[i * p.ibs] = __ldcg(p.link.src_ib + i * p.ibs);
         __threadfence_system();
         __syncthreads();
         if (threadIdx.x == 0) {
-            *p.link.done = 0u;
-            st_release_sys(p.link.dst_flag, p.link.value);
+            if (atomicAdd(p.link.done + 1, 1u) == gridDim.x - 1) {  // last copier: publish, reset both counters
+                p.link.done[0] = 0u;
+                p.link.done[1] = 0u;
+                __threadfence_system();
+                st_release_sys(p.link.dst_flag, p.link.value);
+            }
         }
     }
 }

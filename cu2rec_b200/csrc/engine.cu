@@ -72,24 +72,48 @@ struct Trace {
 // ---------------------------------------------------------------------------------------
 // small RAII pool: everything allocated through it is released when it goes out of scope
 // ---------------------------------------------------------------------------------------
+// The library's own stream-ordered memory pool of a device (one per device and process, created on first use).
+// It is kept warm -- release threshold = never -- so that a train() call does not pay cudaMalloc / cudaFree of
+// several GB every time; the host application's default pool and its cudaMalloc heap are left alone, and
+// cu2b_release_cache() hands the cached memory back.
+cudaMemPool_t *library_pools() {
+    static cudaMemPool_t pools[64] = {nullptr};
+    return pools;
+}
+cudaMemPool_t library_pool(int dev) {
+    if (dev < 0 || dev >= 64) return nullptr;
+    cudaMemPool_t *pools = library_pools();
+    if (pools[dev]) return pools[dev];
+    int supported = 0;
+    cudaDeviceGetAttribute(&supported, cudaDevAttrMemoryPoolsSupported, dev);
+    if (!supported) return nullptr;
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof props);
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t mp = nullptr;
+    if (cudaMemPoolCreate(&mp, &props) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    unsigned long long never = ~0ULL;
+    cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &never);
+    pools[dev] = mp;
+    return mp;
+}
+
 struct DevPool {
     std::vector<void *> ptrs;
-    // Stream-ordered allocation from the device's default memory pool (kept warm: release
-    // threshold = never), so that a train() call does not pay cudaMalloc/cudaFree of several GB
-    // every time. DSGD contexts export their buffers through CUDA IPC and therefore use plain
-    // cudaMalloc (async == false).
+    // Stream-ordered allocation from the library's pool. DSGD contexts export their buffers through CUDA IPC
+    // and therefore use plain cudaMalloc (async == false).
     bool async = false;
     cudaStream_t stream = nullptr;
+    cudaMemPool_t mem_pool = nullptr;
     ~DevPool() { release(); }
     void use_async(cudaStream_t st) {
-        int dev = 0, supported = 0;
+        int dev = 0;
         if (cudaGetDevice(&dev) != cudaSuccess) return;
-        cudaDeviceGetAttribute(&supported, cudaDevAttrMemoryPoolsSupported, dev);
-        if (!supported) return;
-        cudaMemPool_t mp;
-        if (cudaDeviceGetDefaultMemPool(&mp, dev) != cudaSuccess) return;
-        unsigned long long never = ~0ULL;
-        cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &never);
+        mem_pool = library_pool(dev);
+        if (!mem_pool) return;
         async = true;
         stream = st;
     }
@@ -103,7 +127,7 @@ struct DevPool {
     cu2b_status alloc(T **out, size_t count) {
         void *p = nullptr;
         size_t bytes = std::max<size_t>(16, count * sizeof(T));
-        cudaError_t e = async ? cudaMallocAsync(&p, bytes, stream) : cudaMalloc(&p, bytes);
+        cudaError_t e = async ? cudaMallocFromPoolAsync(&p, bytes, mem_pool, stream) : cudaMalloc(&p, bytes);
         if (e != cudaSuccess) {
             *out = nullptr;
             cudaGetLastError();
@@ -151,14 +175,32 @@ expand_coo_kernel(const int *__restrict__ indptr, int rows, const int *__restric
     }
 }
 
+// What the engine needs to know about a device, queried once per process and device
+// (cudaGetDeviceProperties costs milliseconds; a train() call should not pay it twice).
+struct DeviceFacts {
+    int sm_count = 0, cc_major = 0, cc_minor = 0;
+    bool known = false;
+};
+cu2b_status device_facts(int dev, DeviceFacts *out) {
+    static DeviceFacts cache[64];
+    if (dev >= 0 && dev < 64 && cache[dev].known) { *out = cache[dev]; return CU2B_OK; }
+    DeviceFacts f;
+    CUDA_TRY(cudaDeviceGetAttribute(&f.sm_count, cudaDevAttrMultiProcessorCount, dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&f.cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&f.cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+    f.known = true;
+    if (dev >= 0 && dev < 64) cache[dev] = f;
+    *out = f;
+    return CU2B_OK;
+}
+
 cu2b_status check_device() {
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
-    cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
-    if (prop.major != 10)
-        return cu2b_fail(CU2B_ERR_CUDA, "libcu2b is built for sm_100a only; device %d is sm_%d%d (%s)",
-                         dev, prop.major, prop.minor, prop.name);
+    DeviceFacts f;
+    CU2B_TRY(device_facts(dev, &f));
+    if (f.cc_major != 10)
+        return cu2b_fail(CU2B_ERR_CUDA, "libcu2b is built for sm_100a only; device %d is sm_%d%d", dev, f.cc_major, f.cc_minor);
     return CU2B_OK;
 }
 
@@ -1262,9 +1304,9 @@ static cu2b_status session_create_impl(cu2b_session **out, int device, const cu2
     s->rows = train->rows;
     s->cols = train->cols;
     memset(&s->stats, 0, sizeof(s->stats));
-    cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-    s->sm_count = prop.multiProcessorCount;
+    DeviceFacts facts;
+    CU2B_TRY(device_facts(device, &facts));
+    s->sm_count = facts.sm_count;
     CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     if (alloc_stream && !getenv("CU2B_NO_MEMPOOL")) s->pool.use_async(s->stream);
 
@@ -1606,9 +1648,9 @@ struct Scratch {
         s.rows = rows;
         s.cols = cols;
         memset(&s.stats, 0, sizeof(s.stats));
-        cudaDeviceProp prop;
-        CUDA_TRY(cudaGetDeviceProperties(&prop, s.device));
-        s.sm_count = prop.multiProcessorCount;
+        DeviceFacts facts;
+        CU2B_TRY(device_facts(s.device, &facts));
+        s.sm_count = facts.sm_count;
         CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         CU2B_TRY(s.pool.alloc(&s.P, (size_t)rows * s.kp));
         CU2B_TRY(s.pool.alloc(&s.Q, (size_t)cols * s.kp));
@@ -1799,6 +1841,13 @@ extern "C" cu2b_status cu2b_block_schedule_order(const cu2b_rating *coo, int64_t
     const int B = n_blocks > 0 ? n_blocks : auto_blocks(rows, cols);
     CU2B_TRY(build_block_schedule(coo, n, rows, cols, B, &bs, order));
     if (n_blocks_used) *n_blocks_used = B;
+    return CU2B_OK;
+}
+
+extern "C" cu2b_status cu2b_release_cache(void) {
+    cudaMemPool_t *pools = library_pools();
+    for (int dev = 0; dev < 64; ++dev)
+        if (pools[dev]) CUDA_TRY(cudaMemPoolTrimTo(pools[dev], 0));
     return CU2B_OK;
 }
 

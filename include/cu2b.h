@@ -316,6 +316,13 @@ cu2b_status cu2b_predict_topk(const float *P, int rows, const float *Q, int cols
                               const cu2b_csr *exclude, int topk, int32_t *out_items, float *out_scores,
                               double *ms_out);
 
+/* Sessions allocate from a stream-ordered memory pool that the library owns (one per device) and keeps warm
+ * between calls, so that repeated train() calls do not pay for allocating several GB each time (the
+ * reference allocates with cudaMalloc per call, matrix.cu:12-40, training.cu:34-88). This returns the cached
+ * device memory to the driver; live sessions are not affected. CU2B_NO_MEMPOOL=1 in the environment makes
+ * sessions use plain cudaMalloc / cudaFree instead. */
+cu2b_status cu2b_release_cache(void);
+
 /* Device introspection used by bench / CLI ("Free memory: %ld", mf.cu:35-37). */
 cu2b_status cu2b_device_info(int device, char *name, int name_cap, int *sm_count,
                              int *cc_major, int *cc_minor, int64_t *free_bytes,

@@ -1,0 +1,9 @@
+#!/bin/bash
+cd "${GRAFT_REPO_ROOT:-.}"
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2e7_gpu_tests.log 2>&1
+echo "pytest rc=$?"; tail -4 gpurun_out/r2e7_gpu_tests.log
+timeout 600 bash tools/run_bench_n.sh 2 r2_n2_fused --steps 3 --warmup 2
+tail -3 gpurun_out/bench_r2_n2_fused.log
+CU2B_DSGD_FUSED=0 timeout 600 bash tools/run_bench_n.sh 2 r2_n2_unfused --steps 3 --warmup 2
+CU2B_DSGD_ROUND=128 timeout 600 bash tools/run_bench_n.sh 2 r2_n2_fused_round128 --steps 3 --warmup 2

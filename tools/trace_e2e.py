@@ -16,8 +16,9 @@ ptr, pte = cu.CSRMatrix(U, I, *hp), cu.CSRMatrix(U, I, *hq)
 P, Q, ub, ib = (bench.pin(x) for x in (init(U * k), init(I * k), init(U), init(I)))
 out = tuple(bench.pin(x) for x in (P, Q, ub, ib))
 cfg = cu.Config(total_iterations=500, n_factors=k, check_error=500)
-for rep in range(5):
-    if rep == 4: os.environ["CU2B_TRACE"] = "1"
+for rep in range(8):
+    if rep in (1, 7): os.environ["CU2B_TRACE"] = "1"
+    else: os.environ.pop("CU2B_TRACE", None)
     t0 = time.perf_counter()
     s = cu.Session(ptr, pte, cfg, P, Q, ub, ib, mu); t1 = time.perf_counter()
     s.run(500); t2 = time.perf_counter()
