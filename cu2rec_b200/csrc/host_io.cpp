@@ -177,7 +177,9 @@ inline bool is_ws(char c) { return c == ' ' || c == '\n' || c == '\t' || c == '\
 // position just after the number, or nullptr if nothing converts.
 // Fast path: [sign] digits [. digits] with <= 7 significant digits and no exponent is
 // correctly rounded by a single float division (both operands exact in float).
-inline const char *parse_float(const char *p, const char *end, float *out) {
+// stream_rules: the general path follows operator>>(float&) (ratings CSV, util.cu:30) instead of strtof / std::stof
+// (factor files, util.cu:63).
+inline const char *parse_float(const char *p, const char *end, float *out, bool stream_rules = false) {
     const char *q = p;
     bool neg = false;
     if (q < end && (*q == '-' || *q == '+')) { neg = *q == '-'; ++q; }
@@ -198,24 +200,53 @@ inline const char *parse_float(const char *p, const char *end, float *out) {
         *out = neg ? -val : val;
         return q;
     }
-    char tmp[64];
-    std::string big;
-    const char *z = tmp;
-    const size_t n = (size_t)(end - p), m = std::min(n, sizeof(tmp) - 1);
-    memcpy(tmp, p, m);
-    tmp[m] = 0;
-    char *e;
-    float val = strtof(z, &e);
-    if (m < n && e == tmp + m) {  // the number may continue past our copy: take the whole token
-        size_t len = 0;
-        while (len < n && !is_ws(p[len]) && p[len] != ',') ++len;
-        big.assign(p, len);
-        z = big.c_str();
-        val = strtof(z, &e);
+    if (!stream_rules) {  // strtof's own acceptance (hexadecimal, inf, nan included), as std::stof
+        char tmp[64];
+        std::string big;
+        const char *z = tmp;
+        const size_t n = (size_t)(end - p), m = std::min(n, sizeof(tmp) - 1);
+        memcpy(tmp, p, m);
+        tmp[m] = 0;
+        char *e;
+        float val = strtof(z, &e);
+        if (m < n && e == tmp + m) {  // the number may continue past our copy: take the whole token
+            size_t len = 0;
+            while (len < n && !is_ws(p[len]) && p[len] != ',') ++len;
+            big.assign(p, len);
+            z = big.c_str();
+            val = strtof(z, &e);
+        }
+        if (e == z) return nullptr;
+        *out = val;
+        return p + (e - z);
     }
-    if (e == z) return nullptr;
+    // General path: what libstdc++'s operator>>(float&) does (the reference reads with it, util.cu:30). The
+    // stream first collects the longest prefix of the form [sign] digits [. digits] [e|E [sign] digits] -- it
+    // never looks at "inf", "nan" or hexadecimal forms -- and then requires strtof to consume ALL of it: a
+    // dangling exponent ("1e", "4.5e+") or an out-of-range value ("1e50") sets failbit, which ends the
+    // reference's read loop at this row.
+    q = p;
+    if (q < end && (*q == '-' || *q == '+')) ++q;
+    bool mant_digits = false;
+    while (q < end && *q >= '0' && *q <= '9') { ++q; mant_digits = true; }
+    if (q < end && *q == '.') {
+        ++q;
+        while (q < end && *q >= '0' && *q <= '9') { ++q; mant_digits = true; }
+    }
+    if (!mant_digits) return nullptr;
+    if (q < end && (*q == 'e' || *q == 'E')) {
+        const char *x = q + 1;
+        if (x < end && (*x == '-' || *x == '+')) ++x;
+        if (x >= end || *x < '0' || *x > '9') return nullptr;  // the stream has swallowed the 'e': conversion fails
+        while (x < end && *x >= '0' && *x <= '9') ++x;
+        q = x;
+    }
+    const std::string token(p, (size_t)(q - p));
+    char *e = nullptr;
+    const float val = strtof(token.c_str(), &e);
+    if (e != token.c_str() + token.size() || !std::isfinite(val)) return nullptr;
     *out = val;
-    return p + (e - z);
+    return q;
 }
 
 // One "int <char> int <char> float" record starting at p (leading whitespace allowed).
@@ -229,7 +260,12 @@ const char *parse_record(const char *p, const char *end, cu2b_rating *out) {
         if (*p == '-' || *p == '+') { neg = *p == '-'; ++p; }
         if (p >= end || *p < '0' || *p > '9') return nullptr;
         long v = 0;
-        while (p < end && *p >= '0' && *p <= '9') { v = v * 10 + (*p - '0'); ++p; }
+        while (p < end && *p >= '0' && *p <= '9') {
+            v = v * 10 + (*p - '0');
+            ++p;
+            if (v > (long)INT32_MAX + 1) return nullptr;  // operator>>(int&) fails on overflow: the reference stops here
+        }
+        if (!neg && v > (long)INT32_MAX) return nullptr;
         ids[part] = (int)(neg ? -v : v);
         while (p < end && is_ws(*p)) ++p;  // operator>>(char&) skips whitespace,
         if (p >= end) return nullptr;      // then takes any one character as the delimiter
@@ -238,7 +274,7 @@ const char *parse_record(const char *p, const char *end, cu2b_rating *out) {
     while (p < end && is_ws(*p)) ++p;
     if (p >= end) return nullptr;
     float val;
-    p = parse_float(p, end, &val);
+    p = parse_float(p, end, &val, true);
     if (!p) return nullptr;
     out->user = ids[0] - 1;
     out->item = ids[1] - 1;

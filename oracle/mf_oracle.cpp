@@ -33,6 +33,7 @@
 #include <cstring>
 #include <limits>
 #include <random>
+#include <thread>
 #include <vector>
 
 extern "C" {
@@ -325,6 +326,48 @@ void orc_loss(int rows, const int *indptr, const int *indices, const float *data
     if (sae_out) *sae_out = sae;
 }
 
+// The same sums for the loss checks of orc_train on large problems (at-size parity tests): users are cut into
+// contiguous chunks, one thread per chunk, chunk sums added in chunk order (deterministic; differs from the
+// sequential double sum by rounding of order 1e-16). Small problems keep the sequential loop above.
+static void loss_chunked(int rows, const int *indptr, const int *indices, const float *data, const float *P,
+                         const float *Q, const float *user_bias, const float *item_bias, float mu, int k,
+                         float *mae, float *rmse, int flavour) {
+    const long n = indptr[rows];
+    unsigned hw = std::thread::hardware_concurrency();
+    const int nt = (int)std::max(1u, std::min(hw ? hw : 1u, 32u));
+    if (n < (1L << 21) || nt == 1) {
+        orc_loss(rows, indptr, indices, data, P, Q, user_bias, item_bias, mu, k, mae, rmse, nullptr, nullptr, flavour);
+        return;
+    }
+    std::vector<double> sse(nt, 0.0), sae(nt, 0.0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t)
+        th.emplace_back([&, t]() {
+            // chunk bounds by rating count so that the threads finish together
+            const long lo_n = n * t / nt, hi_n = n * (t + 1) / nt;
+            const int u0 = (int)(std::lower_bound(indptr, indptr + rows + 1, (int)lo_n) - indptr);
+            const int u1 = t + 1 == nt ? rows : (int)(std::lower_bound(indptr, indptr + rows + 1, (int)hi_n) - indptr);
+            double a = 0.0, b = 0.0;
+            for (int u = u0; u < u1; ++u) {
+                const float *p = P + (size_t)u * k;
+                const float ub = user_bias[u];
+                for (int j = indptr[u]; j < indptr[u + 1]; ++j) {
+                    const int it = indices[j];
+                    const float e = data[j] - orc_predict(p, Q + (size_t)it * k, k, ub, item_bias[it], mu, flavour);
+                    a += (double)fabsf(e);
+                    b += (double)e * (double)e;
+                }
+            }
+            sae[t] = a;
+            sse[t] = b;
+        });
+    for (auto &x : th) x.join();
+    double a = 0.0, b = 0.0;
+    for (int t = 0; t < nt; ++t) { a += sae[t]; b += sse[t]; }
+    *mae = (float)(a / (double)n);
+    *rmse = (float)sqrt(b / (double)n);
+}
+
 // mf_sequential.cu:146-201 accumulates the same sums in float; kept for comparing against the
 // compiled mf_cpu's printed lines.
 void orc_loss_float_acc(int rows, const int *indptr, const int *indices, const float *data,
@@ -438,10 +481,10 @@ int orc_train(int rows, const int *tr_indptr, const int *tr_indices, const float
         }
         if ((i + 1) % check_error == 0 || i == 0 || (i + 1) % total_iterations == 0) {
             float tr_mae, tr_rmse, te_mae, te_rmse;
-            orc_loss(rows, tr_indptr, tr_indices, tr_data, P, Q, user_bias, item_bias, mu, k,
-                     &tr_mae, &tr_rmse, nullptr, nullptr, flavour);
-            orc_loss(te_rows, te_indptr, te_indices, te_data, P, Q, user_bias, item_bias, mu, k,
-                     &te_mae, &te_rmse, nullptr, nullptr, flavour);
+            loss_chunked(rows, tr_indptr, tr_indices, tr_data, P, Q, user_bias, item_bias, mu, k,
+                         &tr_mae, &tr_rmse, flavour);
+            loss_chunked(te_rows, te_indptr, te_indices, te_data, P, Q, user_bias, item_bias, mu, k,
+                         &te_mae, &te_rmse, flavour);
             last_validation_rmse = validation_rmse;
             validation_rmse = te_rmse;
             if (use_decay) {

@@ -398,3 +398,20 @@ def test_block_schedule_matches_oracle_and_is_conflict_free(B):
         assert len({a for a, _ in pairs}) == len(pairs) == len({b for _, b in pairs})
     _, auto = cu.block_schedule_order(coo, U, I, 0)
     assert auto == min(U, I)
+
+
+def test_read_csv_malformed_rows_match_the_reference_stream_semantics(tmp_path, golden_dir):
+    """Rows a strtof-based reader would swallow (inf, nan, hex, 1e50, dangling exponents) and ids that overflow int:
+    the reference reads with operator>> and stops at the first row the stream rejects. Goldens produced by the
+    unmodified reference readCSV (tests/golden/make_malformed_golden.py)."""
+    cases = json.load(open(os.path.join(golden_dir, "ref_read_csv_malformed.json")))
+    assert len(cases) >= 20
+    for name, want in cases.items():
+        path = tmp_path / (name + ".csv")
+        path.write_text(want["text"])
+        got, rows, cols, gb = cu.readCSV(str(path))
+        assert (len(got), rows, cols) == (want["n"], want["rows"], want["cols"]), name
+        assert got["user"].tolist() == want["users"] and got["item"].tolist() == want["items"], name
+        assert got["rating"].view(np.uint32).tolist() == want["rating_bits"], name
+        assert int(np.float32(gb).view(np.uint32)) == want["global_bias_bits"], name
+        assert np.all(np.isfinite(got["rating"])), name
