@@ -199,7 +199,7 @@ struct UserRunParams {
 // THIN: the draws may carry kDrawRowFrozen / kDrawBiasFrozen (item-step thinning); the default
 // instantiation does not look at the bits. LINKED: fused wait + sub-epoch + hand-off (SubEpochLink).
 template <int L, int V, bool THIN = false, bool LINKED = false>
-__global__ void __launch_bounds__(256, (V == 1 ? 8 : 4))
+__global__ void __launch_bounds__(256, (V == 1 ? (LINKED ? 6 : 8) : 4))
 mf_sgd_user_runs(const UserRunParams p) {
     constexpr int G = 32 / L;
     const int lane = threadIdx.x & 31, g = lane / L, l = lane % L;
@@ -280,18 +280,25 @@ mf_sgd_user_runs(const UserRunParams p) {
     }
     if (LINKED) {
         if (p.link.src_q == nullptr) return;
-        // Hand-off by the whole grid. Every thread's atomic adds are performed device-wide before its CTA counts
-        // itself out (fence, barrier, counter); when the counter reaches the grid size the block is final and
-        // every CTA copies its share of the rows into the downstream rank's array with peer stores. The grid is
-        // sized to be co-resident (occupancy x SMs) and the rank owns its device, so the counter barrier cannot
-        // starve; it is bounded by the same timeout as the other device-side waits anyway.
+        // Hand-off by the CTAs that leave last. Every thread's atomic adds are performed device-wide before its
+        // CTA counts itself out (fence, barrier, counter). A CTA whose ticket is not among the last kCopiers simply
+        // exits (its SM slots go to the next round's sampler, which runs on its own stream); the last kCopiers
+        // wait until the counter reaches the grid size -- the block is final then -- and copy one share each into
+        // the downstream rank's arrays with peer stores; the last copier publishes the arrive flag. The handful
+        // of waiting CTAs finish their own work within the same tail of the kernel, so the wait is short; it is
+        // bounded by the same timeout as the other device-side waits anyway.
+        constexpr unsigned kCopiers = 32;
+        __shared__ unsigned ticket_sh;
         __threadfence();
         __syncthreads();
+        if (threadIdx.x == 0) ticket_sh = atomicAdd(p.link.done, 1u);
+        __syncthreads();
+        const unsigned copiers = min(kCopiers, gridDim.x), first = gridDim.x - copiers;
+        if (ticket_sh < first) return;
         if (threadIdx.x == 0) {
-            atomicAdd(p.link.done, 1u);
             const long long t0 = clock64();
             while (ld_acquire_gpu((const int *)p.link.done) < (int)gridDim.x) {
-                __nanosleep(64);
+                __nanosleep(32);
                 if (clock64() - t0 > p.link.timeout_cycles) {
                     atomicCAS(p.link.error_flag, 0, (20 + p.link.site) * 1000000);
                     break;
@@ -299,15 +306,21 @@ mf_sgd_user_runs(const UserRunParams p) {
             }
         }
         __syncthreads();
-        const long long stride = (long long)gridDim.x * blockDim.x;
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.link.n_vec; i += stride)
-            p.link.dst_q[i] = __ldcg(p.link.src_q + i);
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.link.n_items; i += stride)
+        const long long share = ticket_sh - first, stride = (long long)copiers * blockDim.x;
+        for (long long i = share * blockDim.x + threadIdx.x; i < p.link.n_vec; i += 2 * stride) {
+            const bool two = i + stride < p.link.n_vec;
+            const float4 v0 = __ldcg(p.link.src_q + i);
+            float4 v1 = v0;
+            if (two) v1 = __ldcg(p.link.src_q + i + stride);
+            p.link.dst_q[i] = v0;
+            if (two) p.link.dst_q[i + stride] = v1;
+        }
+        for (long long i = share * blockDim.x + threadIdx.x; i < p.link.n_items; i += stride)
             p.link.dst_ib[i * p.ibs] = __ldcg(p.link.src_ib + i * p.ibs);
         __threadfence_system();
         __syncthreads();
         if (threadIdx.x == 0) {
-            if (atomicAdd(p.link.done + 1, 1u) == gridDim.x - 1) {  // last copier: publish, reset both counters
+            if (atomicAdd(p.link.done + 1, 1u) == copiers - 1) {  // last copier: publish, reset both counters
                 p.link.done[0] = 0u;
                 p.link.done[1] = 0u;
                 __threadfence_system();
