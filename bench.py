@@ -55,6 +55,10 @@ WORKLOADS = {
     # the same for 4 and 2 GPUs (the regime in which round 1's 4-GPU run diverged)
     "nfblock4": (480189, 4442, 25120000, True, 128),
     "nfblock2": (480189, 8885, 50240000, True, 128),
+    # one (user block, item block) cell at 8 / 4 GPUs: with CU2B_DSGD_ROUND = 64 / world this is the sub-epoch kernel
+    # of a real rank, launch for launch (users per rank, draws per run, item popularity of the block)
+    "nfcell8": (60024, 2221, 1570000, True, 128),
+    "nfcell4": (120047, 4442, 6280000, True, 128),
 }
 DATA_SEED = 20240607
 METRIC = "sgd_rating_updates_per_sec"

@@ -222,9 +222,12 @@ mf_sgd_user_runs(const UserRunParams p) {
     float4 *const Pv = reinterpret_cast<float4 *>(p.P);
     float4 *const Qv = reinterpret_cast<float4 *>(p.Q);
     // Warps claim kRunClaim consecutive tiles at a time; the next claim is issued one chunk ahead.
-    // (The SMs do not run at one speed; a static split leaves the fast ones idle at the end.)
-    constexpr int kRunClaim = 4;
+    // (The SMs do not run at one speed; a static split leaves the fast ones idle at the end.) A sub-epoch of a
+    // multi-GPU rank is short -- a few tiles per warp -- so there the claim is a single tile: with four, some warps
+    // ended up with twice the work of others (measured at 8 GPUs: 175 us per sub-epoch where the kernel's
+    // steady-state rate would need 120).
     const int n_tiles = (p.n_active + G - 1) / G;
+    const int kRunClaim = n_tiles < (int)((gridDim.x * blockDim.x) >> 5) * 32 ? 1 : 4;
     unsigned long long claim = 0;
     if (lane == 0) claim = atomicAdd(p.tile_counter, (unsigned long long)kRunClaim);
     for (;;) {
