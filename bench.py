@@ -73,6 +73,9 @@ def log(*a):
 # clocks sampling (B200_PROFILING.md recipe)
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock / power / throttle reasons DURING the timed region. NVML is polled from a thread every few
+    milliseconds (the timed region of a multi-GPU run lasts tens of milliseconds: `nvidia-smi -lms` would return
+    nothing); nvidia-smi is the fallback when the NVML binding is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -81,8 +84,21 @@ class ClockSampler:
         self.device = device
         self.proc = None
         self.lines = []
+        self.samples = []
+        self.nvml = None
+        self._stop = threading.Event()
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -92,11 +108,46 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [x for x in vis.split(",") if x.strip()]
+            if self.device < len(ids) and ids[self.device].strip().isdigit():
+                return int(ids[self.device])
+        return self.device
+
+    def _poll(self):
+        nv = self.nvml
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1e3
+                rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((sm, mx, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.004)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop.set()
+            self.t.join(timeout=1)
+            nv = self.nvml
+            names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            reasons = sorted(n for n, bit in names.items() if any(s[3] & bit for s in self.samples))
+            sm = [s[0] for s in self.samples]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": min(sm) if sm else None,
+                    "sm_max_mhz": max(s[1] for s in self.samples) if self.samples else None,
+                    "power_w_max": max(s[2] for s in self.samples) if self.samples else None, "samples": len(sm),
+                    "reasons": reasons, "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -117,7 +168,8 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons),
+                "source": "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------------------------

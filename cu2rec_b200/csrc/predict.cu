@@ -19,6 +19,13 @@
 //
 // Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2-5 and
 // 6-9 two epilogue groups, one per accumulator buffer (TMEM lane quadrant = warp % 4).
+//
+// Any n_factors: the factor rows are zero-padded on the device to whole 128-byte swizzle rows (k = 50, the
+// reference's default, config.h:27, runs as 64). Up to 128 factors the user tile stays resident in shared memory
+// for the whole sweep over the catalogue; beyond that (k = 300 of experiments/cu2rec.sh:10 runs as 320) user and
+// item tiles stream through a three-stage ring in chunks of 64 factors and the MMAs of all chunks accumulate into
+// the same TMEM tile. Any top-k: a pass yields the 16 best items of a user exactly; further passes with those
+// items added to the exclusion bitmap yield the next 16, and a final kernel orders the union.
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -114,10 +121,14 @@ struct PredictSmemCtl {
     uint64_t a_full, a_empty;
     uint64_t b_full[2], b_empty[2];
     uint64_t acc_full[2], acc_empty[2];
+    uint64_t st_full[3], st_empty[3];  // STREAM: ring of {user chunk, item chunk} stages
     uint32_t tmem_base;
     uint32_t pad;
     float ib[2][2][BN];  // [epilogue group][tile parity][column]
 };
+
+constexpr int CHUNK_SLABS = 2;   // STREAM: factors per stage = 64 (2 x 16 KB of users + 2 x 16 KB of items)
+constexpr int STREAM_STAGES = 3;
 
 struct PredictParams {
     int users, items, kslabs;
@@ -129,7 +140,7 @@ struct PredictParams {
     float *cand_scores;      // [users][2][KC] (TF32 scores incl. item bias; diagnostics)
 };
 
-template <int KC>
+template <int KC, bool STREAM>
 __global__ void __launch_bounds__(kThreadsPredict, 1)
 predict_candidates_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_q,
                           const PredictParams p) {
@@ -137,7 +148,10 @@ predict_candidates_kernel(const __grid_constant__ CUtensorMap map_p, const __gri
     uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // SW128 needs 1024-byte alignment
     uint8_t *smem_a = base;                                        // kslabs slabs
     uint8_t *smem_b = base + (size_t)p.kslabs * SLAB_BYTES;        // 2 stages x kslabs slabs
-    PredictSmemCtl *ctl = (PredictSmemCtl *)(smem_b + (size_t)2 * p.kslabs * SLAB_BYTES);
+    // STREAM: STREAM_STAGES stages of {CHUNK_SLABS user slabs, CHUNK_SLABS item slabs} from `base`
+    constexpr size_t kStageBytes = (size_t)2 * CHUNK_SLABS * SLAB_BYTES;
+    PredictSmemCtl *ctl = STREAM ? (PredictSmemCtl *)(base + STREAM_STAGES * kStageBytes)
+                                 : (PredictSmemCtl *)(smem_b + (size_t)2 * p.kslabs * SLAB_BYTES);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t slab_tx = (uint32_t)p.kslabs * SLAB_BYTES;
 
@@ -149,6 +163,10 @@ predict_candidates_kernel(const __grid_constant__ CUtensorMap map_p, const __gri
             bar_init(&ctl->b_empty[s], 1);
             bar_init(&ctl->acc_full[s], 1);
             bar_init(&ctl->acc_empty[s], 4);
+        }
+        for (int s = 0; s < STREAM_STAGES; ++s) {
+            bar_init(&ctl->st_full[s], 1);
+            bar_init(&ctl->st_empty[s], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -164,7 +182,23 @@ predict_candidates_kernel(const __grid_constant__ CUtensorMap map_p, const __gri
 
     if (warp == 0) {
         // ===== TMA producer =====
-        if (lane == 0) {
+        if (lane == 0 && STREAM) {
+            const int n_chunks = p.kslabs / CHUNK_SLABS;
+            int st = 0;  // global stage counter
+            for (int ut = blockIdx.x; ut < p.n_user_tiles; ut += gridDim.x)
+                for (int j = 0; j < p.n_item_tiles; ++j)
+                    for (int c = 0; c < n_chunks; ++c, ++st) {
+                        const int s = st % STREAM_STAGES;
+                        if (st >= STREAM_STAGES) bar_wait(&ctl->st_empty[s], ((st / STREAM_STAGES) - 1) & 1);
+                        uint8_t *stage = base + (size_t)s * kStageBytes;
+                        bar_expect(&ctl->st_full[s], (uint32_t)kStageBytes);
+                        for (int sl = 0; sl < CHUNK_SLABS; ++sl) {
+                            tma_load_2d(stage + (size_t)sl * SLAB_BYTES, &map_p, (c * CHUNK_SLABS + sl) * SLAB_K, ut * BM, &ctl->st_full[s]);
+                            tma_load_2d(stage + (size_t)(CHUNK_SLABS + sl) * SLAB_BYTES, &map_q, (c * CHUNK_SLABS + sl) * SLAB_K, j * BN,
+                                        &ctl->st_full[s]);
+                        }
+                    }
+        } else if (lane == 0) {
             int it = 0, n = 0;
             for (int ut = blockIdx.x; ut < p.n_user_tiles; ut += gridDim.x, ++n) {
                 if (n > 0) bar_wait(&ctl->a_empty, (n - 1) & 1);
@@ -183,7 +217,33 @@ predict_candidates_kernel(const __grid_constant__ CUtensorMap map_p, const __gri
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
+        if (lane == 0 && STREAM) {
+            const uint32_t idesc = umma_idesc_tf32(BM, BN);
+            const int n_chunks = p.kslabs / CHUNK_SLABS;
+            int st = 0, it = 0;
+            for (int ut = blockIdx.x; ut < p.n_user_tiles; ut += gridDim.x)
+                for (int j = 0; j < p.n_item_tiles; ++j, ++it) {
+                    const int b = it & 1;
+                    if (it >= 2) bar_wait(&ctl->acc_empty[b], ((it >> 1) - 1) & 1);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)b * BN;
+                    for (int c = 0; c < n_chunks; ++c, ++st) {
+                        const int s = st % STREAM_STAGES;
+                        bar_wait(&ctl->st_full[s], (st / STREAM_STAGES) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint8_t *stage = base + (size_t)s * kStageBytes;
+                        for (int sl = 0; sl < CHUNK_SLABS; ++sl) {
+                            const uint32_t a0 = s32(stage + (size_t)sl * SLAB_BYTES);
+                            const uint32_t b0 = s32(stage + (size_t)(CHUNK_SLABS + sl) * SLAB_BYTES);
+#pragma unroll
+                            for (int ks = 0; ks < SLAB_K / 8; ++ks)
+                                umma_tf32(d_tmem, umma_desc_sw128(a0 + ks * 32), umma_desc_sw128(b0 + ks * 32), idesc,
+                                          (uint32_t)((c | sl | ks) != 0));
+                        }
+                        umma_commit(&ctl->st_empty[s]);  // the stage may be refilled once these MMAs retire
+                    }
+                    umma_commit(&ctl->acc_full[b]);
+                }
+        } else if (lane == 0) {
             const uint32_t idesc = umma_idesc_tf32(BM, BN);
             int it = 0, n = 0;
             for (int ut = blockIdx.x; ut < p.n_user_tiles; ut += gridDim.x, ++n) {
@@ -319,12 +379,15 @@ rated_bitmap_kernel(const int *__restrict__ indptr, const int *__restrict__ indi
 }
 
 // Exact fp32 score of every candidate in the reference's op order (predict.cu:22-26), then the
-// final order: score descending, item ascending on ties. One warp per user, lane = candidate.
+// order inside this pass: score descending, item ascending on ties. One warp per user, lane = candidate.
+// The pass's best min(2 KC, 16) candidates go to slots [slot0, slot0 + 16) of the user's collected list; when
+// `bitmap` is given their bits are set so that the next pass looks past them. kp = row pitch (k padded).
 template <int KC>
 __global__ void __launch_bounds__(256)
 predict_rescore_kernel(const float *__restrict__ P, const float *__restrict__ Q, const float *__restrict__ user_bias,
-                       const float *__restrict__ item_bias, float mu, int k, int users,
-                       const int32_t *__restrict__ cand_items, int topk, int32_t *out_items, float *out_scores) {
+                       const float *__restrict__ item_bias, float mu, int k, int kp, int users,
+                       const int32_t *__restrict__ cand_items, int slot0, int slots, int32_t *out_items, float *out_scores,
+                       uint32_t *bitmap, int mask_pitch) {
     const int lane = threadIdx.x & 31;
     const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (u >= users) return;
@@ -332,17 +395,19 @@ predict_rescore_kernel(const float *__restrict__ P, const float *__restrict__ Q,
     int item = lane < 2 * KC ? cand_items[(size_t)u * 2 * KC + lane] : -1;
     float score = -INFINITY;
     if (item >= 0) {
-        // k is a multiple of 32 here: 128-bit loads, products still added one by one in ascending f
-        const float4 *pu = reinterpret_cast<const float4 *>(P + (size_t)u * k);
-        const float4 *qi = reinterpret_cast<const float4 *>(Q + (size_t)item * k);
+        // rows are padded with zeros to kp (a multiple of 32): 128-bit loads, products still added one by one in
+        // ascending f; the zero products past k leave the sum unchanged
+        const float4 *pu = reinterpret_cast<const float4 *>(P + (size_t)u * kp);
+        const float4 *qi = reinterpret_cast<const float4 *>(Q + (size_t)item * kp);
         float pred = __fadd_rn(__fadd_rn(mu, __ldg(user_bias + u)), __ldg(item_bias + item));
+        const int vec = (k + 3) >> 2;
 #pragma unroll 4
-        for (int f = 0; f < k / 4; ++f) {
+        for (int f = 0; f < vec; ++f) {
             const float4 a = __ldg(qi + f), b = __ldg(pu + f);
             pred = __fadd_rn(pred, __fmul_rn(a.x, b.x));
-            pred = __fadd_rn(pred, __fmul_rn(a.y, b.y));
-            pred = __fadd_rn(pred, __fmul_rn(a.z, b.z));
-            pred = __fadd_rn(pred, __fmul_rn(a.w, b.w));
+            if (4 * f + 1 < k) pred = __fadd_rn(pred, __fmul_rn(a.y, b.y));
+            if (4 * f + 2 < k) pred = __fadd_rn(pred, __fmul_rn(a.z, b.z));
+            if (4 * f + 3 < k) pred = __fadd_rn(pred, __fmul_rn(a.w, b.w));
         }
         score = pred;
     }
@@ -353,10 +418,47 @@ predict_rescore_kernel(const float *__restrict__ P, const float *__restrict__ Q,
         const int io = __shfl_sync(0xffffffffu, item, o);
         if (io >= 0 && (so > score || (so == score && io < item))) ++rank;
     }
-    if (item >= 0 && rank < topk) {
-        out_items[(size_t)u * topk + rank] = item;
-        out_scores[(size_t)u * topk + rank] = score;
+    if (item >= 0 && rank < 16) {
+        out_items[(size_t)u * slots + slot0 + rank] = item;
+        out_scores[(size_t)u * slots + slot0 + rank] = score;
+        if (bitmap) atomicOr(bitmap + (size_t)u * mask_pitch + (item >> 5), 1u << (item & 31));
     }
+}
+
+// Final order of a user's collected candidates (<= 128 slots from up to 8 passes): score descending, item
+// ascending on ties, the first topk go out. One warp per user, four slots per lane, rank by counting.
+__global__ void __launch_bounds__(256)
+predict_order_kernel(const int32_t *__restrict__ col_items, const float *__restrict__ col_scores, int slots, int users, int topk,
+                     int32_t *out_items, float *out_scores) {
+    const int lane = threadIdx.x & 31;
+    const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (u >= users) return;
+    int it[4];
+    float sc[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int sidx = q * 32 + lane;
+        it[q] = sidx < slots ? col_items[(size_t)u * slots + sidx] : -1;
+        sc[q] = sidx < slots ? col_scores[(size_t)u * slots + sidx] : -INFINITY;
+    }
+    int rank[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (q * 32 >= slots) break;
+        for (int o = 0; o < 32; ++o) {
+            const float so = __shfl_sync(0xffffffffu, sc[q], o);
+            const int io = __shfl_sync(0xffffffffu, it[q], o);
+#pragma unroll
+            for (int m = 0; m < 4; ++m)
+                if (io >= 0 && it[m] >= 0 && (so > sc[m] || (so == sc[m] && io < it[m]))) ++rank[m];
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+        if (it[m] >= 0 && rank[m] < topk) {
+            out_items[(size_t)u * topk + rank[m]] = it[m];
+            out_scores[(size_t)u * topk + rank[m]] = sc[m];
+        }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -386,30 +488,27 @@ struct DevBuf {
     template <typename T> T *as() { return (T *)p; }
 };
 
-template <int KC>
-cu2b_status run_predict(const CUtensorMap &mp, const CUtensorMap &mq, const PredictParams &pp, int sm_count,
-                        const float *P, const float *Q, const float *ub, const float *ib, float mu, int k, int topk,
-                        int32_t *out_items, float *out_scores, float *ms_candidates, float *ms_rescore) {
-    const size_t smem = (size_t)3 * pp.kslabs * SLAB_BYTES + sizeof(PredictSmemCtl) + 1024;
-    CUDA_TRY(cudaFuncSetAttribute(predict_candidates_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cudaEvent_t e0, e1, e2;
-    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
-    const int grid = std::max(1, std::min(pp.n_user_tiles, sm_count));
-    cudaEventRecord(e0);
-    predict_candidates_kernel<KC><<<grid, kThreadsPredict, smem>>>(mp, mq, pp);
-    cudaEventRecord(e1);
-    const int warps_per_cta = 8;
-    predict_rescore_kernel<KC><<<(pp.users + warps_per_cta - 1) / warps_per_cta, 256>>>(
-        P, Q, ub, ib, mu, k, pp.users, pp.cand_items, topk, out_items, out_scores);
-    cudaEventRecord(e2);
-    cudaError_t e = cudaDeviceSynchronize();
-    if (e == cudaSuccess) e = cudaGetLastError();
-    if (e == cudaSuccess) {
-        cudaEventElapsedTime(ms_candidates, e0, e1);
-        cudaEventElapsedTime(ms_rescore, e1, e2);
+// Row-major [rows x k] host matrix -> [rows x kp] device matrix, zero padded.
+cu2b_status upload_padded(DevBuf &buf, const float *src, int rows, int k, int kp) {
+    cu2b_status rc = buf.alloc((size_t)rows * kp * 4);
+    if (rc != CU2B_OK) return rc;
+    if (kp == k) {
+        CUDA_TRY(cudaMemcpy(buf.p, src, (size_t)rows * k * 4, cudaMemcpyHostToDevice));
+    } else {
+        CUDA_TRY(cudaMemset(buf.p, 0, (size_t)rows * kp * 4));
+        CUDA_TRY(cudaMemcpy2D(buf.p, (size_t)kp * 4, src, (size_t)k * 4, (size_t)k * 4, (size_t)rows, cudaMemcpyHostToDevice));
     }
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
-    if (e != cudaSuccess) return cu2b_fail(CU2B_ERR_CUDA, "predict kernels: %s", cudaGetErrorString(e));
+    return CU2B_OK;
+}
+
+template <bool STREAM>
+cu2b_status launch_candidates(const CUtensorMap &mp, const CUtensorMap &mq, const PredictParams &pp, int sm_count) {
+    const size_t smem = (STREAM ? (size_t)STREAM_STAGES * 2 * CHUNK_SLABS * SLAB_BYTES : (size_t)3 * pp.kslabs * SLAB_BYTES) +
+                        sizeof(PredictSmemCtl) + 1024;
+    CUDA_TRY(cudaFuncSetAttribute(predict_candidates_kernel<16, STREAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = std::max(1, std::min(pp.n_user_tiles, sm_count));
+    predict_candidates_kernel<16, STREAM><<<grid, kThreadsPredict, smem>>>(mp, mq, pp);
+    CUDA_TRY(cudaGetLastError());
     return CU2B_OK;
 }
 
@@ -421,37 +520,41 @@ extern "C" cu2b_status cu2b_predict_topk(const float *P, int rows, const float *
                                          double *ms_out) {
     if (!P || !Q || !user_bias || !item_bias || !out_items || !out_scores || rows < 1 || cols < 1 || topk < 1)
         return cu2b_fail(CU2B_ERR_INVALID, "cu2b_predict_topk: bad argument");
-    if (n_factors < 32 || n_factors > 128 || n_factors % 32)
-        return cu2b_fail(CU2B_ERR_UNSUPPORTED, "cu2b_predict_topk: n_factors must be 32, 64, 96 or 128 in this build (got %d)", n_factors);
-    if (topk > 16) return cu2b_fail(CU2B_ERR_UNSUPPORTED, "cu2b_predict_topk: topk <= 16 in this build (got %d)", topk);
+    if (n_factors < 1 || n_factors > 512)
+        return cu2b_fail(CU2B_ERR_UNSUPPORTED, "cu2b_predict_topk: n_factors must be in [1, 512] (got %d)", n_factors);
+    if (topk > 128) return cu2b_fail(CU2B_ERR_UNSUPPORTED, "cu2b_predict_topk: topk <= 128 (got %d)", topk);
     if (exclude && (exclude->on_device || exclude->rows > rows || exclude->cols > cols))
         return cu2b_fail(CU2B_ERR_INVALID, "cu2b_predict_topk: exclude matrix must be a host CSR within the model dimensions");
-    int dev = 0;
+    int dev = 0, cc_major = 0, sm_count = 0;
     CUDA_TRY(cudaGetDevice(&dev));
-    cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
-    if (prop.major != 10) return cu2b_fail(CU2B_ERR_CUDA, "cu2b_predict_topk needs an sm_100 device (tcgen05)");
+    CUDA_TRY(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    if (cc_major != 10) return cu2b_fail(CU2B_ERR_CUDA, "cu2b_predict_topk needs an sm_100 device (tcgen05)");
     EncodeTiledFn encode = nullptr;
     cudaDriverEntryPointQueryResult qres;
     CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void **)&encode, cudaEnableDefault, &qres));
     if (!encode || qres != cudaDriverEntryPointSuccess) return cu2b_fail(CU2B_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
 
     const int k = n_factors;
-    // per epilogue group; both groups together hand 2*kc candidates to the exact rescoring pass.
-    // A group sees every second item tile, so each list must be able to hold the whole top-k.
+    // factor rows padded to whole 128-byte swizzle rows; beyond 128 factors to whole 64-factor chunks (STREAM)
+    const bool stream = k > 128;
+    const int kp = stream ? ((k + 63) / 64) * 64 : ((k + 31) / 32) * 32;
+    // 16 candidates per epilogue group and pass; both groups together hand 32 candidates to the exact rescoring
+    // pass, whose 16 best are final. A group sees every second item tile, so each list can hold a pass's whole yield.
     const int kc = 16;
-    DevBuf dP, dQ, dub, dib, dcand_i, dcand_s, dout_i, dout_s, dmask, dptr, dind;
+    const int passes = (topk + 15) / 16, slots = passes * 16;
+    DevBuf dP, dQ, dub, dib, dcand_i, dcand_s, dcol_i, dcol_s, dout_i, dout_s, dmask, dptr, dind;
     cu2b_status rc;
-    if ((rc = dP.alloc((size_t)rows * k * 4)) || (rc = dQ.alloc((size_t)cols * k * 4)) || (rc = dub.alloc((size_t)rows * 4)) ||
+    if ((rc = upload_padded(dP, P, rows, k, kp)) || (rc = upload_padded(dQ, Q, cols, k, kp)) || (rc = dub.alloc((size_t)rows * 4)) ||
         (rc = dib.alloc((size_t)cols * 4)) || (rc = dcand_i.alloc((size_t)rows * 2 * kc * 4)) ||
-        (rc = dcand_s.alloc((size_t)rows * 2 * kc * 4)) || (rc = dout_i.alloc((size_t)rows * topk * 4)) ||
+        (rc = dcand_s.alloc((size_t)rows * 2 * kc * 4)) || (rc = dcol_i.alloc((size_t)rows * slots * 4)) ||
+        (rc = dcol_s.alloc((size_t)rows * slots * 4)) || (rc = dout_i.alloc((size_t)rows * topk * 4)) ||
         (rc = dout_s.alloc((size_t)rows * topk * 4)))
         return rc;
-    CUDA_TRY(cudaMemcpy(dP.p, P, (size_t)rows * k * 4, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(dQ.p, Q, (size_t)cols * k * 4, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(dub.p, user_bias, (size_t)rows * 4, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(dib.p, item_bias, (size_t)cols * 4, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemset(dout_i.p, 0xFF, (size_t)rows * topk * 4));  // item -1 = "no such candidate"
+    CUDA_TRY(cudaMemset(dcol_i.p, 0xFF, (size_t)rows * slots * 4));  // item -1 = "no such candidate"
+    CUDA_TRY(cudaMemset(dout_i.p, 0xFF, (size_t)rows * topk * 4));
     {
         std::vector<float> nanv((size_t)rows * topk, NAN);
         CUDA_TRY(cudaMemcpy(dout_s.p, nanv.data(), nanv.size() * 4, cudaMemcpyHostToDevice));
@@ -459,7 +562,7 @@ extern "C" cu2b_status cu2b_predict_topk(const float *P, int rows, const float *
     PredictParams pp;
     pp.users = rows;
     pp.items = cols;
-    pp.kslabs = k / SLAB_K;
+    pp.kslabs = kp / SLAB_K;
     pp.n_user_tiles = (rows + BM - 1) / BM;
     pp.n_item_tiles = (cols + BN - 1) / BN;
     pp.item_bias = dib.as<float>();
@@ -467,25 +570,60 @@ extern "C" cu2b_status cu2b_predict_topk(const float *P, int rows, const float *
     pp.mask_pitch = pp.n_item_tiles * 4;
     pp.cand_items = dcand_i.as<int32_t>();
     pp.cand_scores = dcand_s.as<float>();
-    if (exclude && exclude->nonzeros > 0) {
-        if ((rc = dmask.alloc((size_t)rows * pp.mask_pitch * 4)) || (rc = dptr.alloc(((size_t)exclude->rows + 1) * 4)) ||
-            (rc = dind.alloc((size_t)exclude->nonzeros * 4)))
-            return rc;
+    const bool have_exclude = exclude && exclude->nonzeros > 0;
+    if (have_exclude || passes > 1) {
+        if ((rc = dmask.alloc((size_t)rows * pp.mask_pitch * 4))) return rc;
         CUDA_TRY(cudaMemset(dmask.p, 0, (size_t)rows * pp.mask_pitch * 4));
+        pp.bitmap = dmask.as<uint32_t>();
+    }
+    if (have_exclude) {
+        if ((rc = dptr.alloc(((size_t)exclude->rows + 1) * 4)) || (rc = dind.alloc((size_t)exclude->nonzeros * 4))) return rc;
         CUDA_TRY(cudaMemcpy(dptr.p, exclude->indptr, ((size_t)exclude->rows + 1) * 4, cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(dind.p, exclude->indices, (size_t)exclude->nonzeros * 4, cudaMemcpyHostToDevice));
-        const int grid = (int)std::min<long long>(((long long)exclude->nonzeros + 255) / 256, (long long)prop.multiProcessorCount * 16);
+        const int grid = (int)std::min<long long>(((long long)exclude->nonzeros + 255) / 256, (long long)sm_count * 16);
         rated_bitmap_kernel<<<grid, 256>>>(dptr.as<int>(), dind.as<int>(), exclude->rows, exclude->nonzeros,
                                           dmask.as<uint32_t>(), pp.mask_pitch);
         CUDA_TRY(cudaGetLastError());
-        pp.bitmap = dmask.as<uint32_t>();
     }
     CUtensorMap mp, mq;
-    if ((rc = make_row_major_map(encode, &mp, dP.as<float>(), rows, k)) || (rc = make_row_major_map(encode, &mq, dQ.as<float>(), cols, k)))
+    if ((rc = make_row_major_map(encode, &mp, dP.as<float>(), rows, kp)) || (rc = make_row_major_map(encode, &mq, dQ.as<float>(), cols, kp)))
         return rc;
+    cudaEvent_t ev[3];
+    for (cudaEvent_t &e : ev) cudaEventCreate(&e);
     float ms_c = 0.f, ms_r = 0.f;
-    rc = run_predict<16>(mp, mq, pp, prop.multiProcessorCount, dP.as<float>(), dQ.as<float>(), dub.as<float>(), dib.as<float>(),
-                             global_bias, k, topk, dout_i.as<int32_t>(), dout_s.as<float>(), &ms_c, &ms_r);
+    const int warps_per_cta = 8, rescore_grid = (rows + warps_per_cta - 1) / warps_per_cta;
+    for (int pass = 0; pass < passes && rc == CU2B_OK; ++pass) {
+        cudaEventRecord(ev[0]);
+        rc = stream ? launch_candidates<true>(mp, mq, pp, sm_count) : launch_candidates<false>(mp, mq, pp, sm_count);
+        if (rc != CU2B_OK) break;
+        cudaEventRecord(ev[1]);
+        predict_rescore_kernel<16><<<rescore_grid, 256>>>(dP.as<float>(), dQ.as<float>(), dub.as<float>(), dib.as<float>(),
+                                                         global_bias, k, kp, rows, pp.cand_items, pass * 16, slots,
+                                                         dcol_i.as<int32_t>(), dcol_s.as<float>(),
+                                                         passes > 1 ? dmask.as<uint32_t>() : nullptr, pp.mask_pitch);
+        cudaEventRecord(ev[2]);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) { rc = cu2b_fail(CU2B_ERR_CUDA, "predict kernels: %s", cudaGetErrorString(e)); break; }
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, ev[0], ev[1]);
+        cudaEventElapsedTime(&b, ev[1], ev[2]);
+        ms_c += a;
+        ms_r += b;
+    }
+    if (rc == CU2B_OK) {
+        cudaEventRecord(ev[0]);
+        predict_order_kernel<<<rescore_grid, 256>>>(dcol_i.as<int32_t>(), dcol_s.as<float>(), slots, rows, topk,
+                                                   dout_i.as<int32_t>(), dout_s.as<float>());
+        cudaEventRecord(ev[1]);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) rc = cu2b_fail(CU2B_ERR_CUDA, "predict order kernel: %s", cudaGetErrorString(e));
+        float a = 0.f;
+        cudaEventElapsedTime(&a, ev[0], ev[1]);
+        ms_r += a;
+    }
+    for (cudaEvent_t &e : ev) cudaEventDestroy(e);
     if (rc != CU2B_OK) return rc;
     CUDA_TRY(cudaMemcpy(out_items, dout_i.p, (size_t)rows * topk * 4, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(out_scores, dout_s.p, (size_t)rows * topk * 4, cudaMemcpyDeviceToHost));

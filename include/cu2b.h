@@ -308,8 +308,10 @@ void cu2b_dsgd_destroy(cu2b_dsgd *d);
  * mu + b_u + b_i + p_u.q_i among the items NOT present in `exclude` (may be NULL). Candidate
  * generation runs on the tensor cores (tcgen05, TF32); the returned scores are exact fp32 in the
  * reference's summation order and the order is (score descending, item ascending). Slots that
- * cannot be filled hold item -1 / score NaN. n_factors in {32,64,96,128}, topk <= 16 in this
- * build. ms_out (optional) receives {candidate kernel ms, rescore kernel ms}.
+ * cannot be filled hold item -1 / score NaN. n_factors in [1, 512] (rows are zero-padded on the device
+ * to whole 128-byte rows; the reference's default 50, config.h:27, and the 300 of
+ * experiments/cu2rec.sh:10 included), topk <= 128 (16 per pass over the catalogue). ms_out (optional)
+ * receives {candidate kernels ms, rescore + ordering kernels ms}.
  * ---------------------------------------------------------------------------------- */
 cu2b_status cu2b_predict_topk(const float *P, int rows, const float *Q, int cols, const float *user_bias,
                               const float *item_bias, float global_bias, int n_factors,

@@ -70,6 +70,21 @@ def test_mf_cli_end_to_end_and_outputs_feed_reference_predict(tmp_path):
     assert {3, 10, 40}.isdisjoint({int(r[1]) for r in recs})
     est = [float(r[2]) for r in recs]
     assert est == sorted(est, reverse=True)
+    # extension: every user of the trained model at once through the tcgen05 batched predict
+    allu = subprocess.run([PREDICT, "-c", str(tmp_path / "c.cfg"), "-i", str(tmp_path / "train_f8_item_bias.csv"), "-g",
+                           str(tmp_path / "train_f8_global_bias.csv"), "-q", str(tmp_path / "train_f8_q.csv"), "-p",
+                           str(tmp_path / "train_f8_p.csv"), "-u", str(tmp_path / "train_f8_user_bias.csv"), "-k", "5", "-x",
+                           str(tmp_path / "train.csv")], capture_output=True, text=True)
+    assert allu.returncode == 0, allu.stderr
+    rows = re.findall(r"^User: (\d+)\tRank: (\d+)\tItem: (\d+)\tEstimated rating: (-?[0-9.]+)$", allu.stdout, re.M)
+    assert len(rows) == U * 5 and [int(r[1]) for r in rows[:5]] == [1, 2, 3, 4, 5]
+    seen = set(zip(tr["user"].tolist(), tr["item"].tolist()))
+    assert not any((int(u), int(i)) in seen for u, _, i, _ in rows)
+    Pm, Qm = np.loadtxt(tmp_path / "train_f8_p.csv", delimiter=",", dtype=np.float32), np.loadtxt(tmp_path / "train_f8_q.csv", delimiter=",", dtype=np.float32)
+    ubm, ibm = np.loadtxt(tmp_path / "train_f8_user_bias.csv", dtype=np.float32), np.loadtxt(tmp_path / "train_f8_item_bias.csv", dtype=np.float32)
+    ex = cu.createSparseMatrix(tr, U, I)
+    want_i, _ = O.predict_topk(Pm, Qm, ubm, ibm, np.float32(gb), 5, exclude=(ex.indptr, ex.indices))
+    assert [int(r[2]) for r in rows] == want_i.ravel().tolist()
     if O.ref_binary("predict"):
         ref = subprocess.run([O.ref_binary("predict"), *args], capture_output=True, text=True)
         assert ref.returncode == 0 and "Recommendations:" in ref.stdout, ref.stderr[-300:]

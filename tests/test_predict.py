@@ -15,7 +15,13 @@ def _model(rng, U, I, k):
 
 
 @pytest.mark.parametrize("U,I,k,topk", [(300, 500, 32, 5), (1000, 1777, 64, 10), (777, 2000, 128, 10), (130, 127, 96, 3),
-                                        (257, 4000, 128, 16)])
+                                        (257, 4000, 128, 16),
+                                        # the reference's own factor counts (config.h:27 default 50; experiments/cu2rec.sh:10
+                                        # {50, 300}) and odd ones: rows are zero-padded to whole swizzle rows, k > 128 streams
+                                        (500, 900, 50, 10), (300, 1500, 300, 10), (200, 700, 1, 4), (200, 700, 7, 8),
+                                        (260, 1300, 130, 12), (140, 600, 512, 6),
+                                        # more than 16 per user: further passes over the catalogue, final order kernel
+                                        (300, 2500, 64, 20), (260, 3000, 128, 64), (150, 2100, 300, 40), (90, 1000, 50, 128)])
 def test_topk_matches_brute_force(U, I, k, topk):
     """Items and their order equal the CPU brute force (exact fp32 scores in the reference's op
     order, ties by item id); scores are bit-identical."""
@@ -52,9 +58,18 @@ def test_topk_without_exclusion_and_short_catalogue():
 
 def test_topk_rejects_unsupported_shapes():
     rng = np.random.RandomState(4)
-    P, Q, ub, ib = _model(rng, 10, 10, 50)
+    P, Q, ub, ib = _model(rng, 10, 10, 516)
     with pytest.raises(cu._lib.Cu2bError):
         cu.predict_topk(P, Q, ub, ib, 3.0, 5)
     P, Q, ub, ib = _model(rng, 10, 10, 64)
     with pytest.raises(cu._lib.Cu2bError):
-        cu.predict_topk(P, Q, ub, ib, 3.0, 17)
+        cu.predict_topk(P, Q, ub, ib, 3.0, 129)
+
+
+def test_topk_longer_than_the_catalogue_is_padded():
+    rng = np.random.RandomState(5)
+    P, Q, ub, ib = _model(rng, 70, 30, 50)
+    items, scores, _ = cu.predict_topk(P, Q, ub, ib, 3.0, 40)
+    want_i, want_s = O.predict_topk(P, Q, ub, ib, 3.0, 40)
+    assert np.array_equal(items, want_i) and (items[:, 30:] == -1).all() and np.isnan(scores[:, 30:]).all()
+    assert np.array_equal(scores[:, :30].view(np.uint32), want_s[:, :30].view(np.uint32))
