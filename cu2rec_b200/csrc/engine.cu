@@ -715,6 +715,7 @@ struct cu2b_session {
     std::vector<unsigned long long> item_w;
     int item_w_stride = 1;
     unsigned long long *item_w_dev = nullptr;
+    int *bad_ids = nullptr;  // device counter of item ids outside [0, cols) (check_item_ids_kernel)
     int *active = nullptr;
     int n_active = 0;
     int *user_ids = nullptr;  // DSGD: original user id of each local user (sampler key), else null
@@ -811,7 +812,7 @@ permute_rows_kernel(float *__restrict__ Q, float *__restrict__ stage, const int 
 // of item i per iteration under per-user sampling (one uniform draw per user per iteration, sgd.cu:27-37) in units
 // of 2^-32. Integer atomics => exact, order independent, identical to the host version (item_draw_weights_host).
 __global__ void __launch_bounds__(256)
-item_draw_weight_kernel(const int *__restrict__ indptr, const int *__restrict__ indices, int rows, int user_stride,
+item_draw_weight_kernel(const int *__restrict__ indptr, const int *__restrict__ indices, int rows, int cols, int user_stride,
                         unsigned long long *__restrict__ w) {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -820,8 +821,20 @@ item_draw_weight_kernel(const int *__restrict__ indptr, const int *__restrict__ 
         const int lo = __ldg(indptr + u), hi = __ldg(indptr + u + 1);
         if (hi <= lo) continue;
         const unsigned long long share = 0x100000000ULL / (unsigned long long)(hi - lo);
-        for (int j = lo + lane; j < hi; j += 32) atomicAdd(w + __ldg(indices + j), share);
+        for (int j = lo + lane; j < hi; j += 32) {
+            const int item = __ldg(indices + j);
+            if ((unsigned)item < (unsigned)cols) atomicAdd(w + item, share);  // out-of-range ids are reported by check_item_ids_kernel
+        }
     }
+}
+// Every item id of a rating matrix must lie in [0, cols): the kernels index Q and item_bias with them. One pass
+// over the ids on the device (60 us for 90 M ratings); *bad counts the offenders.
+__global__ void __launch_bounds__(256)
+check_item_ids_kernel(const int *__restrict__ indices, long long nnz, int cols, int *bad) {
+    int mine = 0;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < nnz; j += (long long)gridDim.x * blockDim.x)
+        mine += (unsigned)__ldg(indices + j) >= (unsigned)cols;
+    if (mine) atomicAdd(bad, mine);
 }
 
 int item_bias_stride() {
@@ -1192,8 +1205,13 @@ static cu2b_status session_upload(cu2b_session *s, const cu2b_csr *train, const 
     // users with at least one training rating (sgd.cu:35 skips the others)
     std::vector<int> active;
     active.reserve(s->rows);
-    for (int u = 0; u < s->rows; ++u)
+    bool monotone = indptr_host[0] == 0 && indptr_host[s->rows] == train->nonzeros;
+    for (int u = 0; u < s->rows; ++u) {
+        monotone = monotone && indptr_host[u + 1] >= indptr_host[u];
         if (indptr_host[u + 1] > indptr_host[u]) active.push_back(u);
+    }
+    if (!monotone)
+        return cu2b_fail(CU2B_ERR_INVALID, "train matrix: indptr must start at 0, never decrease and end at nonzeros (%d)", train->nonzeros);
     if (reload && (int)active.size() != s->n_active)
         return cu2b_fail(CU2B_ERR_INVALID, "reload: %d users have training ratings, the session was created with %d "
                          "(launch geometry depends on it)", (int)active.size(), s->n_active);
@@ -1209,6 +1227,7 @@ static cu2b_status session_upload(cu2b_session *s, const cu2b_csr *train, const 
         CU2B_TRY(s->pool.alloc(&s->ub, (size_t)s->rows));
         CU2B_TRY(alloc_item_bias(s));
         CU2B_TRY(s->pool.alloc(&s->item_w_dev, (size_t)std::max(1, s->cols)));
+        CU2B_TRY(s->pool.alloc(&s->bad_ids, (size_t)1));
         if (s->want_placement) {
             CU2B_TRY(s->pool.alloc(&s->item_pos, (size_t)std::max(1, s->cols)));
             CU2B_TRY(s->pool.alloc(&s->Q_stage, (size_t)std::max(1, s->cols) * s->k));
@@ -1227,10 +1246,14 @@ static cu2b_status session_upload(cu2b_session *s, const cu2b_csr *train, const 
         // DSGD strips derive per-item step fractions from the weights: every user (== cu2b_dsgd_item_keep)
         s->item_w_stride = s->dsgd_child ? 1 : (int)std::max<long long>(1, (long long)train->nonzeros >> 24);
         CUDA_TRY(cudaMemsetAsync(s->item_w_dev, 0, (size_t)std::max(1, s->cols) * sizeof(unsigned long long), s->stream));
+        CUDA_TRY(cudaMemsetAsync(s->bad_ids, 0, sizeof(int), s->stream));
         if (train->nonzeros > 0) {
             const int warps = (s->rows + s->item_w_stride - 1) / s->item_w_stride;
             item_draw_weight_kernel<<<std::max(1, std::min((warps + 7) / 8, s->sm_count * 8)), 256, 0, s->stream>>>(
-                s->train.indptr, ids, s->rows, s->item_w_stride, s->item_w_dev);
+                s->train.indptr, ids, s->rows, s->cols, s->item_w_stride, s->item_w_dev);
+            CUDA_TRY(cudaGetLastError());
+            check_item_ids_kernel<<<std::max(1, std::min((train->nonzeros + 255) / 256, s->sm_count * 8)), 256, 0, s->stream>>>(
+                ids, (long long)train->nonzeros, s->cols, s->bad_ids);
             CUDA_TRY(cudaGetLastError());
         }
     }
@@ -1247,7 +1270,12 @@ static cu2b_status session_upload(cu2b_session *s, const cu2b_csr *train, const 
     s->item_w.assign((size_t)s->cols, 0ULL);
     if (s->cols > 0)
         CUDA_TRY(cudaMemcpyAsync(s->item_w.data(), s->item_w_dev, (size_t)s->cols * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+    int bad_host = 0;
+    CUDA_TRY(cudaMemcpyAsync(&bad_host, s->bad_ids, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (bad_host)
+        return cu2b_fail(CU2B_ERR_INVALID, "train matrix: %d item ids lie outside [0, %d) (a ratings file with itemId 0 "
+                         "or ids beyond the declared column count?)", bad_host, s->cols);
     if (s->item_pos && !reload) {
         std::vector<int> order((size_t)s->cols), slot((size_t)s->cols), pos((size_t)s->cols);
         for (int i = 0; i < s->cols; ++i) order[i] = i;
@@ -1268,6 +1296,15 @@ static cu2b_status session_upload(cu2b_session *s, const cu2b_csr *train, const 
         CUDA_TRY(cudaGetLastError());
     }
     CU2B_TRY(scatter_item_bias(s, s->stream));
+    if (test->nonzeros > 0) {
+        check_item_ids_kernel<<<std::max(1, std::min((test->nonzeros + 255) / 256, s->sm_count * 8)), 256, 0, s->stream>>>(
+            up_test.tmp_i ? up_test.tmp_i : test->indices, (long long)test->nonzeros, s->cols, s->bad_ids);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(&bad_host, s->bad_ids, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        if (bad_host)
+            return cu2b_fail(CU2B_ERR_INVALID, "test matrix: %d item ids lie outside [0, %d)", bad_host, s->cols);
+    }
     CU2B_TRY(matrix_expand(s->pool, s->stream, up_test, s->item_pos));
     return CU2B_OK;
 }

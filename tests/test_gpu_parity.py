@@ -633,3 +633,47 @@ def test_config4_deterministic_mode_full_netflix_shape_is_reproducible():
     assert np.array_equal(a["Q"].view(np.uint32), b["Q"].view(np.uint32))
     assert [r["train_rmse"] for r in a["log"]] == [r["train_rmse"] for r in b["log"]]
     assert np.isfinite(a["log"][-1]["train_rmse"]) and a["log"][-1]["train_rmse"] < a["log"][0]["train_rmse"]
+
+
+@pytest.mark.gpu
+def test_session_from_device_resident_csr_and_invalid_item_ids():
+    """cu2b_csr.on_device = 1 (matrix.h:11-19: the reference's CudaCSRMatrix IS device resident): the draw weights that
+    feed the stability bound are computed on the device either way, and the session trains like the host-CSR one.
+    Item ids outside [0, cols) are rejected before any kernel indexes Q with them."""
+    import ctypes as C
+    import torch
+    tr, te = cu.synth_ratings(3000, 400, 120000, rank=4, noise=0.3, seed=2)
+    U, I, k = 3000, 400, 16
+    mtr, mte = cu.createSparseMatrix(tr, U, I), cu.createSparseMatrix(te, U, I)
+    mu = np.float32(tr["rating"].astype(np.float64).mean())
+    init = lambda n: cu.initialize_normal_array(n, k)
+    P, Q, ub, ib = init(U * k), init(I * k), init(U), init(I)
+    cfg = cu.Config(total_iterations=120, n_factors=k, check_error=40)
+    with cu.Session(mtr, mte, cfg, P, Q, ub, ib, mu) as s:
+        s.run(120)
+        host_log = s.log()
+
+    class DevCsr(cu.CSRMatrix):
+        def c(self):
+            m = super().c()
+            self._keep = [torch.from_numpy(a).cuda() for a in (self.indptr, self.indices, self.data)]
+            m.indptr, m.indices, m.data = (C.c_void_p(t.data_ptr()) for t in self._keep)
+            m.on_device = 1
+            return m
+    dtr = DevCsr(U, I, mtr.indptr, mtr.indices, mtr.data)
+    dte = DevCsr(U, I, mte.indptr, mte.indices, mte.data)
+    with cu.Session(dtr, dte, cfg, P, Q, ub, ib, mu) as s:
+        s.run(120)
+        dev_log = s.log()
+    assert [r["iteration"] for r in dev_log] == [r["iteration"] for r in host_log]
+    for a, b in zip(dev_log, host_log):
+        assert abs(a["test_rmse"] - b["test_rmse"]) / b["test_rmse"] < 0.005
+    bad = cu.CSRMatrix(U, I, mtr.indptr, mtr.indices.copy(), mtr.data)
+    bad.indices[1234] = I  # one past the catalogue
+    with pytest.raises(cu._lib.Cu2bError) as err:
+        cu.Session(bad, mte, cfg, P, Q, ub, ib, mu)
+    assert err.value.status == 1 and "item ids" in str(err.value)
+    neg = cu.CSRMatrix(U, I, mtr.indptr, mtr.indices.copy(), mtr.data)
+    neg.indices[7] = -1  # itemId 0 in a 1-based ratings file
+    with pytest.raises(cu._lib.Cu2bError):
+        cu.Session(neg, mte, cfg, P, Q, ub, ib, mu)
