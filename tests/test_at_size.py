@@ -172,6 +172,16 @@ def test_bin_mf_matches_the_reference_cpu_binary_on_a_movielens_small_shape(tmp_
     iterations (the bundled file itself is not redistributable and /root/reference does
     not exist on the GPU box). mf_cpu seeds from std::random_device: its own run-to-run spread is ~0.1 %."""
     tr, te = cu.synth_ratings(610, 9724, 100836, rank=8, noise=0.4, integer_ratings=False, test_fraction=0.2, seed=11)
+    # mf_sequential.cu:111 draws from the INCLUSIVE range [low, high]: with probability 1 / (degree + 1) per iteration
+    # the last user reads one element past the rating arrays and the reference dies on what it finds there. Give the
+    # last user 4 000 more ratings so that a 1000-iteration run usually survives (O.run_mf_cpu retries the rest).
+    rng = np.random.RandomState(11)
+    last = tr[tr["user"] == 609]
+    extra_items = np.setdiff1d(np.arange(9724), np.concatenate([last["item"], te[te["user"] == 609]["item"]]))[:4000]
+    extra = np.zeros(len(extra_items), dtype=cu.RATING_DTYPE)
+    extra["user"], extra["item"], extra["rating"] = 609, extra_items, rng.randint(1, 11, len(extra_items)) * 0.5
+    tr = np.concatenate([tr, extra])
+    tr = tr[np.lexsort((tr["item"], tr["user"]))]
     _write_csv(tmp_path / "train.csv", tr)
     _write_csv(tmp_path / "test.csv", te)
     (tmp_path / "c.cfg").write_text("0 1000 32 0.01 42 0.02 0.02 0.02 0.02")
