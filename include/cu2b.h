@@ -233,11 +233,11 @@ cu2b_status cu2b_session_stats(cu2b_session *s, cu2b_stats *out, int reset);
  * already owns, and resets the schedule state (learning rate, patience, log, iteration counter,
  * statistics) to the configuration the session was created with. A repeated train() on
  * same-shaped data (hyper-parameter sweeps, retraining on a refreshed snapshot) then pays the
- * host->device copies but no allocation or set-up. Hogwild mode only. The launch geometry,
- * including the bound on concurrently applied updates that keeps asynchronous SGD stable (it
- * depends on the most popular item's share of the draws and on the learning rate), is fixed at
- * creation: reload data whose item popularity is markedly more concentrated, or a larger learning
- * rate, into a NEW session instead. */
+ * host->device copies but no allocation or set-up. Hogwild mode only. The item draw weights are recomputed
+ * on the device from the reloaded matrix and the bound on concurrently applied updates that keeps
+ * asynchronous SGD stable (it depends on the most popular item's share of the draws and on the learning
+ * rate) is re-derived from them, as are a DSGD rank's per-item step fractions; only the internal item
+ * placement (a performance heuristic) stays the one chosen at creation. */
 cu2b_status cu2b_session_reload(cu2b_session *s, const cu2b_csr *train, const cu2b_csr *test,
                                 const float *P, const float *Q, const float *user_bias,
                                 const float *item_bias, float global_bias);
@@ -263,8 +263,8 @@ cu2b_status cu2b_dsgd_extract_strip(const cu2b_rating *ratings, int64_t n, const
                                     const int *user_local, const int *item_new, int rank,
                                     cu2b_rating *out, int64_t *n_out);
 
-/* Host only. Item-step thinning fractions (experimental, opt-in through the environment variable
- * CU2B_DSGD_THIN=<budget> read by cu2b_dsgd_create): keep[i] in (0, 1] such that
+/* Host only. Item-step thinning fractions (a DSGD rank applies them to the bias steps of the
+ * popular items by default, CU2B_DSGD_THIN_BIAS, and to the row steps on request, CU2B_DSGD_THIN): keep[i] in (0, 1] such that
  * lr x (item i's share of the draws of its item block under per-user sampling) x groups_in_flight x
  * keep[i] <= budget. Items under the budget keep 1. item_block_ptr == NULL: one block. */
 cu2b_status cu2b_dsgd_item_keep(const cu2b_csr *train_strip, const int *item_block_ptr, int world,

@@ -677,3 +677,19 @@ def test_session_from_device_resident_csr_and_invalid_item_ids():
     neg.indices[7] = -1  # itemId 0 in a 1-based ratings file
     with pytest.raises(cu._lib.Cu2bError):
         cu.Session(neg, mte, cfg, P, Q, ub, ib, mu)
+
+
+@pytest.mark.gpu
+def test_release_cache_returns_the_pooled_device_memory():
+    """Sessions allocate from a memory pool the library owns and keeps warm between calls (the reference
+    cudaMallocs per call, matrix.cu:12-40); cu2b_release_cache hands it back to the driver."""
+    tr, te = cu.synth_ratings(20000, 2000, 1000000, rank=4, noise=0.3, seed=6)
+    U, I, k = 20000, 2000, 128
+    mtr, mte = cu.createSparseMatrix(tr, U, I), cu.createSparseMatrix(te, U, I)
+    init = lambda n: cu.initialize_normal_array(n, k)
+    cfg = cu.Config(total_iterations=2, n_factors=k, check_error=2)
+    with cu.Session(mtr, mte, cfg, init(U * k), init(I * k), init(U), init(I), 3.5) as s:
+        s.run(2)
+    held = cu.device_info()["free_bytes"]
+    cu._lib.check(cu._lib.load().cu2b_release_cache())
+    assert cu.device_info()["free_bytes"] >= held + (8 << 20)  # P alone is 10 MB
