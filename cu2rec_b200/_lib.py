@@ -64,6 +64,7 @@ SYMBOLS = {
     "cu2b_residuals": (C.c_int, [C.POINTER(Csr), _P, _P, _P, _P, C.c_float, C.c_int, _P]),
     "cu2b_error_metrics": (C.c_int, [_P, C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "cu2b_sample_per_user": (C.c_int, [C.POINTER(Csr), C.c_int, C.c_int, C.c_int, _P, C.POINTER(C.c_int64)]),
+    "cu2b_sample_per_rating": (C.c_int, [C.POINTER(Csr), C.c_int, C.c_int64, C.c_int64, _P]),
     "cu2b_sgd_apply": (C.c_int, [_P, C.c_int64, _P, C.c_int, _P, C.c_int, _P, _P, C.c_float, C.POINTER(Config), C.c_int]),
     "cu2b_sgd_blocked": (C.c_int, [_P, C.c_int64, _P, C.c_int, _P, C.c_int, _P, _P, C.c_float, C.POINTER(Config), C.c_int, C.c_int]),
     "cu2b_block_schedule_order": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, C.c_int, _P, C.POINTER(C.c_int)]),

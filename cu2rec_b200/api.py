@@ -214,6 +214,14 @@ def sample_per_user(matrix, seed, iter0, n_iter):
     return out
 
 
+def sample_per_rating(matrix, seed, first_update, n_updates):
+    """per_rating sampler: updates [first_update, first_update + n_updates) of a run (shuffled passes over the ratings)."""
+    m = matrix.c()
+    out = np.empty(n_updates, dtype=RATING_DTYPE)
+    check(_lib.load().cu2b_sample_per_rating(C.byref(m), seed, first_update, n_updates, _ptr(out)))
+    return out
+
+
 def sgd_apply(stream, P, Q, user_bias, item_bias, global_bias, cfg, order=0):
     """sgd.cu:40-72 arithmetic over an explicit stream; returns updated copies."""
     stream = np.ascontiguousarray(stream, dtype=RATING_DTYPE)

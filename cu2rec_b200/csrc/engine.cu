@@ -1108,11 +1108,18 @@ cu2b_status enqueue_sgd_iterations(cu2b_session *s, int iter_abs, int n_seg) {
     if (s->round_iters > 1) return enqueue_tiled_iterations(s, iter_abs, n_seg);
     while (n_seg > 0) {
         const int nb = std::min(n_seg, s->max_batch_segs);
-        // 1. sampler: one draw per active user per iteration (sgd.cu:27-37)
+        // 1. sampler: one draw per active user per iteration (sgd.cu:27-37), or the next n_active ratings of a
+        //    shuffled pass over the rating list (per_rating)
         {
             const int id = s->timing.begin(Timing::SAMPLER, s->stream);
             const long long draws = (long long)nb * s->n_active;
             const int grid = (int)std::min<long long>((draws + 255) / 256, (long long)s->sm_count * 16);
+            if (s->cfg.sampler == CU2B_SAMPLER_PER_RATING)
+                sample_per_rating_kernel<<<grid, 256, 0, s->stream>>>(
+                    s->train.coo, (unsigned long long)s->train.nnz, feistel_half_bits((unsigned long long)s->train.nnz),
+                    (uint32_t)s->cfg.seed, (unsigned long long)iter_abs * (unsigned long long)s->n_active, draws, s->n_active,
+                    s->stream_buf, s->seg_pitch);
+            else
             sample_per_user_kernel<<<grid, 256, 0, s->stream>>>(
                 s->train.indptr, s->train.coo, s->active, s->n_active, (uint32_t)s->cfg.seed, iter_abs,
                 draws, s->stream_buf, s->seg_pitch, s->user_ids);
@@ -1130,7 +1137,9 @@ cu2b_status enqueue_sgd_iterations(cu2b_session *s, int iter_abs, int n_seg) {
             sv.chunk = s->chunk;
             sv.chunks_per_seg = s->chunks_per_seg;
             sv.num_chunks = (long long)nb * s->chunks_per_seg;
-            CU2B_TRY(launch_sgd(s, sv, s->gate, s->segs_done, 0));
+            // per_rating: a user may appear anywhere in any segment, so the per-user ordering gate (chunk j of
+            // iteration t after chunk j of iteration t - 1) means nothing; both rows take their steps as L2 atomic adds
+            CU2B_TRY(launch_sgd(s, sv, s->cfg.sampler == CU2B_SAMPLER_PER_RATING ? nullptr : s->gate, s->segs_done, 0));
             s->timing.end(id, s->stream);
         }
         s->segs_done += nb;
@@ -1326,8 +1335,10 @@ static cu2b_status session_create_impl(cu2b_session **out, int device, const cu2
     if (cfg->check_error < 1) return cu2b_fail(CU2B_ERR_INVALID, "check_error must be >= 1");
     if (cfg->mode != CU2B_MODE_HOGWILD && cfg->mode != CU2B_MODE_DETERMINISTIC)
         return cu2b_fail(CU2B_ERR_INVALID, "unknown mode %d", cfg->mode);
-    if (cfg->sampler != CU2B_SAMPLER_PER_USER)
-        return cu2b_fail(CU2B_ERR_UNSUPPORTED, "sampler=per_rating is not available in this build");
+    if (cfg->sampler != CU2B_SAMPLER_PER_USER && cfg->sampler != CU2B_SAMPLER_PER_RATING)
+        return cu2b_fail(CU2B_ERR_INVALID, "unknown sampler %d", cfg->sampler);
+    if (cfg->sampler == CU2B_SAMPLER_PER_RATING && !alloc_stream)
+        return cu2b_fail(CU2B_ERR_UNSUPPORTED, "sampler=per_rating is a single-GPU schedule (DSGD draws per user)");
     CUDA_TRY(cudaSetDevice(device));
     CU2B_TRY(check_device());
     cu2b_session *s = new cu2b_session();
@@ -1378,7 +1389,7 @@ static cu2b_status session_create_impl(cu2b_session **out, int device, const cu2
     const long long cap_ratings = 48LL << 20;  // <= 576 MB of triplets per batch
     s->max_batch_segs = (int)std::max<long long>(1, std::min<long long>(cap_ratings / std::max<long long>(1, s->seg_pitch), 4096));
     s->round_iters = 1;
-    if (alloc_stream && cfg->mode == CU2B_MODE_HOGWILD && cfg->round_iters > 1) {
+    if (alloc_stream && cfg->mode == CU2B_MODE_HOGWILD && cfg->round_iters > 1 && cfg->sampler == CU2B_SAMPLER_PER_USER) {
         const char *pipe = getenv("CU2B_TILE_PIPE");
         s->fused_sampler = !(pipe && strcmp(pipe, "tma") == 0);
         const int per_user_max = s->fused_sampler ? kRoundDrawsPerWarp / (32 / s->L)
@@ -1807,6 +1818,28 @@ extern "C" cu2b_status cu2b_sample_per_user(const cu2b_csr *m, int seed, int ite
                                                  iter0, draws, out_dev, (long long)active.size(), nullptr);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpy(out, out_dev, (size_t)draws * sizeof(cu2b_rating), cudaMemcpyDeviceToHost));
+    return CU2B_OK;
+}
+
+extern "C" cu2b_status cu2b_sample_per_rating(const cu2b_csr *m, int seed, int64_t first_update, int64_t n_updates,
+                                              cu2b_rating *out) {
+    CU2B_TRY(validate_csr(m, "cu2b_sample_per_rating"));
+    if (first_update < 0 || n_updates < 0 || (!out && n_updates > 0) || m->nonzeros <= 0)
+        return cu2b_fail(CU2B_ERR_INVALID, "cu2b_sample_per_rating: bad argument");
+    CU2B_TRY(check_device());
+    if (n_updates == 0) return CU2B_OK;
+    DevPool pool;
+    cudaStream_t st = 0;
+    DevMatrix dm;
+    CU2B_TRY(upload_matrix(pool, st, m, &dm, nullptr));
+    cu2b_rating *out_dev;
+    CU2B_TRY(pool.alloc(&out_dev, (size_t)n_updates));
+    const int grid = (int)std::min<long long>((n_updates + 255) / 256, 148 * 16);
+    sample_per_rating_kernel<<<grid, 256, 0, st>>>(dm.coo, (unsigned long long)m->nonzeros, feistel_half_bits((unsigned long long)m->nonzeros),
+                                                   (uint32_t)seed, (unsigned long long)first_update, (long long)n_updates,
+                                                   (int)std::min<int64_t>(n_updates, INT32_MAX), out_dev, (long long)n_updates);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(out, out_dev, (size_t)n_updates * sizeof(cu2b_rating), cudaMemcpyDeviceToHost));
     return CU2B_OK;
 }
 

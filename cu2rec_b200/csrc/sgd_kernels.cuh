@@ -102,6 +102,62 @@ sample_per_user_kernel(const int *__restrict__ indptr, const cu2b_rating *__rest
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// per_rating sampler (CU2B_SAMPLER_PER_RATING; no reference counterpart -- the reference only samples per
+// user, sgd.cu:27-37): the update stream is a shuffled pass over the rating list. Update number q of a
+// run (q = iteration x active users + position) applies rating perm_e(q mod nnz) of pass e = q / nnz,
+// perm_e a keyed bijection of [0, nnz): a 4-round Feistel network on 2h bits (2^(2h) >= nnz) with cycle
+// walking, round function = one Philox-style multiply-xor keyed by (seed, pass, round). Integer only,
+// so the CPU oracle (orc_rating_permutation) reproduces it bit for bit.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t feistel_round(uint32_t x, uint32_t key) {
+    uint32_t v = (x ^ key) * 0x9E3779B1u;
+    v ^= v >> 15;
+    v *= 0x85EBCA77u;
+    v ^= v >> 13;
+    return v;
+}
+__host__ __device__ __forceinline__ unsigned long long rating_permutation(unsigned long long j, unsigned long long n, int half_bits,
+                                                                          uint32_t seed, uint32_t pass) {
+    const uint32_t mask = half_bits >= 32 ? 0xffffffffu : ((1u << half_bits) - 1u);
+    unsigned long long x = j;
+    do {
+        uint32_t l = (uint32_t)(x >> half_bits) & mask, r = (uint32_t)x & mask;
+#pragma unroll
+        for (uint32_t round = 0; round < 4; ++round) {
+            const uint32_t t = l ^ (feistel_round(r, seed ^ (pass * 0x632BE5ABu) ^ (round * 0xB5297A4Du + 0x68E31DA4u)) & mask);
+            l = r;
+            r = t;
+        }
+        x = ((unsigned long long)l << half_bits) | r;
+    } while (x >= n);  // cycle walking: a bijection of [0, 2^(2h)) restricted to [0, n) stays a bijection
+    return x;
+}
+__host__ __device__ __forceinline__ int feistel_half_bits(unsigned long long n) {
+    int bits = 1;
+    while (bits < 64 && (1ULL << bits) < n) ++bits;
+    return (bits + 1) / 2;
+}
+
+// Thread i writes update q0 + i of the run to segment (i / seg_len) of the update stream.
+__global__ void __launch_bounds__(256)
+sample_per_rating_kernel(const cu2b_rating *__restrict__ coo, unsigned long long nnz, int half_bits, uint32_t seed,
+                         unsigned long long q0, long long n_draws, int seg_len, cu2b_rating *__restrict__ out,
+                         long long seg_pitch) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n_draws; i += stride) {
+        const unsigned long long q = q0 + (unsigned long long)i;
+        const unsigned long long r = rating_permutation(q % nnz, nnz, half_bits, seed, (uint32_t)(q / nnz));
+        cu2b_rating v;
+        v.user = __ldg(&coo[r].user);
+        v.item = __ldg(&coo[r].item);
+        v.rating = __ldg(&coo[r].rating);
+        const long long t = i / seg_len;
+        out[t * seg_pitch + (i - t * seg_len)] = v;
+    }
+}
+
 // One SGD step of a row element, learning rate folded in:
 //   lr * (err * other - reg * self)  ==  fma(a, other, -(c * self)),  a = lr * err, c = lr * reg
 // (mf_sequential.cu:134-137 / sgd.cu:55-61). The row then takes self + step with ONE rounding,

@@ -69,8 +69,11 @@ typedef struct cu2b_config {
     /* extensions */
     int mode;     /* CU2B_MODE_*: Hogwild (default) or deterministic conflict-free blocks */
     int sampler;  /* CU2B_SAMPLER_*: per_user = the reference's one-rating-per-user-per-
-                     iteration distribution (sgd.cu:27-37, default); per_rating = shuffled
-                     pass over the rating list */
+                     iteration distribution (sgd.cu:27-37, default; the parity mode); per_rating =
+                     shuffled passes over the rating list, an iteration still being one update per
+                     active user (single GPU, iteration-synchronous kernel; it converges to a LOWER
+                     test RMSE than the reference's distribution at equal updates -- SURVEY 7.1 --
+                     so it is offered, not compared two-sidedly) */
     int n_blocks; /* deterministic mode: B of the BxB block grid, 0 = automatic */
     int n_gpus;   /* DSGD width, 0/1 = single GPU */
     int round_iters; /* Hogwild schedule on one GPU: this many consecutive iterations of a user are
@@ -157,6 +160,11 @@ cu2b_status cu2b_error_metrics(const float *err, int64_t n, float *mae, float *r
  * rating per user that has any, ascending user order. out must hold n_iter * (active users). */
 cu2b_status cu2b_sample_per_user(const cu2b_csr *m, int seed, int iter0, int n_iter,
                                  cu2b_rating *out, int64_t *n_out);
+/* The per_rating sampler's stream (CU2B_SAMPLER_PER_RATING; no reference counterpart): updates
+ * [first_update, first_update + n_updates) of a run = a shuffled pass over the rating list, pass after pass
+ * (update q applies rating perm_e(q mod nnz) of pass e = q / nnz; perm_e is a keyed bijection of [0, nnz)). */
+cu2b_status cu2b_sample_per_rating(const cu2b_csr *m, int seed, int64_t first_update, int64_t n_updates,
+                                   cu2b_rating *out);
 /* sgd.cu:40-72 update arithmetic (in place Q / item_bias as mf_sequential.cu:114-141) applied
  * to an explicit stream of ratings. order: 0 = Hogwild (parallel, racy by design),
  * 1 = strictly sequential in stream order (one update in flight; for bit-exact checks). */

@@ -448,6 +448,52 @@ long orc_sample_per_user(int rows, const int *indptr, const int *indices, const 
 }
 
 // ---------------------------------------------------------------------------------------
+// per_rating sampler (an extension of ours; the reference only samples per user, sgd.cu:27-37): update q of a run
+// applies rating perm_e(q mod nnz) of pass e = q / nnz, perm_e a 4-round Feistel network on 2h bits with cycle
+// walking. Restated here from the definition in include/cu2b.h / sgd_kernels.cuh so that the tests can compare
+// the CUDA stream with an independent evaluation.
+// ---------------------------------------------------------------------------------------
+static inline uint32_t orc_feistel_round(uint32_t x, uint32_t key) {
+    uint32_t v = (x ^ key) * 0x9E3779B1u;
+    v ^= v >> 15;
+    v *= 0x85EBCA77u;
+    v ^= v >> 13;
+    return v;
+}
+unsigned long long orc_rating_permutation(unsigned long long j, unsigned long long n, uint32_t seed, uint32_t pass) {
+    int bits = 1;
+    while (bits < 64 && (1ULL << bits) < n) ++bits;
+    const int h = (bits + 1) / 2;
+    const uint32_t mask = h >= 32 ? 0xffffffffu : ((1u << h) - 1u);
+    unsigned long long x = j;
+    do {
+        uint32_t l = (uint32_t)(x >> h) & mask, r = (uint32_t)x & mask;
+        for (uint32_t round = 0; round < 4; ++round) {
+            const uint32_t t = l ^ (orc_feistel_round(r, seed ^ (pass * 0x632BE5ABu) ^ (round * 0xB5297A4Du + 0x68E31DA4u)) & mask);
+            l = r;
+            r = t;
+        }
+        x = ((unsigned long long)l << h) | r;
+    } while (x >= n);
+    return x;
+}
+// triplets (CSR order) of updates [first, first + count)
+void orc_sample_per_rating(int rows, const int *indptr, const int *indices, const float *data, int seed, long long first,
+                           long long count, orc_triplet *out) {
+    const unsigned long long n = (unsigned long long)indptr[rows];
+    std::vector<int> user_of((size_t)n);
+    for (int u = 0; u < rows; ++u)
+        for (int j = indptr[u]; j < indptr[u + 1]; ++j) user_of[j] = u;
+    for (long long i = 0; i < count; ++i) {
+        const unsigned long long q = (unsigned long long)(first + i);
+        const unsigned long long r = orc_rating_permutation(q % n, n, (uint32_t)seed, (uint32_t)(q / n));
+        out[i].user = user_of[r];
+        out[i].item = indices[r];
+        out[i].rating = data[r];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Whole training loop. Update loop: mf_sequential.cu:102-143 (one sampled rating per user per
 // iteration, Q / item_bias in place). Check cadence: training.cu:118 == mf_sequential.cu:146.
 // Patience / learning-rate decay: training.cu:103,129,146-155 (only when use_decay != 0;

@@ -151,6 +151,13 @@ def sample_per_user(indptr, indices, data, seed, iter0, n_iter):
     return out
 
 
+def sample_per_rating(indptr, indices, data, seed, first, count):
+    out = np.empty(count, dtype=TRIPLET)
+    lib().orc_sample_per_rating(indptr.shape[0] - 1, _p(indptr), _p(indices), _p(data), seed, C.c_longlong(first),
+                                C.c_longlong(count), _p(out))
+    return out
+
+
 def train(tr, te, P, Q, ub, ib, mu, h, seed, total_iterations, check_error=500, patience=2.0, lr_decay=0.2,
           use_decay=True, flavour=FLAVOUR_REF, iter0=0):
     """tr / te = (indptr, indices, data). Arrays are updated in place (copies returned)."""

@@ -693,3 +693,34 @@ def test_release_cache_returns_the_pooled_device_memory():
     held = cu.device_info()["free_bytes"]
     cu._lib.check(cu._lib.load().cu2b_release_cache())
     assert cu.device_info()["free_bytes"] >= held + (8 << 20)  # P alone is 10 MB
+
+
+@pytest.mark.gpu
+def test_per_rating_sampler_stream_and_training():
+    """CU2B_SAMPLER_PER_RATING (no reference counterpart; SURVEY 7 hard part 1): the update stream is a shuffled pass
+    over the rating list, bit-identical to the oracle's evaluation of the same keyed permutation; training with it
+    applies the same number of updates per iteration and is not worse than the reference's per-user distribution
+    (it converges lower, which is why parity is claimed with per_user only)."""
+    tr, te = cu.synth_ratings(3000, 500, 100000, rank=4, noise=0.3, seed=9)
+    U, I, k = 3000, 500, 32
+    mtr, mte = cu.createSparseMatrix(tr, U, I), cu.createSparseMatrix(te, U, I)
+    n = mtr.nonzeros
+    first, count = n // 3, 2 * n + 1234          # starts inside pass 0, ends inside pass 2
+    got = cu.sample_per_rating(mtr, 42, first, count)
+    want = O.sample_per_rating(mtr.indptr, mtr.indices, mtr.data, 42, first, count)
+    for f in ("user", "item", "rating"):
+        assert np.array_equal(got[f], want[f]), f
+    one_pass = cu.sample_per_rating(mtr, 42, n, n)  # exactly pass 1: every rating once
+    key = lambda a: np.sort(a["user"].astype(np.int64) * I + a["item"])
+    assert np.array_equal(key(one_pass), key(np.array(tr, dtype=cu.RATING_DTYPE)))
+    mu = np.float32(tr["rating"].astype(np.float64).mean())
+    per_user = cu.train(mtr, mte, cu.Config(total_iterations=300, n_factors=k, check_error=100), mu)
+    per_rating = cu.train(mtr, mte, cu.Config(total_iterations=300, n_factors=k, check_error=100, sampler=cu.api.SAMPLER_PER_RATING), mu)
+    assert per_rating["stats"]["updates"] == per_user["stats"]["updates"] == 300 * U
+    a, b = per_rating["log"][-1]["test_rmse"], per_user["log"][-1]["test_rmse"]
+    assert np.isfinite(a) and a <= b * 1.005, (a, b)
+    part = cu.dsgd_partition(tr, U, I, 1)
+    init = lambda m: cu.initialize_normal_array(m, k)
+    inp = cu.dsgd_rank_inputs(tr, te, U, I, part, 0, init(U * k), init(I * k), init(U), init(I))
+    with pytest.raises(cu._lib.Cu2bError):
+        cu.Dsgd(0, 1, inp, part, cu.Config(total_iterations=10, n_factors=k, sampler=cu.api.SAMPLER_PER_RATING), mu)
