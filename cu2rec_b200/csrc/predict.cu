@@ -306,12 +306,14 @@ predict_candidates_kernel(const __grid_constant__ CUtensorMap map_p, const __gri
                     const uint32_t live = (valid >= 32 ? 0xffffffffu : valid <= 0 ? 0u : ((1u << valid) - 1u)) & ~mword;
                     // cheap unrolled pass: add the item bias, mark the columns that beat the current
                     // KC-th best score. After the first few tiles almost no column does.
+                    // Three instructions per column: the bias add, thr - score (negative <=> the column beats the
+                    // threshold) and a funnel shift that collects the sign bits (column 31 first, so column c ends up in bit c).
                     const float thr = cs[KC - 1];
                     uint32_t hits = 0;
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) {
+                    for (int c = 31; c >= 0; --c) {
                         v[c] += ibs[ch * 32 + c];
-                        hits |= (uint32_t)(v[c] > thr) << c;
+                        hits = __funnelshift_l(__float_as_uint(thr - v[c]), hits, 1);
                     }
                     hits &= live;
                     // rare path, kept out of the unrolled code (it exists once, not 128 times)
