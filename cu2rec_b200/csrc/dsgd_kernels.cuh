@@ -186,6 +186,7 @@ struct UserRunParams {
     const int *row_off;   // [n_active][world + 1]
     const int *active_users;
     int n_active, pitch, world, block;
+    int claim;            // tiles per claim; 0 = by strip length
     unsigned long long *tile_counter;  // dynamic tile claims (a tile = the G users of one warp); zeroed before launch
     float *P, *Q, *user_bias, *item_bias;
     int kp, ibs;
@@ -222,12 +223,13 @@ mf_sgd_user_runs(const UserRunParams p) {
     float4 *const Pv = reinterpret_cast<float4 *>(p.P);
     float4 *const Qv = reinterpret_cast<float4 *>(p.Q);
     // Warps claim kRunClaim consecutive tiles at a time; the next claim is issued one chunk ahead.
-    // (The SMs do not run at one speed; a static split leaves the fast ones idle at the end.) A sub-epoch of a
-    // multi-GPU rank is short -- a few tiles per warp -- so there the claim is a single tile: with four, some warps
-    // ended up with twice the work of others (measured at 8 GPUs: 175 us per sub-epoch where the kernel's
-    // steady-state rate would need 120).
+    // (The SMs do not run at one speed; a static split leaves the fast ones idle at the end.) Four tiles per claim
+    // also on the short strips of a multi-GPU rank: single-tile claims balance the warps better on paper, but the
+    // claim counter is ONE address and same-address atomics retire at ~0.5 G/s, so 60 k claims per 170 us sub-epoch
+    // made the counter the bottleneck (8 GPUs, same box: 17.9 G updates/s with four tiles per claim, 16.4 with one;
+    // profiles/r2c_bench_n8_*.json). CU2B_DSGD_CLAIM overrides for experiments.
     const int n_tiles = (p.n_active + G - 1) / G;
-    const int kRunClaim = n_tiles < (int)((gridDim.x * blockDim.x) >> 5) * 32 ? 1 : 4;
+    const int kRunClaim = p.claim > 0 ? p.claim : 4;
     unsigned long long claim = 0;
     if (lane == 0) claim = atomicAdd(p.tile_counter, (unsigned long long)kRunClaim);
     for (;;) {
