@@ -43,12 +43,14 @@ __device__ __forceinline__ int item_block_of(int item, const int *sh_ptr, int wo
 }
 
 // A sampled draw inside a user's run: the user is implied by the row. With item-step thinning
-// (opt-in, see dsgd_sample_runs_kernel) bit 31 of `item` marks a draw whose item ROW step is
+// (see dsgd_sample_runs_kernel) bit 31 of `item` marks a draw whose item ROW step is
 // skipped and bit 30 one whose item BIAS step is skipped; item ids are < 2^30 then.
 struct __align__(8) DsgdDraw {
     int item;
     float rating;
 };
+constexpr int kClaimStride = 64;   // claim counters 512 bytes apart: atomics on one L2 line serialise
+constexpr int kClaimRanges = 64;
 constexpr int kDrawsPerLane = 8;  // dsgd_sample_runs_kernel keeps a round's draws in registers: rounds of <= 256 iterations
 constexpr int kDrawRowFrozen = (int)0x80000000u;
 constexpr int kDrawBiasFrozen = 0x40000000;
@@ -68,7 +70,7 @@ __device__ __forceinline__ DsgdDraw ld_draw_pinned(const DsgdDraw *p) {
 // inside a block (ballot ranking => deterministic). row_off[a*(world+1)+b] = start of block b
 // inside row a. In sub-epoch b the update kernel walks exactly run [row_off[b], row_off[b+1]).
 //
-// keep_row / keep_bias (optional, opt-in: CU2B_DSGD_THIN / CU2B_DSGD_THIN_BIAS): keep[i] in (0, 1] is the
+// keep_bias (default for DSGD ranks, CU2B_DSGD_THIN_BIAS) / keep_row (opt-in, CU2B_DSGD_THIN): keep[i] in (0, 1] is the
 // fraction of item i's draws whose item ROW step / item BIAS step is applied; a draw that skips one is
 // flagged with kDrawRowFrozen / kDrawBiasFrozen (the user side always moves). The decision is the second
 // Philox word of the draw's own counter compared with keep[item], so it is a pure function of (seed, user,
@@ -186,7 +188,7 @@ struct UserRunParams {
     const int *row_off;   // [n_active][world + 1]
     const int *active_users;
     int n_active, pitch, world, block;
-    int claim;            // tiles per claim; 0 = by strip length
+    int claim, n_ranges;  // tiles per claim; claim counters (one per contiguous range of users, kClaimStride apart)
     unsigned long long *tile_counter;  // dynamic tile claims (a tile = the G users of one warp); zeroed before launch
     float *P, *Q, *user_bias, *item_bias;
     int kp, ibs;
@@ -200,7 +202,7 @@ struct UserRunParams {
 // THIN: the draws may carry kDrawRowFrozen / kDrawBiasFrozen (item-step thinning); the default
 // instantiation does not look at the bits. LINKED: fused wait + sub-epoch + hand-off (SubEpochLink).
 template <int L, int V, bool THIN = false, bool LINKED = false>
-__global__ void __launch_bounds__(256, (V == 1 ? (LINKED ? 6 : 8) : 4))
+__global__ void __launch_bounds__(256, (V == 1 ? 5 : 4))
 mf_sgd_user_runs(const UserRunParams p) {
     constexpr int G = 32 / L;
     const int lane = threadIdx.x & 31, g = lane / L, l = lane % L;
@@ -222,21 +224,33 @@ mf_sgd_user_runs(const UserRunParams p) {
     const StepCoef sc = step_coef(lr, p.P_reg, p.Q_reg, p.ub_reg, p.ib_reg);
     float4 *const Pv = reinterpret_cast<float4 *>(p.P);
     float4 *const Qv = reinterpret_cast<float4 *>(p.Q);
-    // Warps claim kRunClaim consecutive tiles at a time; the next claim is issued one chunk ahead.
-    // (The SMs do not run at one speed; a static split leaves the fast ones idle at the end.) Four tiles per claim
-    // also on the short strips of a multi-GPU rank: single-tile claims balance the warps better on paper, but the
-    // claim counter is ONE address and same-address atomics retire at ~0.5 G/s, so 60 k claims per 170 us sub-epoch
-    // made the counter the bottleneck (8 GPUs, same box: 17.9 G updates/s with four tiles per claim, 16.4 with one;
-    // profiles/r2c_bench_n8_*.json). CU2B_DSGD_CLAIM overrides for experiments.
+    // Dynamic tile claims (the SMs do not run at one speed; a static split leaves the fast ones idle at the end).
+    // The users are cut into n_ranges contiguous ranges with one claim counter each, 512 bytes apart; a warp claims
+    // `claim` tiles at a time from its home range (the next claim is issued one chunk ahead) and, when a range is
+    // used up, moves on to the next one. Why not one counter: a sub-epoch of a multi-GPU rank is short (a few tiles
+    // per warp), so the claims should be small to balance the warps, but small claims on ONE address cost: atomics
+    // on one L2 line retire at ~0.5 G/s (profiles/r2_l2_roofline.md), and at 8 GPUs single-tile claims on one
+    // counter ran at 16.4 G updates/s against 17.9 with four tiles per claim (profiles/r2c_bench_n8_*.json).
+    // Several counters take the pressure off: 16 ranges x 2 tiles per claim is the measured best (18.3; r2d_*).
+    // n_ranges = 1 is the single-counter scheme.
     const int n_tiles = (p.n_active + G - 1) / G;
-    const int kRunClaim = p.claim > 0 ? p.claim : 4;
+    const int n_ranges = max(1, p.n_ranges), claim_sz = max(1, p.claim);
+    const int range_len = (n_tiles + n_ranges - 1) / n_ranges;
+    int range = (int)((((unsigned)blockIdx.x * blockDim.x + threadIdx.x) >> 5) % (unsigned)n_ranges), ranges_tried = 0;
     unsigned long long claim = 0;
-    if (lane == 0) claim = atomicAdd(p.tile_counter, (unsigned long long)kRunClaim);
+    if (lane == 0) claim = atomicAdd(p.tile_counter + (size_t)range * kClaimStride, (unsigned long long)claim_sz);
     for (;;) {
-        const long long t0 = (long long)__shfl_sync(0xffffffffu, claim, 0);
-        if (t0 >= n_tiles) break;
-        if (lane == 0) claim = atomicAdd(p.tile_counter, (unsigned long long)kRunClaim);
-        const int t1 = (int)min((long long)n_tiles, t0 + kRunClaim);
+        const long long t = (long long)__shfl_sync(0xffffffffu, claim, 0);
+        const int base = range * range_len;
+        const int lim = min(range_len, n_tiles - base);  // tiles in this range (<= 0 for trailing empty ranges)
+        if (t >= lim) {                                  // range used up: try the next one, give up after a full circle
+            if (++ranges_tried >= n_ranges) break;
+            range = range + 1 == n_ranges ? 0 : range + 1;
+            if (lane == 0) claim = atomicAdd(p.tile_counter + (size_t)range * kClaimStride, (unsigned long long)claim_sz);
+            continue;
+        }
+        if (lane == 0) claim = atomicAdd(p.tile_counter + (size_t)range * kClaimStride, (unsigned long long)claim_sz);
+        const int t0 = base + (int)t, t1 = base + (int)min((long long)lim, t + claim_sz);
     for (int tile = (int)t0; tile < t1; ++tile) {
         const int a0 = tile * G;
         const int a = a0 + g;
