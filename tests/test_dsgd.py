@@ -408,3 +408,23 @@ def test_train_entry_point_rejects_more_gpus_than_the_box_has():
     cfg = cu.Config(total_iterations=4, n_factors=8, check_error=2, n_gpus=64)
     with pytest.raises(cu._lib.Cu2bError):
         cu.train(mtr, mte, cfg, 3.5)
+
+
+def test_partition_places_one_popular_row_per_l2_block():
+    """Row placement inside an item block (cu2b_paired_slots): the two 512-byte rows of a 1 KB block share one
+    pair of L2 slices, so the popular half of a block's items sits on the even matrix rows in popularity order and the
+    other half on the odd rows -- every slice pair holds exactly one popular row, block weights fall along the range."""
+    tr, te, U, I = _problem(U=3000, I=401, n=120000)
+    counts = np.bincount(tr["item"], minlength=I)
+    for world in (1, 3, 4):
+        part = cu.dsgd_partition(tr, U, I, world)
+        inv = np.empty(I, np.int64)
+        inv[part.item_new] = np.arange(I)          # matrix row -> original item
+        for b in range(world):
+            r0, r1 = int(part.item_block_ptr[b]), int(part.item_block_ptr[b + 1])
+            rows = np.arange(r0, r1)
+            c = counts[inv[rows]]
+            even, odd = c[rows % 2 == 0], c[rows % 2 == 1]
+            assert np.all(np.diff(even) <= 0), "popular rows in popularity order on the even rows"
+            assert np.all(np.diff(odd) <= 0)
+            assert even.min() >= odd.max(), "every even row is at least as popular as every odd row"
