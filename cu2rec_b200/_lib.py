@@ -73,6 +73,7 @@ SYMBOLS = {
     "cu2b_session_create": (C.c_int, [C.POINTER(_P), C.c_int, C.POINTER(Csr), C.POINTER(Csr), C.POINTER(Config),
                                       _P, _P, _P, _P, C.c_float]),
     "cu2b_session_run": (C.c_int, [_P, C.c_int]),
+    "cu2b_session_run_download": (C.c_int, [_P, C.c_int, _P, _P, _P, _P]),
     "cu2b_session_reload": (C.c_int, [_P, C.POINTER(Csr), C.POINTER(Csr), _P, _P, _P, _P, C.c_float]),
     "cu2b_dsgd_reload": (C.c_int, [_P, C.POINTER(Csr), C.POINTER(Csr), _P, _P, _P, _P, C.c_float]),
     "cu2b_session_eval": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),

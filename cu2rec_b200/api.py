@@ -307,6 +307,15 @@ class Session:
     def run(self, n_iterations):
         check(self.lib.cu2b_session_run(self.h, n_iterations))
 
+    def run_download(self, n_iterations, out=None):
+        """run() + download() as one call: the model's D2H overlaps the run's last loss check. -> (P, Q, user_bias, item_bias)"""
+        if out is None:
+            out = (np.empty((self.rows, self.k), dtype=np.float32), np.empty((self.cols, self.k), dtype=np.float32),
+                   np.empty(self.rows, dtype=np.float32), np.empty(self.cols, dtype=np.float32))
+        P, Q, ub, ib = out
+        check(self.lib.cu2b_session_run_download(self.h, n_iterations, _ptr(P), _ptr(Q), _ptr(ub), _ptr(ib)))
+        return P, Q, ub, ib
+
     def reload(self, train_matrix, test_matrix, P, Q, user_bias, item_bias, global_bias):
         """Start over on same-shaped data with a new initial model (cu2b_session_reload)."""
         P, Q, ub, ib = _f32(P), _f32(Q), _f32(user_bias), _f32(item_bias)

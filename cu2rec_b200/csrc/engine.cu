@@ -710,6 +710,8 @@ struct cu2b_session {
     int *item_pos = nullptr;
     float *Q_stage = nullptr;  // [cols x k] dense staging for the permuting upload / download of Q
     bool want_placement = false;
+    cudaStream_t out_stream = nullptr;  // cu2b_session_run_download: the model leaves while the last loss check runs
+    cudaEvent_t ev_model_final = nullptr;
     // expected draws per iteration of every item (external ids), units of 2^-32 (item_draw_weight_kernel),
     // from every item_w_stride-th user; refreshed by every upload (create and reload)
     std::vector<unsigned long long> item_w;
@@ -774,6 +776,8 @@ struct cu2b_session {
             cudaStreamDestroy(stream);
         }
         if (sampler_stream) cudaStreamDestroy(sampler_stream);
+        if (out_stream) { cudaStreamSynchronize(out_stream); cudaStreamDestroy(out_stream); }
+        if (ev_model_final) cudaEventDestroy(ev_model_final);
         for (int b = 0; b < 2; ++b) {
             if (ev_sampled[b]) cudaEventDestroy(ev_sampled[b]);
             if (ev_consumed[b]) cudaEventDestroy(ev_consumed[b]);
@@ -864,13 +868,13 @@ cu2b_status scatter_item_bias(cu2b_session *s, cudaStream_t st) {
     return CU2B_OK;
 }
 
-cu2b_status download_item_bias(cu2b_session *s, float *host) {
+cu2b_status download_item_bias(cu2b_session *s, float *host, cudaStream_t st) {
     if (s->cols == 0) return CU2B_OK;
     if (s->ibs != 1 || s->item_pos) {
-        bias_gather_kernel<<<std::max(1, std::min((s->cols + 255) / 256, 592)), 256, 0, s->stream>>>(s->ib, s->ib_dense, s->cols, s->ibs, s->item_pos);
+        bias_gather_kernel<<<std::max(1, std::min((s->cols + 255) / 256, 592)), 256, 0, st>>>(s->ib, s->ib_dense, s->cols, s->ibs, s->item_pos);
         CUDA_TRY(cudaGetLastError());
     }
-    CUDA_TRY(cudaMemcpyAsync(host, s->ib_dense, (size_t)s->cols * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(host, s->ib_dense, (size_t)s->cols * sizeof(float), cudaMemcpyDeviceToHost, st));
     return CU2B_OK;
 }
 
@@ -1474,10 +1478,39 @@ extern "C" cu2b_status cu2b_session_create(cu2b_session **out, int device, const
     return session_create_impl(out, device, train, test, cfg, P, Q, user_bias, item_bias, global_bias, true);
 }
 
-extern "C" cu2b_status cu2b_session_run(cu2b_session *s, int n_iterations) {
+namespace {
+struct ModelOut {
+    float *P, *Q, *user_bias, *item_bias;
+};
+
+// D2H of the model (each part optional) on stream st; Q and item_bias come back in the caller's item order.
+cu2b_status enqueue_download(cu2b_session *s, cudaStream_t st, const ModelOut &o) {
+    if (o.P) CU2B_TRY(download_dense(st, o.P, s->P, s->rows, s->k, s->kp));
+    if (o.Q && s->item_pos && s->cols > 0) {
+        const long long total = (long long)s->cols * s->kp;
+        permute_rows_kernel<<<(int)std::max<long long>(1, std::min<long long>((total + 255) / 256, s->sm_count * 8LL)), 256, 0, st>>>(
+            s->Q, s->Q_stage, s->item_pos, s->cols, s->k, s->kp, 0);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(o.Q, s->Q_stage, (size_t)s->cols * s->k * sizeof(float), cudaMemcpyDeviceToHost, st));
+    } else if (o.Q) {
+        CU2B_TRY(download_dense(st, o.Q, s->Q, s->cols, s->k, s->kp));
+    }
+    if (o.user_bias) CUDA_TRY(cudaMemcpyAsync(o.user_bias, s->ub, (size_t)s->rows * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (o.item_bias) CU2B_TRY(download_item_bias(s, o.item_bias, st));
+    return CU2B_OK;
+}
+
+// The loop of training.cu:107-170, enqueued as a whole. out != nullptr: the model is also downloaded; when the call
+// ends with a loss check (it does whenever it reaches total_iterations, training.cu:118) the D2H copies run on a
+// second stream WHILE that check evaluates the final model -- the check only reads it.
+cu2b_status session_run_impl(cu2b_session *s, int n_iterations, const ModelOut *out) {
     if (!s || n_iterations < 0) return cu2b_fail(CU2B_ERR_INVALID, "cu2b_session_run: bad argument");
     if (s->dsgd_child) return cu2b_fail(CU2B_ERR_INVALID, "this session belongs to a DSGD context; use cu2b_dsgd_run");
     CUDA_TRY(cudaSetDevice(s->device));
+    if (out && !s->out_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&s->out_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&s->ev_model_final, cudaEventDisableTiming));
+    }
     const int total = s->cfg.total_iterations, ce = s->cfg.check_error;
     auto is_check = [&](int i) {  // training.cu:118
         return (i + 1) % ce == 0 || i == 0 || (total > 0 && (i + 1) % total == 0);
@@ -1485,6 +1518,7 @@ extern "C" cu2b_status cu2b_session_run(cu2b_session *s, int n_iterations) {
     const int tot_id = s->timing.begin(Timing::TOTAL, s->stream);
     int i = s->iter_done;
     const int end = i + n_iterations;
+    bool downloading = false;
     while (i < end) {
         int j = i;
         while (j < end && !is_check(j)) ++j;  // next check iteration (or end)
@@ -1495,11 +1529,18 @@ extern "C" cu2b_status cu2b_session_run(cu2b_session *s, int n_iterations) {
             else
                 CU2B_TRY(enqueue_sgd_iterations(s, s->cfg.cur_iterations + i, seg_end - i));
         }
+        if (out && seg_end == end && j < end) {  // the model is final: it leaves while the last check reads it
+            CU2B_TRY(stream_after(s->out_stream, s->stream, s->ev_model_final));
+            CU2B_TRY(enqueue_download(s, s->out_stream, *out));
+            downloading = true;
+        }
         if (j < end) CU2B_TRY(enqueue_check(s, j + 1, 1, true));
         i = seg_end;
     }
     s->timing.end(tot_id, s->stream);
+    if (out && !downloading) CU2B_TRY(enqueue_download(s, s->stream, *out));
     CUDA_TRY(cudaStreamSynchronize(s->stream));  // the only host sync of the loop
+    if (downloading) CUDA_TRY(cudaStreamSynchronize(s->out_stream));
     s->iter_done = end;
     double ms[Timing::NKIND] = {0, 0, 0, 0, 0, 0};
     s->timing.collect(ms);
@@ -1508,6 +1549,15 @@ extern "C" cu2b_status cu2b_session_run(cu2b_session *s, int n_iterations) {
     s->stats.sampler_ms += ms[Timing::SAMPLER];
     s->stats.total_ms += ms[Timing::TOTAL];
     return check_device_error(s);  // a timed-out device-side wait, or a non-finite loss check (CU2B_ERR_DIVERGED)
+}
+}  // namespace
+
+extern "C" cu2b_status cu2b_session_run(cu2b_session *s, int n_iterations) { return session_run_impl(s, n_iterations, nullptr); }
+
+extern "C" cu2b_status cu2b_session_run_download(cu2b_session *s, int n_iterations, float *P, float *Q, float *user_bias,
+                                                 float *item_bias) {
+    const ModelOut out{P, Q, user_bias, item_bias};
+    return session_run_impl(s, n_iterations, &out);
 }
 
 static cu2b_status session_reload_impl(cu2b_session *s, const cu2b_csr *train, const cu2b_csr *test, const float *P,
@@ -1574,18 +1624,7 @@ extern "C" cu2b_status cu2b_session_download(cu2b_session *s, float *P, float *Q
     if (!s) return cu2b_fail(CU2B_ERR_INVALID, "cu2b_session_download: null session");
     CUDA_TRY(cudaSetDevice(s->device));
     Trace tr("session_download");
-    if (P) CU2B_TRY(download_dense(s->stream, P, s->P, s->rows, s->k, s->kp));
-    if (Q && s->item_pos && s->cols > 0) {
-        const long long total = (long long)s->cols * s->kp;
-        permute_rows_kernel<<<(int)std::max<long long>(1, std::min<long long>((total + 255) / 256, s->sm_count * 8LL)), 256, 0, s->stream>>>(
-            s->Q, s->Q_stage, s->item_pos, s->cols, s->k, s->kp, 0);
-        CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaMemcpyAsync(Q, s->Q_stage, (size_t)s->cols * s->k * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
-    } else if (Q) {
-        CU2B_TRY(download_dense(s->stream, Q, s->Q, s->cols, s->k, s->kp));
-    }
-    if (user_bias) CUDA_TRY(cudaMemcpyAsync(user_bias, s->ub, (size_t)s->rows * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
-    if (item_bias) CU2B_TRY(download_item_bias(s, item_bias));
+    CU2B_TRY(enqueue_download(s, s->stream, ModelOut{P, Q, user_bias, item_bias}));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     tr.mark("D2H");
     return CU2B_OK;
@@ -1645,8 +1684,7 @@ extern "C" cu2b_status cu2b_train(const cu2b_csr *train, const cu2b_csr *test, c
     CUDA_TRY(cudaGetDevice(&dev));
     cu2b_session *s = nullptr;
     CU2B_TRY(cu2b_session_create(&s, dev, train, test, cfg, P, Q, user_bias, item_bias, global_bias));
-    cu2b_status rc = cu2b_session_run(s, cfg->total_iterations);
-    if (rc == CU2B_OK) rc = cu2b_session_download(s, P, Q, user_bias, item_bias);
+    cu2b_status rc = cu2b_session_run_download(s, cfg->total_iterations, P, Q, user_bias, item_bias);
     std::vector<cu2b_metrics> rows_log;
     int have = 0;
     if (rc == CU2B_OK) {
@@ -1864,7 +1902,7 @@ extern "C" cu2b_status cu2b_sgd_apply(const cu2b_rating *stream, int64_t n, floa
     CU2B_TRY(download_dense(s.stream, P, s.P, rows, s.k, s.kp));
     CU2B_TRY(download_dense(s.stream, Q, s.Q, cols, s.k, s.kp));
     CUDA_TRY(cudaMemcpyAsync(ub, s.ub, (size_t)rows * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
-    CU2B_TRY(download_item_bias(&s, ib));
+    CU2B_TRY(download_item_bias(&s, ib, s.stream));
     CUDA_TRY(cudaStreamSynchronize(s.stream));
     return CU2B_OK;
 }
@@ -1895,7 +1933,7 @@ extern "C" cu2b_status cu2b_sgd_blocked(const cu2b_rating *coo, int64_t n, float
     CU2B_TRY(download_dense(s.stream, P, s.P, rows, s.k, s.kp));
     CU2B_TRY(download_dense(s.stream, Q, s.Q, cols, s.k, s.kp));
     CUDA_TRY(cudaMemcpyAsync(ub, s.ub, (size_t)rows * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
-    CU2B_TRY(download_item_bias(&s, ib));
+    CU2B_TRY(download_item_bias(&s, ib, s.stream));
     CUDA_TRY(cudaStreamSynchronize(s.stream));
     return CU2B_OK;
 }

@@ -229,6 +229,11 @@ cu2b_status cu2b_session_create(cu2b_session **out, int device, const cu2b_csr *
 /* Runs n_iterations more iterations (continuing cur_iterations); blocks until done. The
  * "last iteration" check of training.cu:118 fires at cfg.total_iterations. */
 cu2b_status cu2b_session_run(cu2b_session *s, int n_iterations);
+/* cu2b_session_run followed by cu2b_session_download as ONE call (what train() does at its end, training.cu:180-185):
+ * when the run ends with a loss check -- it does whenever it reaches total_iterations -- the device->host copies
+ * of the final model run on a second stream while that check evaluates it. Any output pointer may be NULL. */
+cu2b_status cu2b_session_run_download(cu2b_session *s, int n_iterations, float *P, float *Q, float *user_bias,
+                                      float *item_bias);
 cu2b_status cu2b_session_eval(cu2b_session *s, float *train_mae, float *train_rmse,
                               float *test_mae, float *test_rmse);
 cu2b_status cu2b_session_log(cu2b_session *s, cu2b_metrics *out, int cap, int *n);

@@ -724,3 +724,37 @@ def test_per_rating_sampler_stream_and_training():
     inp = cu.dsgd_rank_inputs(tr, te, U, I, part, 0, init(U * k), init(I * k), init(U), init(I))
     with pytest.raises(cu._lib.Cu2bError):
         cu.Dsgd(0, 1, inp, part, cu.Config(total_iterations=10, n_factors=k, sampler=cu.api.SAMPLER_PER_RATING), mu)
+
+
+@pytest.mark.gpu
+def test_run_download_equals_run_then_download():
+    """cu2b_session_run_download: the model leaves on a second stream while the run's last loss check reads it. On a
+    problem whose items are never shared between users every schedule is deterministic, so the outputs must equal a
+    run followed by a download bit for bit (item placement and padded biases included)."""
+    rng = np.random.RandomState(12)
+    U, k, iters = 3000, 128, 64
+    deg = rng.randint(1, 6, U)
+    n = int(deg.sum())
+    tr = np.zeros(n, dtype=cu.RATING_DTYPE)
+    tr["user"], tr["item"], tr["rating"] = np.repeat(np.arange(U), deg), rng.permutation(n), rng.randint(1, 6, n)
+    tr = tr[np.lexsort((tr["item"], tr["user"]))]
+    te = tr[::3].copy()
+    mtr, mte = cu.createSparseMatrix(tr, U, n), cu.createSparseMatrix(te, U, n)
+    init = lambda m: cu.initialize_normal_array(m, k)
+    P, Q, ub, ib = init(U * k), init(n * k), init(U), init(n)
+    cfg = cu.Config(total_iterations=iters, n_factors=k, check_error=32)
+    with cu.Session(mtr, mte, cfg, P, Q, ub, ib, 3.0) as s:
+        s.run(iters)
+        want, want_log = s.download(), s.log()
+    with cu.Session(mtr, mte, cfg, P, Q, ub, ib, 3.0) as s:
+        got, got_log = s.run_download(iters), s.log()
+    assert got_log == want_log and [r["iteration"] for r in got_log] == [1, 32, 64]
+    for a, b in zip(got, want):
+        assert np.array_equal(np.asarray(a).view(np.uint32), np.asarray(b).view(np.uint32))
+    # a call that does not end on a check, and partial outputs
+    with cu.Session(mtr, mte, cfg, P, Q, ub, ib, 3.0) as s:
+        s.run(10)
+        Pp, _, ubp, _ = s.download()
+    with cu.Session(mtr, mte, cfg, P, Q, ub, ib, 3.0) as s:
+        got10 = s.run_download(10)
+    assert np.array_equal(got10[0].view(np.uint32), Pp.view(np.uint32)) and np.array_equal(got10[2].view(np.uint32), ubp.view(np.uint32))

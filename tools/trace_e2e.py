@@ -21,8 +21,11 @@ for rep in range(8):
     else: os.environ.pop("CU2B_TRACE", None)
     t0 = time.perf_counter()
     s = cu.Session(ptr, pte, cfg, P, Q, ub, ib, mu); t1 = time.perf_counter()
-    s.run(500); t2 = time.perf_counter()
-    s.download(out=out); t3 = time.perf_counter()
+    if os.environ.get("TRACE_FUSED_DOWNLOAD", "1") == "1":
+        s.run_download(500, out=out); t2 = t3 = time.perf_counter()   # D2H overlaps the last loss check
+    else:
+        s.run(500); t2 = time.perf_counter()
+        s.download(out=out); t3 = time.perf_counter()
     lg = s.log(); t4 = time.perf_counter()
     s.close(); t5 = time.perf_counter()
     print("rep %d create %.1f run %.1f download %.1f log %.1f destroy %.1f total %.1f ms" % (
