@@ -55,6 +55,12 @@ mf_loss_fused(const LossParams p) {
     const int g = lane / L, l = lane % L;
     const int vecs = p.kp >> 2;
     double sse = 0.0, sae = 0.0;
+    // The ratings arrive in CSR order, so the ratings a lane group sees in consecutive passes mostly belong to the
+    // same user: its slice of that user's P row and the user bias stay in registers until the user changes (the
+    // kernel is bound by L1/L2 row traffic, not by issue slots; same operands, same arithmetic, same bits).
+    float4 pu[V];
+    float ub_cur = 0.f;
+    int cur_user = -1;
     for (int it = 0;; ++it) {
         const int s = it % kStages;
         mbar_wait(&sm.full[s], (it / kStages) & 1);
@@ -65,21 +71,30 @@ mf_loss_fused(const LossParams p) {
             const int j = base + g;
             const bool ok = j < cnt;
             const cu2b_rating rt = sm.stage[s][ok ? j : 0];
-            const float4 *prow = reinterpret_cast<const float4 *>(p.P + (size_t)rt.user * p.kp);
+            if (ok && rt.user != cur_user) {
+                const float4 *prow = reinterpret_cast<const float4 *>(p.P + (size_t)rt.user * p.kp);
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    const int idx = v * L + l;
+                    pu[v] = idx < vecs ? __ldg(prow + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                ub_cur = __ldg(p.user_bias + rt.user);
+                cur_user = rt.user;
+            }
             const float4 *qrow = reinterpret_cast<const float4 *>(p.Q + (size_t)rt.item * p.kp);
             float acc = 0.f;
 #pragma unroll
             for (int v = 0; v < V; ++v) {
                 const int idx = v * L + l;
                 if (ok && idx < vecs) {
-                    const float4 a = __ldg(prow + idx), b = __ldg(qrow + idx);
+                    const float4 a = pu[v], b = __ldg(qrow + idx);
                     acc = __fmaf_rn(a.x, b.x, acc);
                     acc = __fmaf_rn(a.y, b.y, acc);
                     acc = __fmaf_rn(a.z, b.z, acc);
                     acc = __fmaf_rn(a.w, b.w, acc);
                 }
             }
-            const float ub = ok ? __ldg(p.user_bias + rt.user) : 0.f;
+            const float ub = ok ? ub_cur : 0.f;
             const float ib = ok ? __ldg(p.item_bias + (size_t)rt.item * p.ibs) : 0.f;
             const float dot = group_sum<L>(acc);
             const float pred = __fadd_rn(__fadd_rn(__fadd_rn(p.mu, ub), ib), dot);
