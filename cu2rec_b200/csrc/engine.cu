@@ -396,9 +396,20 @@ void loss_layout_for(int kp, int *L, int *V) {
     *V = (vecs + l - 1) / l;
 }
 
+template <int L>
+LossKernel pick_loss_wide(int V, int U) {
+    if (V == 3) return U >= 4 ? mf_loss_fused<L, 3, 4> : U == 2 ? mf_loss_fused<L, 3, 2> : mf_loss_fused<L, 3, 1>;
+    return U >= 4 ? mf_loss_fused<L, 4, 4> : U == 2 ? mf_loss_fused<L, 4, 2> : mf_loss_fused<L, 4, 1>;
+}
+
+// Ratings in flight per lane group (loss_kernels.cuh): kLossUnroll by default, CU2B_LOSS_UNROLL = 1 | 2 | 4 for A/B runs.
+constexpr int kLossUnroll = 1;
+
 LossKernel pick_loss(int kp) {
     int L, V;
     loss_layout_for(kp, &L, &V);
+    int U = kLossUnroll;
+    if (const char *e = getenv("CU2B_LOSS_UNROLL")) U = atoi(e);
     switch (L) {
         case 1:
             switch (V) {
@@ -407,11 +418,11 @@ LossKernel pick_loss(int kp) {
                 case 3: return mf_loss_fused<1, 3>;
                 default: return mf_loss_fused<1, 4>;
             }
-        case 2: return V == 3 ? mf_loss_fused<2, 3> : mf_loss_fused<2, 4>;
-        case 4: return V == 3 ? mf_loss_fused<4, 3> : mf_loss_fused<4, 4>;
-        case 8: return V == 3 ? mf_loss_fused<8, 3> : mf_loss_fused<8, 4>;
-        case 16: return V == 3 ? mf_loss_fused<16, 3> : mf_loss_fused<16, 4>;
-        default: return V == 3 ? mf_loss_fused<32, 3> : mf_loss_fused<32, 4>;
+        case 2: return pick_loss_wide<2>(V, U);
+        case 4: return pick_loss_wide<4>(V, U);
+        case 8: return pick_loss_wide<8>(V, U);
+        case 16: return pick_loss_wide<16>(V, U);
+        default: return pick_loss_wide<32>(V, U);
     }
 }
 

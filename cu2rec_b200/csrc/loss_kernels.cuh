@@ -30,8 +30,14 @@ __device__ __forceinline__ double warp_sum_d(double v) {
     return v;
 }
 
-template <int L, int V>
-__global__ void __launch_bounds__(kThreads)
+// U = ratings a lane group keeps in flight (their Q-row slices are requested back to back before the first one is
+// used). Measured on the Netflix shape at k = 128 (profiles/r2_loss_kernel.md): U = 1 at 4 CTAs/SM 3.4 ms per check,
+// U = 2 at 3 CTAs/SM 5.5 ms, U = 4 at 2 CTAs/SM 8.6 ms -- the kernel is bound by the L2 -> SM row traffic (14.7 of the
+// 20.5 TB/s gather peak), not by latency, and every spilled register adds to exactly that traffic. U = 1 is the product.
+constexpr int loss_min_ctas(int U) { return U >= 4 ? 2 : U == 2 ? 3 : 4; }
+
+template <int L, int V, int U = 1>
+__global__ void __launch_bounds__(kThreads, loss_min_ctas(U))
 mf_loss_fused(const LossParams p) {
     __shared__ StreamSmem sm;
     __shared__ double wsum[kConsumerWarps][2];
@@ -52,12 +58,13 @@ mf_loss_fused(const LossParams p) {
         return;
     }
     constexpr int G = 32 / L;
+    constexpr int kGroups = kConsumerWarps * G;
     const int g = lane / L, l = lane % L;
     const int vecs = p.kp >> 2;
     double sse = 0.0, sae = 0.0;
-    // The ratings arrive in CSR order, so the ratings a lane group sees in consecutive passes mostly belong to the
-    // same user: its slice of that user's P row and the user bias stay in registers until the user changes (the
-    // kernel is bound by L1/L2 row traffic, not by issue slots; same operands, same arithmetic, same bits).
+    // The ratings arrive in CSR order and a lane group takes a CONTIGUOUS run of every chunk, so consecutive ratings of
+    // a group mostly belong to the same user: its slice of that user's P row and the user bias stay in registers
+    // until the user changes (same operands, same operation order per rating, same residual bits).
     float4 pu[V];
     float ub_cur = 0.f;
     int cur_user = -1;
@@ -67,42 +74,59 @@ mf_loss_fused(const LossParams p) {
         const int cnt = sm.count[s];
         if (cnt < 0) break;
         const long long c = sm.chunk_id[s];
-        for (int base = warp * G; base < cnt; base += kConsumerWarps * G) {
-            const int j = base + g;
-            const bool ok = j < cnt;
-            const cu2b_rating rt = sm.stage[s][ok ? j : 0];
-            if (ok && rt.user != cur_user) {
-                const float4 *prow = reinterpret_cast<const float4 *>(p.P + (size_t)rt.user * p.kp);
+        const int per = (cnt + kGroups - 1) / kGroups;  // warp-uniform trip count: the group sums are shuffles
+        const int j0 = (warp * G + g) * per, j1 = min(cnt, j0 + per);
+        for (int t = 0; t < per; t += U) {
+            cu2b_rating rt[U];
+            bool ok[U];
+            float4 q[U][V];
+            float ib[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int j = j0 + t + u;
+                ok[u] = j < j1;
+                rt[u] = sm.stage[s][ok[u] ? j : 0];
+                const float4 *qrow = reinterpret_cast<const float4 *>(p.Q + (size_t)rt[u].item * p.kp);
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
                     const int idx = v * L + l;
-                    pu[v] = idx < vecs ? __ldg(prow + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    q[u][v] = (ok[u] && idx < vecs) ? __ldg(qrow + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                ub_cur = __ldg(p.user_bias + rt.user);
-                cur_user = rt.user;
+                ib[u] = ok[u] ? __ldg(p.item_bias + (size_t)rt[u].item * p.ibs) : 0.f;
             }
-            const float4 *qrow = reinterpret_cast<const float4 *>(p.Q + (size_t)rt.item * p.kp);
-            float acc = 0.f;
 #pragma unroll
-            for (int v = 0; v < V; ++v) {
-                const int idx = v * L + l;
-                if (ok && idx < vecs) {
-                    const float4 a = pu[v], b = __ldg(qrow + idx);
-                    acc = __fmaf_rn(a.x, b.x, acc);
-                    acc = __fmaf_rn(a.y, b.y, acc);
-                    acc = __fmaf_rn(a.z, b.z, acc);
-                    acc = __fmaf_rn(a.w, b.w, acc);
+            for (int u = 0; u < U; ++u) {
+                if (ok[u] && rt[u].user != cur_user) {
+                    const float4 *prow = reinterpret_cast<const float4 *>(p.P + (size_t)rt[u].user * p.kp);
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        const int idx = v * L + l;
+                        pu[v] = idx < vecs ? __ldg(prow + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    ub_cur = __ldg(p.user_bias + rt[u].user);
+                    cur_user = rt[u].user;
                 }
-            }
-            const float ub = ok ? ub_cur : 0.f;
-            const float ib = ok ? __ldg(p.item_bias + (size_t)rt.item * p.ibs) : 0.f;
-            const float dot = group_sum<L>(acc);
-            const float pred = __fadd_rn(__fadd_rn(__fadd_rn(p.mu, ub), ib), dot);
-            const float err = __fsub_rn(rt.rating, pred);
-            if (ok && l == 0) {
-                sse += (double)err * (double)err;
-                sae += (double)fabsf(err);
-                if (p.err_out) p.err_out[c * p.sv.chunk + j] = err;  // flat stream: seg_pitch unused
+                float acc = 0.f;
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    const int idx = v * L + l;
+                    if (ok[u] && idx < vecs) {
+                        const float4 a = pu[v], b = q[u][v];
+                        acc = __fmaf_rn(a.x, b.x, acc);
+                        acc = __fmaf_rn(a.y, b.y, acc);
+                        acc = __fmaf_rn(a.z, b.z, acc);
+                        acc = __fmaf_rn(a.w, b.w, acc);
+                    }
+                }
+                const float ub = ok[u] ? ub_cur : 0.f;
+                const float dot = group_sum<L>(acc);
+                const float pred = __fadd_rn(__fadd_rn(__fadd_rn(p.mu, ub), ib[u]), dot);
+                const float err = __fsub_rn(rt[u].rating, pred);
+                if (ok[u] && l == 0) {
+                    sse += (double)err * (double)err;
+                    sae += (double)fabsf(err);
+                    if (p.err_out) p.err_out[c * p.sv.chunk + j0 + t + u] = err;  // flat stream: seg_pitch unused
+                }
             }
         }
         __syncwarp();
