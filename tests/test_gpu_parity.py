@@ -758,3 +758,32 @@ def test_run_download_equals_run_then_download():
     with cu.Session(mtr, mte, cfg, P, Q, ub, ib, 3.0) as s:
         got10 = s.run_download(10)
     assert np.array_equal(got10[0].view(np.uint32), Pp.view(np.uint32)) and np.array_equal(got10[2].view(np.uint32), ubp.view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_non_finite_model_is_reported_as_diverged_not_as_success():
+    """The device-side guard (loss_kernels.cuh flag_non_finite) without any chaos involved: a model that is not finite
+    when a loss check evaluates it makes cu2b_session_run / cu2b_train return CU2B_ERR_DIVERGED (the reference prints
+    `nan` and exits 0, training.cu:118-160; round 1 did the same at 4 GPUs)."""
+    tr, te = cu.synth_ratings(2000, 300, 60000, rank=4, noise=0.3, seed=4)
+    U, I, k = 2000, 300, 16
+    mtr, mte = cu.createSparseMatrix(tr, U, I), cu.createSparseMatrix(te, U, I)
+    mu = np.float32(tr["rating"].astype(np.float64).mean())
+    init = lambda n: cu.initialize_normal_array(n, k)
+    P, Q, ub, ib = init(U * k), init(I * k), init(U), init(I)
+    cfg = cu.Config(total_iterations=40, n_factors=k, check_error=20)
+    with cu.Session(mtr, mte, cfg, P, Q, ub, ib, mu) as s:  # the finite model trains
+        s.run(40)
+        assert all(np.isfinite(r["test_rmse"]) for r in s.log())
+    for poison in (np.float32("nan"), np.float32("inf")):
+        Qbad = Q.copy()
+        Qbad[int(mtr.indices[0]) * k] = poison  # a rated item: the first train check sees it
+        with cu.Session(mtr, mte, cfg, P, Qbad, ub, ib, mu) as s:
+            with pytest.raises(cu._lib.Cu2bError) as err:
+                s.run(40)
+            assert err.value.status == 6 and "non-finite" in str(err.value)
+    # a learning rate that makes plain SGD itself blow up: same status through the train() entry point
+    wild = cu.Config(total_iterations=200, n_factors=k, check_error=50, learning_rate=50.0)
+    with pytest.raises(cu._lib.Cu2bError) as err:
+        cu.train(mtr, mte, wild, mu)
+    assert err.value.status == 6
