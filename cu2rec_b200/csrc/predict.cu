@@ -117,6 +117,28 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// v[c] for a per-lane column index: a five-level select tree (31 selects, depth 5) instead of a 32-step chain.
+__device__ __forceinline__ float pick32(const float (&v)[32], int c) {
+    float a[16], b[8], d[4];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = (c & 1) ? v[2 * j + 1] : v[2 * j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[j] = (c & 2) ? a[2 * j + 1] : a[2 * j];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) d[j] = (c & 4) ? b[2 * j + 1] : b[2 * j];
+    const float e0 = (c & 8) ? d[1] : d[0], e1 = (c & 8) ? d[3] : d[2];
+    return (c & 16) ? e1 : e0;
+}
+
+// Pending candidates per epilogue thread (shared memory behind PredictSmemCtl, [slot][thread]): columns that beat a
+// user's threshold are parked here and merged into the sorted register list in batches, when some lane's ring is full.
+// A warp executes the merge for all its lanes at once, so batching raises its lane efficiency from ~17 % (one hit per
+// lane and pass) to ~45 %; the merge sees the candidates in item order and re-checks the threshold, so the list is the
+// one immediate insertion builds.
+constexpr int kRing = 8;
+constexpr int kEpilogueThreads = 256;
+constexpr size_t kRingBytes = (size_t)2 * kRing * kEpilogueThreads * sizeof(float);
+
 struct PredictSmemCtl {
     uint64_t a_full, a_empty;
     uint64_t b_full[2], b_empty[2];
@@ -275,6 +297,9 @@ predict_candidates_kernel(const __grid_constant__ CUtensorMap map_p, const __gri
         const int grp = (warp - 2) >> 2;        // 0 or 1
         const int quad = warp & 3;              // TMEM lane quadrant this warp may read
         const int et = ((warp - 2) & 3) * 32 + lane;  // 0..127 inside the group (stages the item-bias tile)
+        float *ring_sc = reinterpret_cast<float *>(ctl + 1);
+        int *ring_it = reinterpret_cast<int *>(ring_sc + kRing * kEpilogueThreads);
+        const int rt = grp * 128 + et;
         int n = 0;
         for (int ut = blockIdx.x; ut < p.n_user_tiles; ut += gridDim.x, ++n) {
             const int u = ut * BM + quad * 32 + lane;
@@ -282,6 +307,33 @@ predict_candidates_kernel(const __grid_constant__ CUtensorMap map_p, const __gri
             int ci[KC];
 #pragma unroll
             for (int i = 0; i < KC; ++i) { cs[i] = -INFINITY; ci[i] = -1; }
+            int cnt = 0;  // entries in this thread's ring
+            // Merge the parked candidates, oldest first. Position = number of kept scores >= sc (ties keep the earlier
+            // item first). Scores: new[i] = max(old[i], min(old[i-1], sc)) is exactly "keep / insert here / shift down"
+            // for a descending list; items follow with the two comparisons of the neighbours.
+            auto merge_pending = [&]() {
+                const int most = __reduce_max_sync(0xffffffffu, cnt);
+#pragma unroll 1
+                for (int r = 0; r < most; ++r) {
+                    if (r < cnt) {
+                        const float sc = ring_sc[r * kEpilogueThreads + rt];
+                        const int item = ring_it[r * kEpilogueThreads + rt];
+                        if (sc > cs[KC - 1]) {
+                            bool ge_hi = cs[KC - 1] >= sc;
+#pragma unroll
+                            for (int i = KC - 1; i > 0; --i) {
+                                const bool ge_lo = cs[i - 1] >= sc;
+                                ci[i] = ge_hi ? ci[i] : (ge_lo ? item : ci[i - 1]);
+                                cs[i] = fmaxf(cs[i], fminf(cs[i - 1], sc));
+                                ge_hi = ge_lo;
+                            }
+                            ci[0] = ge_hi ? ci[0] : item;
+                            cs[0] = fmaxf(cs[0], sc);
+                        }
+                    }
+                }
+                cnt = 0;
+            };
             const uint4 *mrow = (p.bitmap && u < p.users) ? reinterpret_cast<const uint4 *>(p.bitmap + (size_t)u * p.mask_pitch) : nullptr;
             const int it0 = n * p.n_item_tiles;  // global tile counter at the start of this user tile
             // first item tile of this user tile that belongs to my buffer
@@ -316,30 +368,19 @@ predict_candidates_kernel(const __grid_constant__ CUtensorMap map_p, const __gri
                         hits = __funnelshift_l(__float_as_uint(thr - v[c]), hits, 1);
                     }
                     hits &= live;
-                    // rare path, kept out of the unrolled code (it exists once, not 128 times)
+                    // park the hits (the loop body exists once, not 128 times); merge when a ring is full
                     while (__any_sync(0xffffffffu, hits != 0)) {
                         if (hits) {
                             const int c = __ffs(hits) - 1;
                             hits &= hits - 1;
-                            float sc = 0.f;
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) sc = (i == c) ? v[i] : sc;
+                            const float sc = pick32(v, c);
                             if (sc > cs[KC - 1]) {
-                                const int item = n0 + ch * 32 + c;
-                                // position = number of kept scores >= sc (ties keep the earlier item
-                                // first); compares and moves are independent (no serial bubble chain)
-                                int pos = 0;
-#pragma unroll
-                                for (int i = 0; i < KC; ++i) pos += (cs[i] >= sc);
-#pragma unroll
-                                for (int i = KC - 1; i > 0; --i) {
-                                    const bool shift = i > pos;
-                                    cs[i] = shift ? cs[i - 1] : (i == pos ? sc : cs[i]);
-                                    ci[i] = shift ? ci[i - 1] : (i == pos ? item : ci[i]);
-                                }
-                                if (pos == 0) { cs[0] = sc; ci[0] = item; }
+                                ring_sc[cnt * kEpilogueThreads + rt] = sc;
+                                ring_it[cnt * kEpilogueThreads + rt] = n0 + ch * 32 + c;
+                                ++cnt;
                             }
                         }
+                        if (__any_sync(0xffffffffu, cnt == kRing)) merge_pending();
                     }
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -347,6 +388,7 @@ predict_candidates_kernel(const __grid_constant__ CUtensorMap map_p, const __gri
                 if (lane == 0) bar_arrive(&ctl->acc_empty[grp]);
                 mask = mask_next;
             }
+            merge_pending();
             if (u < p.users) {
 #pragma unroll
                 for (int i = 0; i < KC; ++i) {
@@ -506,7 +548,7 @@ cu2b_status upload_padded(DevBuf &buf, const float *src, int rows, int k, int kp
 template <bool STREAM>
 cu2b_status launch_candidates(const CUtensorMap &mp, const CUtensorMap &mq, const PredictParams &pp, int sm_count) {
     const size_t smem = (STREAM ? (size_t)STREAM_STAGES * 2 * CHUNK_SLABS * SLAB_BYTES : (size_t)3 * pp.kslabs * SLAB_BYTES) +
-                        sizeof(PredictSmemCtl) + 1024;
+                        sizeof(PredictSmemCtl) + kRingBytes + 1024;
     CUDA_TRY(cudaFuncSetAttribute(predict_candidates_kernel<16, STREAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = std::max(1, std::min(pp.n_user_tiles, sm_count));
     predict_candidates_kernel<16, STREAM><<<grid, kThreadsPredict, smem>>>(mp, mq, pp);
