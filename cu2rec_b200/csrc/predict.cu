@@ -139,10 +139,15 @@ constexpr int kRing = 8;
 constexpr int kEpilogueThreads = 256;
 constexpr size_t kRingBytes = (size_t)2 * kRing * kEpilogueThreads * sizeof(float);
 
+// Accumulator tiles in TMEM: 4 x 128 columns = all 512. Each epilogue group owns two of them alternately, so the MMAs
+// of a group's next tile run while the group is still scanning the current one (with one tile per group the chain
+// epilogue -> acc_empty -> MMA -> acc_full -> epilogue left the epilogue warps waiting 47 % of the time).
+constexpr int kAccBufs = 4;
+
 struct PredictSmemCtl {
     uint64_t a_full, a_empty;
     uint64_t b_full[2], b_empty[2];
-    uint64_t acc_full[2], acc_empty[2];
+    uint64_t acc_full[kAccBufs], acc_empty[kAccBufs];
     uint64_t st_full[3], st_empty[3];  // STREAM: ring of {user chunk, item chunk} stages
     uint32_t tmem_base;
     uint32_t pad;
@@ -161,6 +166,15 @@ struct PredictParams {
     int32_t *cand_items;     // [users][2][KC]: one sorted list per epilogue group
     float *cand_scores;      // [users][2][KC] (TF32 scores incl. item bias; diagnostics)
 };
+
+// -DCU2B_PREDICT_PROFILE: cycles one epilogue warp of each group spends per phase (printed by CTA 0; tools/r2 README).
+#ifdef CU2B_PREDICT_PROFILE
+#define PROF_DECL long long prof[6] = {0, 0, 0, 0, 0, 0}; long long prof_t = clock64();
+#define PROF(i) { const long long now_ = clock64(); prof[i] += now_ - prof_t; prof_t = now_; }
+#else
+#define PROF_DECL
+#define PROF(i)
+#endif
 
 template <int KC, bool STREAM>
 __global__ void __launch_bounds__(kThreadsPredict, 1)
@@ -183,6 +197,8 @@ predict_candidates_kernel(const __grid_constant__ CUtensorMap map_p, const __gri
         for (int s = 0; s < 2; ++s) {
             bar_init(&ctl->b_full[s], 1);
             bar_init(&ctl->b_empty[s], 1);
+        }
+        for (int s = 0; s < kAccBufs; ++s) {
             bar_init(&ctl->acc_full[s], 1);
             bar_init(&ctl->acc_empty[s], 4);
         }
@@ -192,8 +208,8 @@ predict_candidates_kernel(const __grid_constant__ CUtensorMap map_p, const __gri
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {  // TMEM: 2 accumulators x 128 columns
-        const uint32_t ncols = 256;
+    if (warp == 1) {  // TMEM: kAccBufs accumulators x 128 columns
+        const uint32_t ncols = kAccBufs * BN;
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&ctl->tmem_base)), "r"(ncols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -228,6 +244,7 @@ predict_candidates_kernel(const __grid_constant__ CUtensorMap map_p, const __gri
                 for (int sl = 0; sl < p.kslabs; ++sl)
                     tma_load_2d(smem_a + (size_t)sl * SLAB_BYTES, &map_p, sl * SLAB_K, ut * BM, &ctl->a_full);
                 for (int j = 0; j < p.n_item_tiles; ++j, ++it) {
+                    // (one barrier pair per 16 KB slab instead of per tile was measured and is slower: 5.9 against 5.2 ms)
                     const int s = it & 1;
                     if (it >= 2) bar_wait(&ctl->b_empty[s], ((it >> 1) - 1) & 1);
                     bar_expect(&ctl->b_full[s], slab_tx);
@@ -245,8 +262,8 @@ predict_candidates_kernel(const __grid_constant__ CUtensorMap map_p, const __gri
             int st = 0, it = 0;
             for (int ut = blockIdx.x; ut < p.n_user_tiles; ut += gridDim.x)
                 for (int j = 0; j < p.n_item_tiles; ++j, ++it) {
-                    const int b = it & 1;
-                    if (it >= 2) bar_wait(&ctl->acc_empty[b], ((it >> 1) - 1) & 1);
+                    const int b = it % kAccBufs;
+                    if (it >= kAccBufs) bar_wait(&ctl->acc_empty[b], ((it / kAccBufs) - 1) & 1);
                     const uint32_t d_tmem = tmem_base + (uint32_t)b * BN;
                     for (int c = 0; c < n_chunks; ++c, ++st) {
                         const int s = st % STREAM_STAGES;
@@ -272,10 +289,11 @@ predict_candidates_kernel(const __grid_constant__ CUtensorMap map_p, const __gri
                 bar_wait(&ctl->a_full, n & 1);
                 for (int j = 0; j < p.n_item_tiles; ++j, ++it) {
                     const int s = it & 1;
+                    const int b = it % kAccBufs;
                     bar_wait(&ctl->b_full[s], (it >> 1) & 1);
-                    if (it >= 2) bar_wait(&ctl->acc_empty[s], ((it >> 1) - 1) & 1);
+                    if (it >= kAccBufs) bar_wait(&ctl->acc_empty[b], ((it / kAccBufs) - 1) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t d_tmem = tmem_base + (uint32_t)s * BN;
+                    const uint32_t d_tmem = tmem_base + (uint32_t)b * BN;
                     for (int sl = 0; sl < p.kslabs; ++sl) {
                         const uint32_t a0 = s32(smem_a + (size_t)sl * SLAB_BYTES);
                         const uint32_t b0 = s32(smem_b + ((size_t)s * p.kslabs + sl) * SLAB_BYTES);
@@ -285,7 +303,7 @@ predict_candidates_kernel(const __grid_constant__ CUtensorMap map_p, const __gri
                                       (uint32_t)((sl | ks) != 0));
                     }
                     umma_commit(&ctl->b_empty[s]);   // smem stage may be refilled once these MMAs retire
-                    umma_commit(&ctl->acc_full[s]);  // accumulator ready for the epilogue
+                    umma_commit(&ctl->acc_full[b]);  // accumulator ready for the epilogue
                 }
                 umma_commit(&ctl->a_empty);
             }
@@ -301,6 +319,7 @@ predict_candidates_kernel(const __grid_constant__ CUtensorMap map_p, const __gri
         int *ring_it = reinterpret_cast<int *>(ring_sc + kRing * kEpilogueThreads);
         const int rt = grp * 128 + et;
         int n = 0;
+        PROF_DECL
         for (int ut = blockIdx.x; ut < p.n_user_tiles; ut += gridDim.x, ++n) {
             const int u = ut * BM + quad * 32 + lane;
             float cs[KC];
@@ -347,12 +366,15 @@ predict_candidates_kernel(const __grid_constant__ CUtensorMap map_p, const __gri
                 const uint4 mask_next = (mrow && j + 2 < p.n_item_tiles) ? __ldg(mrow + j + 2) : make_uint4(0u, 0u, 0u, 0u);
                 if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
                 else          asm volatile("bar.sync 2, 128;" ::: "memory");
-                bar_wait(&ctl->acc_full[grp], (it >> 1) & 1);
+                const int ab = it % kAccBufs;  // this group's tiles alternate between accumulators grp and grp + 2
+                bar_wait(&ctl->acc_full[ab], (it / kAccBufs) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                PROF(0)
 #pragma unroll 1
                 for (int ch = 0; ch < BN / 32; ++ch) {
                     float v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(grp * BN + ch * 32), v);
+                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * BN + ch * 32), v);
+                    PROF(1)
                     const uint32_t mword = ch == 0 ? mask.x : ch == 1 ? mask.y : ch == 2 ? mask.z : mask.w;
                     const int valid = p.items - (n0 + ch * 32);  // columns [0, valid) of this chunk exist
                     const uint32_t live = (valid >= 32 ? 0xffffffffu : valid <= 0 ? 0u : ((1u << valid) - 1u)) & ~mword;
@@ -368,6 +390,7 @@ predict_candidates_kernel(const __grid_constant__ CUtensorMap map_p, const __gri
                         hits = __funnelshift_l(__float_as_uint(thr - v[c]), hits, 1);
                     }
                     hits &= live;
+                    PROF(2)
                     // park the hits (the loop body exists once, not 128 times); merge when a ring is full
                     while (__any_sync(0xffffffffu, hits != 0)) {
                         if (hits) {
@@ -380,15 +403,17 @@ predict_candidates_kernel(const __grid_constant__ CUtensorMap map_p, const __gri
                                 ++cnt;
                             }
                         }
-                        if (__any_sync(0xffffffffu, cnt == kRing)) merge_pending();
+                        if (__any_sync(0xffffffffu, cnt == kRing)) { PROF(3) merge_pending(); PROF(4) }
                     }
+                    PROF(3)
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) bar_arrive(&ctl->acc_empty[grp]);
+                if (lane == 0) bar_arrive(&ctl->acc_empty[ab]);
                 mask = mask_next;
             }
             merge_pending();
+            PROF(4)
             if (u < p.users) {
 #pragma unroll
                 for (int i = 0; i < KC; ++i) {
@@ -396,13 +421,19 @@ predict_candidates_kernel(const __grid_constant__ CUtensorMap map_p, const __gri
                     p.cand_scores[((size_t)u * 2 + grp) * KC + i] = cs[i];
                 }
             }
+            PROF(5)
         }
+#ifdef CU2B_PREDICT_PROFILE
+        if (blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 6))
+            printf("PROF warp %d: wait %lld ld %lld scan %lld loop %lld merge %lld store %lld cycles\n", warp, prof[0], prof[1], prof[2],
+                   prof[3], prof[4], prof[5]);
+#endif
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t ncols = 256;
+        const uint32_t ncols = kAccBufs * BN;
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
     }
 }
