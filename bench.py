@@ -278,6 +278,10 @@ class CpuReference:
             secs = float(re.search(r"Time taken for \d+ of iterations is ([0-9.eE+-]+)", out).group(1))
             rmse = float([l for l in out.splitlines() if l.startswith("TEST:")][-1].split()[-1])
             return updates, secs, rmse
+        return self._run_port(self.iters)
+
+    def _run_port(self, iters):
+        """The oracle restatement (oracle/mf_oracle.cpp: seeded counter-based sampler, half-open range) on the sample."""
         O, k = self.O, self.k
         import cu2rec_b200 as cu
         mtr, mte = cu.createSparseMatrix(self.tr, self.U, self.I), cu.createSparseMatrix(self.te, self.U, self.I)
@@ -286,8 +290,18 @@ class CpuReference:
         P, Q, ub, ib = init(self.U * k), init(self.I * k), init(self.U), init(self.I)
         t0 = time.perf_counter()
         *_, lg = O.train((mtr.indptr, mtr.indices, mtr.data), (mte.indptr, mte.indices, mte.data), P, Q, ub, ib, mu,
-                         O.hyper(k), 42, self.iters, use_decay=False)
-        return updates, time.perf_counter() - t0, lg[-1]["test_rmse"]
+                         O.hyper(k), 42, iters, use_decay=False)
+        return iters * self.U, time.perf_counter() - t0, lg[-1]["test_rmse"]
+
+    def port_fixed_rng(self, budget_s=3.0):
+        """SURVEY 8d: ~21 us of every mf_cpu update is the std::random_device + mt19937 construction
+        (mf_sequential.cu:109), so the restatement with a seeded RNG is reported beside it -- labelled, not a substitute."""
+        iters = int(max(2, min(2000, budget_s / (0.4e-6 * max(1.0, self.k / 32) * self.U))))
+        u, s, rmse = self._run_port(iters)
+        return {"value": u / s, "unit": UNIT, "cores": 1, "kind": "port", "seconds": s, "final_test_rmse": rmse,
+                "what": "CPU oracle (fixed RNG): the restatement oracle/mf_oracle.cpp, same sample, %d iterations, updates on one "
+                        "thread (its two loss checks use the host threads; they are < 2 %% of the time); "
+                        "not the reference and not the headline baseline" % iters}
 
 
 def run_reference_arm(args):
@@ -315,7 +329,8 @@ def run_reference_arm(args):
                        step="%d reference iterations on the first %d users (bounded sample; per-update cost does not depend "
                             "on the sample size) incl. the reference's loss checks" % (ref.iters, ref.U)),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": ref.kind, "sample": ref.sample_desc(),
-                         "host_cores_available": os.cpu_count(), "final_test_rmse": rmse},
+                         "host_cores_available": os.cpu_count(), "final_test_rmse": rmse,
+                         "port_fixed_rng": ref.port_fixed_rng() if ref.kind == "reference" else None},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -593,7 +608,8 @@ def run_ours(args):
         ref = CpuReference(args.workload, k, budget_s=args.cpu_budget)
         u, s, r_rmse = ref.run_once()
         cpu = {"value": u / s, "unit": UNIT, "cores": 1, "kind": ref.kind, "sample": ref.sample_desc(),
-               "host_cores_available": os.cpu_count(), "seconds": s, "final_test_rmse": r_rmse}
+               "host_cores_available": os.cpu_count(), "seconds": s, "final_test_rmse": r_rmse,
+               "port_fixed_rng": ref.port_fixed_rng() if ref.kind == "reference" else None}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
