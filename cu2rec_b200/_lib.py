@@ -53,6 +53,8 @@ SYMBOLS = {
     "cu2b_config_format": (C.c_int, [C.POINTER(Config), C.c_char_p, C.c_int]),
     "cu2b_read_csv": (C.c_int, [C.c_char_p, C.POINTER(C.POINTER(Rating)), C.POINTER(C.c_int64),
                                 C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float)]),
+    "cu2b_read_csv_cached": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.POINTER(Rating)), C.POINTER(C.c_int64),
+                                       C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "cu2b_build_csr": (C.c_int, [_P, C.c_int64, C.c_int, _P, _P, _P]),
     "cu2b_read_array": (C.c_int, [C.c_char_p, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "cu2b_write_csv": (C.c_int, [C.c_char_p, _P, C.c_int, C.c_int]),

@@ -77,13 +77,22 @@ class Config:
 # ------------------------------------------------------------------------------------------
 # util.h
 # ------------------------------------------------------------------------------------------
-def readCSV(path):
-    """util.cu:17-45 -> (ratings[RATING_DTYPE], rows, cols, global_bias)."""
+def readCSV(path, cache=None):
+    """util.cu:17-45 -> (ratings[RATING_DTYPE], rows, cols, global_bias). cache: None = parse the text; True = through the
+    binary sidecar "<path>.cu2bcache"; a path = through that sidecar (cu2b_read_csv_cached). readCSV.last_hit tells
+    whether the last cached read used the sidecar."""
     lib = _lib.load()
     p = C.POINTER(Rating)()
     n = C.c_int64()
     rows, cols, gb = C.c_int(), C.c_int(), C.c_float()
-    check(lib.cu2b_read_csv(str(path).encode(), C.byref(p), C.byref(n), C.byref(rows), C.byref(cols), C.byref(gb)))
+    if cache is None or cache is False:
+        check(lib.cu2b_read_csv(str(path).encode(), C.byref(p), C.byref(n), C.byref(rows), C.byref(cols), C.byref(gb)))
+    else:
+        hit = C.c_int()
+        where = None if cache is True else str(cache).encode()
+        check(lib.cu2b_read_csv_cached(str(path).encode(), where, C.byref(p), C.byref(n), C.byref(rows), C.byref(cols),
+                                       C.byref(gb), C.byref(hit)))
+        readCSV.last_hit = bool(hit.value)
     try:
         out = np.empty(n.value, dtype=RATING_DTYPE)
         if n.value:
@@ -91,6 +100,9 @@ def readCSV(path):
     finally:
         lib.cu2b_free(p)
     return out, rows.value, cols.value, np.float32(gb.value)
+
+
+readCSV.last_hit = False
 
 
 @dataclass

@@ -20,6 +20,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -103,7 +104,12 @@ inline std::vector<Rating> readCSV(const std::string &filename, int *rows, int *
     cu2b_rating *r = nullptr;
     int64_t n = 0;
     std::vector<Rating> out;
-    if (cu2b_read_csv(filename.c_str(), &r, &n, rows, cols, global_bias) != CU2B_OK) {
+    // CU2B_CSV_CACHE=1: keep / use a binary sidecar "<file>.cu2bcache" (same results; a second run skips the parse)
+    const char *cache = getenv("CU2B_CSV_CACHE");
+    const bool cached = cache && *cache && strcmp(cache, "0") != 0;
+    const cu2b_status rc = cached ? cu2b_read_csv_cached(filename.c_str(), nullptr, &r, &n, rows, cols, global_bias, nullptr)
+                                  : cu2b_read_csv(filename.c_str(), &r, &n, rows, cols, global_bias);
+    if (rc != CU2B_OK) {
         fprintf(stderr, "ERROR: The file isnt open.\n");  // util.cu:42
         return out;
     }

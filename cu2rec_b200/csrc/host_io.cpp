@@ -444,6 +444,115 @@ extern "C" cu2b_status cu2b_read_csv(const char *path, cu2b_rating **ratings, in
     return CU2B_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Binary sidecar of a parsed ratings file. Layout: a 48-byte header, then n triplets of 12 bytes.
+// A sidecar belongs to one exact state of its source: size and modification time are part of the header.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct SidecarHeader {
+    char magic[8];        // "CU2BRAT1"
+    uint64_t src_size;    // st_size of the CSV it was parsed from
+    int64_t src_mtime_ns; // st_mtim of that CSV
+    int64_t n;            // triplets that follow
+    int32_t rows, cols;   // max userId / max itemId (util.cu:36-37)
+    float global_bias;    // mean rating (util.cu:38)
+    uint32_t elem_bytes;  // sizeof(cu2b_rating)
+};
+static_assert(sizeof(SidecarHeader) == 48, "sidecar header layout");
+const char kSidecarMagic[8] = {'C', 'U', '2', 'B', 'R', 'A', 'T', '1'};
+
+int64_t mtime_ns(const struct stat &st) { return (int64_t)st.st_mtim.tv_sec * 1000000000LL + st.st_mtim.tv_nsec; }
+
+// -> true and *out (malloc'd) when `cache` is a sidecar of the source described by `src`
+bool sidecar_load(const char *cache, const struct stat &src, cu2b_rating **out, SidecarHeader *h) {
+    int fd = open(cache, O_RDONLY);
+    if (fd < 0) return false;
+    struct stat cst;
+    bool ok = fstat(fd, &cst) == 0 && (size_t)cst.st_size >= sizeof(SidecarHeader) &&
+              pread(fd, h, sizeof(*h), 0) == (ssize_t)sizeof(*h) && memcmp(h->magic, kSidecarMagic, 8) == 0 &&
+              h->elem_bytes == sizeof(cu2b_rating) && h->src_size == (uint64_t)src.st_size && h->src_mtime_ns == mtime_ns(src) &&
+              h->n >= 0 && (uint64_t)cst.st_size == sizeof(SidecarHeader) + (uint64_t)h->n * sizeof(cu2b_rating);
+    cu2b_rating *r = nullptr;
+    if (ok) {
+        const size_t bytes = (size_t)h->n * sizeof(cu2b_rating);
+        r = (cu2b_rating *)malloc(std::max<size_t>(bytes, 16));
+        ok = r != nullptr;
+        if (ok && bytes) {
+            // page-cache to memory at memcpy speed: every thread preads its own slice
+            const int nt = bytes < cu2b_io_parallel_min_bytes() ? 1 : std::max(1, omp_get_max_threads());
+            int bad = 0;
+#pragma omp parallel for num_threads(nt) schedule(static, 1) reduction(+ : bad)
+            for (int t = 0; t < nt; ++t) {
+                size_t lo = bytes * t / nt, hi = bytes * (t + 1) / nt;
+                while (lo < hi) {
+                    ssize_t got = pread(fd, (char *)r + lo, hi - lo, (off_t)(sizeof(SidecarHeader) + lo));
+                    if (got <= 0) { ++bad; break; }
+                    lo += (size_t)got;
+                }
+            }
+            ok = bad == 0;
+        }
+    }
+    close(fd);
+    if (!ok) { free(r); return false; }
+    *out = r;
+    return true;
+}
+
+// Best effort: a sidecar that cannot be written (read-only directory, full disk) is not an error of the read.
+void sidecar_store(const char *cache, const struct stat &src, const cu2b_rating *r, int64_t n, int rows, int cols, float gb) {
+    std::string tmp = std::string(cache) + ".tmp." + std::to_string((long)getpid());
+    int fd = open(tmp.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) return;
+    SidecarHeader h;
+    memcpy(h.magic, kSidecarMagic, 8);
+    h.src_size = (uint64_t)src.st_size;
+    h.src_mtime_ns = mtime_ns(src);
+    h.n = n;
+    h.rows = rows;
+    h.cols = cols;
+    h.global_bias = gb;
+    h.elem_bytes = (uint32_t)sizeof(cu2b_rating);
+    bool ok = write(fd, &h, sizeof(h)) == (ssize_t)sizeof(h);
+    const char *p = (const char *)r;
+    size_t left = (size_t)n * sizeof(cu2b_rating);
+    while (ok && left) {
+        ssize_t put = write(fd, p, std::min<size_t>(left, (size_t)1 << 30));
+        ok = put > 0;
+        if (ok) { p += put; left -= (size_t)put; }
+    }
+    ok = (close(fd) == 0) && ok;
+    if (!ok || rename(tmp.c_str(), cache) != 0) unlink(tmp.c_str());  // readers only ever see complete sidecars
+}
+}  // namespace
+
+extern "C" cu2b_status cu2b_read_csv_cached(const char *path, const char *cache_path, cu2b_rating **ratings, int64_t *n_out,
+                                            int *rows, int *cols, float *global_bias, int *hit) {
+    if (!path || !ratings || !n_out || !rows || !cols || !global_bias)
+        return cu2b_fail(CU2B_ERR_INVALID, "cu2b_read_csv_cached: null argument");
+    if (hit) *hit = 0;
+    const std::string cache = cache_path ? std::string(cache_path) : std::string(path) + ".cu2bcache";
+    struct stat src;
+    if (stat(path, &src) != 0) return cu2b_read_csv(path, ratings, n_out, rows, cols, global_bias);  // the reader reports it
+    SidecarHeader h;
+    cu2b_rating *r = nullptr;
+    if (sidecar_load(cache.c_str(), src, &r, &h)) {
+        *ratings = r;
+        *n_out = h.n;
+        *rows = h.rows;
+        *cols = h.cols;
+        *global_bias = h.global_bias;
+        if (hit) *hit = 1;
+        return CU2B_OK;
+    }
+    cu2b_status rc = cu2b_read_csv(path, ratings, n_out, rows, cols, global_bias);
+    if (rc != CU2B_OK) return rc;
+    struct stat again;  // a file that changed while it was parsed gets no sidecar
+    if (stat(path, &again) == 0 && again.st_size == src.st_size && mtime_ns(again) == mtime_ns(src))
+        sidecar_store(cache.c_str(), src, *ratings, *n_out, *rows, *cols, *global_bias);
+    return CU2B_OK;
+}
+
 extern "C" cu2b_status cu2b_build_csr(const cu2b_rating *r, int64_t n, int rows, int *indptr,
                                       int *indices, float *data) {
     if ((!r && n > 0) || !indptr || rows < 0 || n < 0 || n > INT32_MAX)

@@ -106,6 +106,13 @@ typedef struct cu2b_rating { /* util.h:19-24 struct Rating; also the device stre
  * *ratings is allocated by the library (cu2b_free). */
 cu2b_status cu2b_read_csv(const char *path, cu2b_rating **ratings, int64_t *n, int *rows,
                           int *cols, float *global_bias);
+/* The same read through a binary sidecar (no reference counterpart: util.cu:17-45 re-parses the text on
+ * every run). `cache_path` NULL = "<path>.cu2bcache". If that file is a sidecar written for exactly this state of
+ * `path` (same size and modification time), its triplets, dimensions and mean are returned without parsing and
+ * *hit = 1; otherwise the CSV is parsed as by cu2b_read_csv and the sidecar is (re)written, best effort and
+ * atomically (temporary file + rename). The results are identical either way. `hit` may be NULL. */
+cu2b_status cu2b_read_csv_cached(const char *path, const char *cache_path, cu2b_rating **ratings, int64_t *n, int *rows,
+                                 int *cols, float *global_bias, int *hit);
 /* util.cu:152-179 createSparseMatrix (host part): ratings grouped by ascending user -> CSR;
  * missing users repeat indptr. indptr has rows+1 entries. */
 cu2b_status cu2b_build_csr(const cu2b_rating *ratings, int64_t n, int rows, int *indptr,

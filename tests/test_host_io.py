@@ -415,3 +415,86 @@ def test_read_csv_malformed_rows_match_the_reference_stream_semantics(tmp_path, 
         assert got["rating"].view(np.uint32).tolist() == want["rating_bits"], name
         assert int(np.float32(gb).view(np.uint32)) == want["global_bias_bits"], name
         assert np.all(np.isfinite(got["rating"])), name
+
+
+def test_read_csv_through_the_binary_sidecar(tmp_path):
+    """the sidecar returns exactly what parsing returns, belongs to one state of its source (size + mtime),
+    is rewritten when the source changes, and a damaged or foreign file at its place is ignored."""
+    import os
+    rng = np.random.RandomState(5)
+    n = 20000
+    r = np.zeros(n, dtype=cu.RATING_DTYPE)
+    r["user"] = np.sort(rng.randint(0, 700, n))
+    r["item"] = rng.randint(0, 300, n)
+    r["rating"] = rng.randint(1, 11, n) * 0.5
+    path = tmp_path / "ratings.csv"
+    cu.write_ratings_csv(path, r)
+    want = cu.readCSV(path)
+    side = str(path) + ".cu2bcache"
+
+    def same(a, b):
+        return (a[0].tobytes() == b[0].tobytes() and a[1:3] == b[1:3]
+                and np.float32(a[3]).tobytes() == np.float32(b[3]).tobytes())
+    first = cu.readCSV(path, cache=True)
+    assert not cu.readCSV.last_hit and os.path.exists(side) and same(first, want)
+    assert os.path.getsize(side) == 48 + 12 * n
+    again = cu.readCSV(path, cache=True)
+    assert cu.readCSV.last_hit and same(again, want)
+    # the source changes (one more rating): the stale sidecar is not used and is replaced
+    with open(path, "a") as f:
+        f.write("701,5,4.5\n")
+    st = os.stat(path)
+    os.utime(path, ns=(st.st_atime_ns, st.st_mtime_ns + 1_000_000_000))
+    grown = cu.readCSV(path, cache=True)
+    assert not cu.readCSV.last_hit and len(grown[0]) == n + 1 and same(grown, cu.readCSV(path))
+    assert cu.readCSV(path, cache=True)[0].tobytes() == grown[0].tobytes() and cu.readCSV.last_hit
+    # same size, later mtime: still a different state of the file
+    os.utime(path, ns=(st.st_atime_ns, st.st_mtime_ns + 5_000_000_000))
+    cu.readCSV(path, cache=True)
+    assert not cu.readCSV.last_hit
+    # a truncated sidecar and a foreign file are ignored (and replaced by a good one)
+    for damage in (lambda: open(side, "r+b").truncate(48 + 12 * 100), lambda: open(side, "wb").write(b"not a sidecar" * 10)):
+        damage()
+        got = cu.readCSV(path, cache=True)
+        assert not cu.readCSV.last_hit and same(got, grown)
+        cu.readCSV(path, cache=True)
+        assert cu.readCSV.last_hit
+    # an explicit sidecar path; an unwritable one is not an error of the read
+    other = tmp_path / "elsewhere.bin"
+    assert same(cu.readCSV(path, cache=other), grown) and other.exists()
+    assert same(cu.readCSV(path, cache=other), grown) and cu.readCSV.last_hit
+    assert same(cu.readCSV(path, cache=tmp_path / "no" / "such" / "dir" / "x.bin"), grown) and not cu.readCSV.last_hit
+    # a missing source reports what the plain reader reports
+    with pytest.raises(cu._lib.Cu2bError) as err:
+        cu.readCSV(tmp_path / "absent.csv", cache=True)
+    assert err.value.status == 2
+
+
+def test_shim_read_csv_uses_the_sidecar_when_asked(tmp_path):
+    """CU2B_CSV_CACHE=1 routes the shim's readCSV (what bin/mf calls) through the sidecar: same CSR either way."""
+    import os, subprocess
+    r = np.zeros(500, dtype=cu.RATING_DTYPE)
+    r["user"] = np.sort(np.arange(500) % 40)
+    r["item"] = (np.arange(500) * 7) % 60
+    r["rating"] = 1 + (np.arange(500) % 9) * 0.5
+    path = tmp_path / "r.csv"
+    cu.write_ratings_csv(path, r)
+    src = tmp_path / "t.cpp"
+    src.write_text("""#include "cu2rec_shim.h"
+#include <cstdio>
+int main(int argc, char **argv) { int rows, cols; float gb; auto v = readCSV(argv[1], &rows, &cols, &gb);
+  double s = 0; for (auto &x : v) s += x.rating * (x.userID + 1) + x.itemID;
+  printf("%zu %d %d %.9g %.9g\\n", v.size(), rows, cols, gb, s); return 0; }
+""")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "t"
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I" + os.path.join(root, "include"), "-I" + os.path.join(root, "cu2rec_b200", "csrc"),
+                    str(src), "-o", str(exe), "-L" + os.path.join(root, "cu2rec_b200", "lib"), "-lcu2b",
+                    "-Wl,-rpath," + os.path.join(root, "cu2rec_b200", "lib")], check=True)
+    plain = subprocess.run([str(exe), str(path)], check=True, capture_output=True, text=True).stdout
+    assert not os.path.exists(str(path) + ".cu2bcache")
+    env = dict(os.environ, CU2B_CSV_CACHE="1")
+    miss = subprocess.run([str(exe), str(path)], check=True, capture_output=True, text=True, env=env).stdout
+    assert os.path.exists(str(path) + ".cu2bcache")
+    hit = subprocess.run([str(exe), str(path)], check=True, capture_output=True, text=True, env=env).stdout
+    assert plain == miss == hit and plain.split()[0] == "500"
