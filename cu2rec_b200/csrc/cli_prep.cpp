@@ -8,13 +8,17 @@
 //   prep create_config <file> [-n iters] [-f factors] [-l lr] [-s seed] [-p p_reg] [-q q_reg]
 //                      [-u user_bias_reg] [-i item_bias_reg]                        (create_config.py)
 //   prep convert_to_np <matrix.csv> [...]            -> <matrix>.npy                (convert_to_np.py)
+//   prep dsgd_partition <train.csv> <n_gpus>         -> <train>_dsgd<G>_users.csv, <train>_dsgd<G>_items.csv
+//        (no reference counterpart: the block permutation multi-GPU training uses, cu2b_dsgd_partition)
 // Host only (no GPU needed).
 #include <getopt.h>
 
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "cu2b.h"
 
@@ -38,7 +42,8 @@ static int usage() {
             "       prep sort_ratings <ratings.csv>\n"
             "       prep split_to_test_train <ratings.csv> <test_ratio> [-s seed]\n"
             "       prep create_config <file> [-n N] [-f F] [-l LR] [-s SEED] [-p P] [-q Q] [-u UB] [-i IB]\n"
-            "       prep convert_to_np <matrix.csv> [...]\n");
+            "       prep convert_to_np <matrix.csv> [...]\n"
+            "       prep dsgd_partition <train.csv> <n_gpus>\n");
     return 2;
 }
 
@@ -110,6 +115,50 @@ int main(int argc, char **argv) {
             const std::string out = (has_ext ? in.substr(0, dot) : in) + ".npy";
             if (cu2b_prep_convert_to_np(in.c_str(), out.c_str(), nullptr, nullptr) != CU2B_OK) return fail();
         }
+        return 0;
+    }
+    if (cmd == "dsgd_partition") {
+        // The user / item block permutation of the DSGD trainer for this file and GPU count, as two CSVs with the
+        // 1-based ids of the ratings file: userId,block,local_index and itemId,block,row (row = position of the item
+        // in the renumbered catalogue; block b is the contiguous row range the trainer rotates as one unit).
+        if (argc < 4) return usage();
+        const int world = atoi(argv[3]);
+        cu2b_rating *r = nullptr;
+        int64_t n = 0;
+        int rows = 0, cols = 0;
+        float mean = 0.f;
+        if (cu2b_read_csv(argv[2], &r, &n, &rows, &cols, &mean) != CU2B_OK) return fail();
+        if (world < 1 || rows < 1 || cols < 1) {
+            cu2b_free(r);
+            fprintf(stderr, "prep: dsgd_partition needs n_gpus >= 1 and a non-empty ratings file\n");
+            return 1;
+        }
+        std::vector<int> ublock((size_t)rows), ulocal((size_t)rows), per_block((size_t)world), inew((size_t)cols), iptr((size_t)world + 1);
+        std::vector<int64_t> nnz((size_t)world * world);
+        const cu2b_status rc = cu2b_dsgd_partition(r, n, rows, cols, world, ublock.data(), ulocal.data(), per_block.data(), inew.data(),
+                                                   iptr.data(), nnz.data());
+        cu2b_free(r);
+        if (rc != CU2B_OK) return fail();
+        const std::string tag = "dsgd" + std::to_string(world);
+        const std::string uf = with_suffix(argv[2], (tag + "_users").c_str()), itf = with_suffix(argv[2], (tag + "_items").c_str());
+        FILE *f = fopen(uf.c_str(), "w");
+        if (!f) { fprintf(stderr, "prep: cannot write %s\n", uf.c_str()); return 1; }
+        fprintf(f, "userId,block,local_index\n");
+        for (int u = 0; u < rows; ++u) fprintf(f, "%d,%d,%d\n", u + 1, ublock[u], ulocal[u]);
+        fclose(f);
+        f = fopen(itf.c_str(), "w");
+        if (!f) { fprintf(stderr, "prep: cannot write %s\n", itf.c_str()); return 1; }
+        fprintf(f, "itemId,block,row\n");
+        for (int i = 0; i < cols; ++i) {
+            int b = 0;
+            while (b + 1 < world && inew[i] >= iptr[b + 1]) ++b;
+            fprintf(f, "%d,%d,%d\n", i + 1, b, inew[i]);
+        }
+        fclose(f);
+        int64_t lo = INT64_MAX, hi = 0;
+        for (int64_t v : nnz) { lo = v < lo ? v : lo; hi = v > hi ? v : hi; }
+        printf("%d x %d rating blocks, %lld ratings: smallest block %lld, largest %lld (x%.4f of the mean)\n", world, world, (long long)n,
+               (long long)lo, (long long)hi, n > 0 ? (double)hi * world * world / (double)n : 0.0);
         return 0;
     }
     return usage();
