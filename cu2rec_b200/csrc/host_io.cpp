@@ -1070,12 +1070,31 @@ cu2b_status cu2b_dsgd_partition_rows(const cu2b_rating *train, int64_t n, int ro
     if ((!train && n > 0) || rows < 0 || cols < 0 || world < 1 || !user_block || !user_local || !users_per_block ||
         !item_new || !item_block_ptr)
         return cu2b_fail(CU2B_ERR_INVALID, "cu2b_dsgd_partition: bad argument");
+    // degrees: per-thread histograms over contiguous slices of the ratings, summed in thread order (integers: exact)
     std::vector<int64_t> udeg(rows, 0), ideg(cols, 0);
-    for (int64_t t = 0; t < n; ++t) {
-        if (train[t].user < 0 || train[t].user >= rows || train[t].item < 0 || train[t].item >= cols)
-            return cu2b_fail(CU2B_ERR_INVALID, "cu2b_dsgd_partition: rating %ld out of range", (long)t);
-        udeg[train[t].user]++;
-        ideg[train[t].item]++;
+    {
+        const int nt = (size_t)n * sizeof(cu2b_rating) < cu2b_io_parallel_min_bytes() ? 1 : std::max(1, omp_get_max_threads());
+        std::vector<std::vector<int64_t>> ih((size_t)nt);
+        std::vector<int64_t> bad((size_t)nt, -1);
+#pragma omp parallel for num_threads(nt) schedule(static, 1)
+        for (int th = 0; th < nt; ++th) {
+            ih[th].assign((size_t)cols, 0);
+            const int64_t lo = n * th / nt, hi = n * (th + 1) / nt;
+            for (int64_t t = lo; t < hi; ++t) {
+                const int u = train[t].user, i = train[t].item;
+                if (u < 0 || u >= rows || i < 0 || i >= cols) { bad[th] = t; break; }
+                ih[th][i]++;
+                if (nt == 1) udeg[u]++;
+                else {
+#pragma omp atomic
+                    udeg[u]++;
+                }
+            }
+        }
+        for (int th = 0; th < nt; ++th)
+            if (bad[th] >= 0) return cu2b_fail(CU2B_ERR_INVALID, "cu2b_dsgd_partition: rating %ld out of range", (long)bad[th]);
+        for (int th = 0; th < nt; ++th)
+            for (int i = 0; i < cols; ++i) ideg[i] += ih[th][i];
     }
     std::vector<int> ub, ibk;
     lpt_assign(udeg, world, &ub);
@@ -1104,8 +1123,17 @@ cu2b_status cu2b_dsgd_partition_rows(const cu2b_rating *train, int64_t n, int ro
         }
     }
     if (block_nnz) {
-        for (int b = 0; b < world * world; ++b) block_nnz[b] = 0;
-        for (int64_t t = 0; t < n; ++t) block_nnz[(size_t)ub[train[t].user] * world + ibk[train[t].item]]++;
+        const int nt = (size_t)n * sizeof(cu2b_rating) < cu2b_io_parallel_min_bytes() ? 1 : std::max(1, omp_get_max_threads());
+        std::vector<std::vector<int64_t>> part((size_t)nt, std::vector<int64_t>((size_t)world * world, 0));
+#pragma omp parallel for num_threads(nt) schedule(static, 1)
+        for (int th = 0; th < nt; ++th) {
+            const int64_t lo = n * th / nt, hi = n * (th + 1) / nt;
+            for (int64_t t = lo; t < hi; ++t) part[th][(size_t)ub[train[t].user] * world + ibk[train[t].item]]++;
+        }
+        for (int b = 0; b < world * world; ++b) {
+            block_nnz[b] = 0;
+            for (int th = 0; th < nt; ++th) block_nnz[b] += part[th][b];
+        }
     }
     return CU2B_OK;
 }
@@ -1117,18 +1145,34 @@ extern "C" cu2b_status cu2b_dsgd_extract_strip(const cu2b_rating *ratings, int64
                                                cu2b_rating *out, int64_t *n_out) {
     if ((!ratings && n > 0) || !user_block || !user_local || !item_new || !n_out)
         return cu2b_fail(CU2B_ERR_INVALID, "cu2b_dsgd_extract_strip: bad argument");
-    int64_t w = 0;
     // input is grouped by ascending user and local ids ascend with the original ids inside a
-    // block, so a single filtered pass keeps the strip grouped by ascending local user
-    for (int64_t t = 0; t < n; ++t) {
-        const int u = ratings[t].user;
-        if (user_block[u] != rank) continue;
-        if (out) {
-            out[w].user = user_local[u];
-            out[w].item = item_new[ratings[t].item];
-            out[w].rating = ratings[t].rating;
+    // block, so a filtered pass keeps the strip grouped by ascending local user. Two phases over contiguous slices:
+    // count the strip's ratings per slice, then every thread writes its slice's part at its offset.
+    const int nt = (size_t)n * sizeof(cu2b_rating) < cu2b_io_parallel_min_bytes() ? 1 : std::max(1, omp_get_max_threads());
+    std::vector<int64_t> first((size_t)nt + 1, 0);
+#pragma omp parallel for num_threads(nt) schedule(static, 1)
+    for (int th = 0; th < nt; ++th) {
+        const int64_t lo = n * th / nt, hi = n * (th + 1) / nt;
+        int64_t c = 0;
+        for (int64_t t = lo; t < hi; ++t) c += user_block[ratings[t].user] == rank;
+        first[th + 1] = c;
+    }
+    for (int th = 0; th < nt; ++th) first[th + 1] += first[th];
+    const int64_t w = first[nt];
+    if (out) {
+#pragma omp parallel for num_threads(nt) schedule(static, 1)
+        for (int th = 0; th < nt; ++th) {
+            const int64_t lo = n * th / nt, hi = n * (th + 1) / nt;
+            int64_t at = first[th];
+            for (int64_t t = lo; t < hi; ++t) {
+                const int u = ratings[t].user;
+                if (user_block[u] != rank) continue;
+                out[at].user = user_local[u];
+                out[at].item = item_new[ratings[t].item];
+                out[at].rating = ratings[t].rating;
+                ++at;
+            }
         }
-        ++w;
     }
     *n_out = w;
     return CU2B_OK;

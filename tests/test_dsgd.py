@@ -428,3 +428,32 @@ def test_partition_places_one_popular_row_per_l2_block():
             assert np.all(np.diff(even) <= 0), "popular rows in popularity order on the even rows"
             assert np.all(np.diff(odd) <= 0)
             assert even.min() >= odd.max(), "every even row is at least as popular as every odd row"
+
+
+def test_partition_and_strips_are_the_same_serial_and_threaded(monkeypatch):
+    """cu2b_dsgd_partition / cu2b_dsgd_extract_strip cut large inputs into per-thread slices (per-thread histograms,
+    count-then-write): same partition, same block counts, same strips as the single-threaded pass, also when a slice
+    boundary falls inside a user's ratings and when an id is out of range."""
+    tr, _ = cu.synth_ratings(1500, 333, 60000, rank=4, noise=0.3, seed=8)
+    U, I = 1500, 333
+    outs = []
+    for min_bytes in ("0", str(1 << 40)):
+        monkeypatch.setenv("CU2B_IO_PARALLEL_MIN_BYTES", min_bytes)
+        for threads in (("3", "8") if min_bytes == "0" else ("1",)):
+            monkeypatch.setenv("OMP_NUM_THREADS", threads)
+            part = cu.dsgd_partition(tr, U, I, 4)
+            strips = [cu.dsgd_extract_strip(tr, part, r) for r in range(4)]
+            outs.append((part, strips))
+    ref_part, ref_strips = outs[-1]
+    assert sum(len(s) for s in ref_strips) == len(tr) and int(ref_part.block_nnz.sum()) == len(tr)
+    for part, strips in outs[:-1]:
+        for name in ("user_block", "user_local", "users_per_block", "item_new", "item_block_ptr", "block_nnz"):
+            assert np.array_equal(getattr(part, name), getattr(ref_part, name)), name
+        for a, b in zip(strips, ref_strips):
+            assert a.tobytes() == b.tobytes()
+    monkeypatch.setenv("CU2B_IO_PARALLEL_MIN_BYTES", "0")
+    bad = tr.copy()
+    bad["item"][41234] = I
+    with pytest.raises(cu._lib.Cu2bError) as err:
+        cu.dsgd_partition(bad, U, I, 4)
+    assert "41234" in str(err.value)
