@@ -19,4 +19,4 @@ for name, f, nbytes in (("h2d 1 stream", one, 2*n), ("h2d 2 streams", two, 2*n),
         torch.cuda.synchronize(); t = time.perf_counter(); f(); torch.cuda.synchronize(); dt = time.perf_counter() - t
     print(name, "%.1f GB/s" % (nbytes / dt / 1e9))
 import os; print("cpus", os.cpu_count())
-os.system("nvidia-smi topo -m | head -20; numactl -H 2>/dev/null | head -5; lscpu | grep -i 'numa\|model name\|^CPU(s)'")
+os.system(r"nvidia-smi topo -m | head -20; numactl -H 2>/dev/null | head -5; lscpu | grep -i 'numa\|model name\|^CPU(s)'")
