@@ -310,7 +310,7 @@ def run_reference_arm(args):
         return 0  # under torchrun only rank 0 measures the CPU reference
     k = args.k or WORKLOADS[args.workload][4]
     total = max(1, args.steps + args.warmup)
-    ref = CpuReference(args.workload, k, budget_s=min(12.0, 150.0 / total))
+    ref = CpuReference(args.workload, k, budget_s=min(12.0, args.cpu_budget, 150.0 / total))
     for _ in range(args.warmup):
         ref.run_once()
     ups, secs, rmse = 0, 0.0, None
