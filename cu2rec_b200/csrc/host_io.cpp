@@ -501,9 +501,10 @@ bool sidecar_load(const char *cache, const struct stat &src, cu2b_rating **out, 
 
 // Best effort: a sidecar that cannot be written (read-only directory, full disk) is not an error of the read.
 void sidecar_store(const char *cache, const struct stat &src, const cu2b_rating *r, int64_t n, int rows, int cols, float gb) {
-    std::string tmp = std::string(cache) + ".tmp." + std::to_string((long)getpid());
-    int fd = open(tmp.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    std::string tmp = std::string(cache) + ".tmp.XXXXXX";  // unique per writer: threads and processes may race for one sidecar
+    int fd = mkstemp(&tmp[0]);
     if (fd < 0) return;
+    fchmod(fd, 0644);
     SidecarHeader h;
     memcpy(h.magic, kSidecarMagic, 8);
     h.src_size = (uint64_t)src.st_size;
